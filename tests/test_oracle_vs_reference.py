@@ -1,0 +1,108 @@
+"""Pins the restated rollout oracle to the UNMODIFIED reference (loaded through import stubs).
+
+Runs only where /root/reference exists (the build container); the committed fixtures under
+tests/golden/ carry the same evidence to the GPU box."""
+import numpy as np
+import pytest
+
+from oracle import ref_loader as R
+from oracle import rollout_oracle as O
+
+pytestmark = [pytest.mark.reference,
+              pytest.mark.skipif(not R.available(), reason="reference tree not present")]
+
+
+def _rand_states(sys, B, seed, scale=None):
+    rng = np.random.default_rng(seed)
+    scale = np.ones(sys.n) * 2.0 if scale is None else np.asarray(scale)
+    return rng.uniform(-1, 1, size=(B, sys.n)) * scale
+
+
+CASES = {
+    "linear": (R.make_linear, None),
+    "cartpole": (R.make_cartpole, [3, 4, 3, 5]),
+    "acrobot": (R.make_acrobot, [4, 4, 6, 6]),
+    "quad2d": (R.make_quad2d, [2, 2, 4, 3, 3, 3]),
+    "quad10d": (R.make_quad10d, [2, 2, 2, 1.2, 1.2, 2, 2, 2, 2, 2]),
+}
+
+
+@pytest.mark.parametrize("kind", list(CASES))
+def test_f_g_and_step_match_reference(kind):
+    make, scale = CASES[kind]
+    dyn = make()
+    sys = O.std_system(kind)
+    xs = _rand_states(sys, 64, 1, scale)
+    rng = np.random.default_rng(2)
+    us = rng.uniform(-1.5, 1.5, size=(64, sys.m)) * np.maximum(np.abs(sys.umin), np.abs(sys.umax))
+    f, g = sys.f_g(xs)
+    xn = sys.step(xs, us, "euler")
+    for i in range(xs.shape[0]):
+        fr, gr = dyn.get_control_affine_matrix(xs[i].copy())
+        np.testing.assert_allclose(f[i], fr, rtol=1e-12, atol=1e-12)
+        np.testing.assert_allclose(g[i], np.asarray(gr).reshape(sys.n, sys.m), rtol=1e-12, atol=1e-12)
+        xr = dyn.simulate(xs[i].copy(), us[i].copy())
+        np.testing.assert_allclose(xn[i], xr, rtol=1e-12, atol=1e-12)
+        if kind != "acrobot":  # Acrobot.states_wrap only accepts (4,) (acrobot.py:73)
+            np.testing.assert_allclose(sys.wrap(xs[i:i + 1] * 3)[0], dyn.states_wrap(xs[i].copy() * 3), atol=1e-14)
+        else:
+            np.testing.assert_allclose(sys.wrap(xs[i:i + 1] * 3)[0], dyn.states_wrap(xs[i] * 3), atol=1e-14)
+
+
+def _ref_controller(kind, dyn):
+    if kind == "lqr":
+        return R.ref_import("controller.lqr").LQR(dyn, np.eye(2), np.eye(1))
+    if kind == "cartpole_es":
+        return R.CachedLqrTerm(R.ref_import("controller.cartpole_energy_shaping").CartpoleEnergyShapingController(dyn))
+    if kind == "acrobot_es":
+        return R.CachedLqrTerm(R.ref_import("controller.acrobot_energy_shaping").AcrobotEnergyShapingController(dyn))
+    mod = R.ref_import("controller.quadrotors_model_based_controller")
+    if kind == "quad2d_hover":
+        return mod.Quadrotors2DHoveringController(dyn, np.zeros(6), np.eye(6), np.eye(2))
+    if kind == "quad10d_hover":
+        return mod.NearHoverQuadcopterHoveringController(dyn, np.zeros(10), np.eye(10), np.eye(3))
+    raise ValueError(kind)
+
+
+CTL_CASES = [("linear", "lqr"), ("cartpole", "cartpole_es"), ("acrobot", "acrobot_es"),
+             ("quad2d", "quad2d_hover"), ("quad10d", "quad10d_hover")]
+
+
+@pytest.mark.parametrize("skind,ckind", CTL_CASES)
+def test_controller_matches_reference(skind, ckind):
+    make, scale = CASES[skind]
+    dyn = make()
+    sys = O.std_system(skind)
+    ctl = O.std_controller(ckind, sys)
+    rc = _ref_controller(ckind, dyn)
+    xs = _rand_states(sys, 256, 3, scale)
+    if ckind in ("cartpole_es", "acrobot_es"):  # make sure both branches are exercised
+        xf = np.array([0, np.pi, 0, 0]) if ckind == "cartpole_es" else np.array([np.pi, 0, 0, 0])
+        xs[:128] = xf + np.random.default_rng(4).uniform(-0.3, 0.3, size=(128, 4))
+    u = ctl.control(sys, xs)
+    for i in range(xs.shape[0]):
+        ur = np.atleast_1d(rc.get_control_efforts(xs[i].copy()))
+        np.testing.assert_allclose(u[i], ur, rtol=1e-10, atol=1e-10)
+    np.testing.assert_allclose(ctl.K, np.asarray(rc.K if ckind not in ("cartpole_es", "acrobot_es") else rc.K), rtol=1e-12)
+
+
+@pytest.mark.parametrize("skind,ckind,steps", [("linear", "lqr", 300), ("cartpole", "cartpole_es", 400),
+                                               ("acrobot", "acrobot_es", 120), ("quad2d", "quad2d_hover", 300),
+                                               ("quad10d", "quad10d_hover", 300)])
+def test_closed_loop_trajectory_matches_reference(skind, ckind, steps):
+    make, _ = CASES[skind]
+    dyn = make()
+    sys = O.std_system(skind)
+    ctl = O.std_controller(ckind, sys)
+    rc = _ref_controller(ckind, dyn)
+    if skind == "acrobot":
+        x0 = np.array([[0.001, 0, 0, 0], [0.05, -0.02, 0.1, 0.0]])  # acrobot_energy_shaping.py:131
+    else:
+        x0 = np.stack([dyn.get_initial_state() for _ in range(3)])
+    xs, us, xf, _ = O.rollout(sys, ctl, x0, steps, "euler", record_stride=1)
+    for e in range(x0.shape[0]):
+        xr, ur = R.reference_rollout(dyn, rc.get_control_efforts, x0[e], steps)
+        # chaotic systems amplify 1e-16 rounding differences (closed-form M^-1 vs np.linalg.inv)
+        tol = 1e-6 if skind == "acrobot" else 1e-9
+        np.testing.assert_allclose(xs[:, e], xr, rtol=tol, atol=tol)
+        np.testing.assert_allclose(us[:, e], ur, rtol=tol * 100, atol=tol * 100)
