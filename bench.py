@@ -1,0 +1,331 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the hot path (BASELINE.json): closed-loop env-steps/s of the batched rollout
+and HJB-residual states/s of the vhjb pass, on N B200s of one node.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload NAME]
+
+One "step" = one pass of the hot path over one batch of synthetic input (one rollout launch over all
+environments of this rank, or one vhjb residual+gradient+Adam step over this rank's sampled states).
+Rank 0 prints ONE JSON line.  N > 1: launched under torchrun, one rank per GPU; environments / states are sharded
+by rank (weak scaling: the per-GPU batch is fixed), no data-path collective for rollouts.
+
+``--impl reference`` times the reference's own arithmetic for the same workload on the host cores: the oracle port
+(oracle/rollout_oracle.py — NumPy float64, vectorised over environments; the reference itself is a Python
+package that cannot travel to the GPU box), one process per core, on a bounded sample of the workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import multiprocessing as mp
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+# ---------------------------------------------------------------------------------------------------------------
+# workloads.  flops = "FLOP model v1" per env-step; bytes = HBM bytes per env-step when recording.
+# ---------------------------------------------------------------------------------------------------------------
+ROLLOUTS = {
+    # name: system, controller, envs per GPU, horizon, flops/step (euler, rk4), config label
+    "quad2d_hover": dict(sys="quad2d", ctl="quad2d_hover", envs=1 << 24, T=1000, flops={"euler": 65, "rk4": 158},
+                         label="C4: 2-D drone hovering, quadrotors model-based controller, 16M envs x 1000 steps"),
+    "cartpole_lqr": dict(sys="cartpole", ctl="cartpole_lqr", envs=4096, T=500, flops={"euler": 50, "rk4": 151},
+                         label="C1: cartpole LQR balancing, 4096 initial states x 500 steps"),
+    "cartpole_lqr_big": dict(sys="cartpole", ctl="cartpole_lqr", envs=1 << 24, T=500, flops={"euler": 50, "rk4": 151},
+                             label="cartpole LQR balancing, 16M initial states x 500 steps"),
+    "acrobot_es": dict(sys="acrobot", ctl="acrobot_es", envs=1 << 22, T=2000, flops={"euler": 156, "rk4": 302},
+                       label="C3: acrobot energy-shaping swing-up, 4M envs x 2000 steps"),
+    "quad10d_hover": dict(sys="quad10d", ctl="quad10d_hover", envs=1 << 23, T=1000, flops={"euler": 124, "rk4": 258},
+                          label="10-D quadcopter hover LQR, 8M envs x 1000 steps"),
+}
+DEFAULT_WORKLOAD = "quad2d_hover"
+
+
+def synthetic_x0_host(sysname, count, seed):
+    """Synthetic initial states: the system's own x0 distribution, fp32."""
+    rng = np.random.default_rng(seed)
+    spec = {"quad2d": ([0] * 6, [1] * 6), "cartpole": ([0, 3.14, 0, 0], [2.4, 0.05, 1, 0.05]),
+            "acrobot": ([0] * 4, [0.1] * 4), "quad10d": ([0] * 10, [1, 1, 1, .5, .5, 1, 1, 1, .5, .5]),
+            "linear": ([0, 0], [1, 1])}[sysname]
+    mean, std = np.float32(spec[0]), np.float32(spec[1])
+    return (rng.uniform(-1, 1, size=(count, len(mean))).astype(np.float32) * std + mean).astype(np.float32)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# CPU side: the oracle port on host cores (cpu_baseline and --impl reference)
+# ---------------------------------------------------------------------------------------------------------------
+def _cpu_rollout_worker(args):
+    sysname, ctlname, envs, T, integ, seed = args
+    os.environ.setdefault("OMP_NUM_THREADS", "1")
+    from oracle import rollout_oracle as O
+    osys = O.std_system(sysname)
+    octl = O.std_controller(ctlname, osys)
+    ocost = O.OracleCost(np.eye(osys.n), np.eye(osys.m), octl.xf if octl.xf is not None else np.zeros(osys.n),
+                         octl.uf if octl.uf is not None else np.zeros(osys.m))
+    x0 = synthetic_x0_host(sysname, envs, seed).astype(np.float64)
+    t0 = time.perf_counter()
+    O.rollout(osys, octl, x0, T, integ, record_stride=0, cost=ocost)
+    return time.perf_counter() - t0
+
+
+def cpu_rollout_throughput(w, integ, cores, envs_per_core, T):
+    """env-steps/s of the oracle port with one process per core (each integrates envs_per_core x T)."""
+    ctx = mp.get_context("spawn")
+    jobs = [(w["sys"], w["ctl"], envs_per_core, T, integ, 99 + i) for i in range(cores)]
+    t0 = time.perf_counter()
+    with ctx.Pool(cores) as pool:
+        pool.map(_cpu_rollout_worker, jobs)
+    wall = time.perf_counter() - t0
+    return cores * envs_per_core * T / wall, wall
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# clocks
+# ---------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.gpu), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.12)
+        self.proc.terminate()
+        sm, smax, reasons = [], None, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); smax = float(r[2])
+            except (ValueError, IndexError):
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        # "under load" = samples in the upper half of the observed range (idle samples bracket the timed region)
+        load = [v for v in sm if v >= 0.5 * max(sm)] if sm else []
+        return {"sm_mhz": float(np.median(load)) if load else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------------------------
+def dist_setup(n_gpus):
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return rank, world, local
+
+
+def run_reference_arm(args, w, integ, rank, world):
+    """The reference's arithmetic on the host cores (oracle port; see module docstring).  Rank 0 only."""
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    T = w["T"]
+    # bounded sample: size one step at ~2 s of CPU work per core (vectorised NumPy runs ~2-5e6 env-steps/s/core)
+    envs_per_core = max(256, min(w["envs"] // cores, int(6e6 // T)))
+    vals = []
+    for _ in range(args.warmup):
+        cpu_rollout_throughput(w, integ, cores, max(64, envs_per_core // 8), T)
+    t_all = 0.0
+    for _ in range(args.steps):
+        v, wall = cpu_rollout_throughput(w, integ, cores, envs_per_core, T)
+        vals.append(v); t_all += wall
+    value = float(np.mean(vals))
+    sample = f"{cores} procs x {envs_per_core} envs x {T} {integ} steps per bench step (oracle/rollout_oracle.py, NumPy fp64)"
+    line = {
+        "impl": "reference", "metric": "closed-loop env-steps/s", "value": value, "unit": "env-steps/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_all / max(1, args.steps),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": w["label"], "integrator": integ, "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "env-steps/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_rollout(args, w, integ):
+    rank, world, local = dist_setup(args.gpus)
+    if args.impl == "reference":
+        run_reference_arm(args, w, integ, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the product path is CUDA-only)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    from tests.helpers import make_controller, make_dynamics
+    from q_learning_with_hjb_b200 import _lib as L
+    from q_learning_with_hjb_b200.rollout import BatchedRollout, RunningCost
+
+    envs = args.envs or w["envs"]
+    T = args.horizon or w["T"]
+    dyn = make_dynamics(w["sys"])
+    dyn.fast_trig = not args.accurate_trig
+    ctl = make_controller(w["ctl"], dyn)
+    n, m = dyn.get_dimension()
+    cost = RunningCost(np.eye(n), np.eye(m), getattr(ctl, "xf", np.zeros(n)), getattr(ctl, "uf", np.zeros(m)))
+    plan = BatchedRollout(dyn, ctl, envs, T, integrator=integ, record_stride=args.record_stride, cost=cost)
+
+    # synthetic inputs: seed = 1234 + rank, generated on the host once, resident in HBM for `value`
+    x0_host = synthetic_x0_host(w["sys"], envs, 1234 + rank)
+    x0_dev = torch.as_tensor(x0_host).cuda()
+    pinned = plan.pinned_x0()
+    pinned.copy_(torch.as_tensor(x0_host))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- FP32 FMA peak probe (roofline denominator for the CUDA-core bound) ----
+    sink = torch.empty(148 * 8 * 256 * 2, device="cuda", dtype=torch.float32)
+    import ctypes as C
+    flops = C.c_double(0)
+    for _ in range(2):
+        L.check(L.lib().hjb_fma_peak_probe(L.ptr(sink), sink.numel(), 20000, C.byref(flops), L.stream_ptr()))
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    L.check(L.lib().hjb_fma_peak_probe(L.ptr(sink), sink.numel(), 20000, C.byref(flops), L.stream_ptr()))
+    e1.record(); torch.cuda.synchronize()
+    fma_peak_tflops = flops.value / (e0.elapsed_time(e1) * 1e-3) / 1e12
+
+    # ---- device-resident timing (`value`) ----
+    for _ in range(max(args.warmup, 3)):
+        plan.launch(x0_dev)
+    barrier()
+    clocks = ClockSampler(local); clocks.start()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    t_begin = torch.cuda.Event(enable_timing=True); t_end = torch.cuda.Event(enable_timing=True)
+    t_begin.record()
+    for a, b in evs:
+        a.record(); plan.launch(x0_dev); b.record()
+    t_end.record()
+    barrier()
+    clk = clocks.stop()
+    total_ms = t_begin.elapsed_time(t_end)
+    kernel_ms = float(np.mean([a.elapsed_time(b) for a, b in evs]))
+
+    # ---- end to end through the public API with HOST buffers (`e2e`) ----
+    for _ in range(2):
+        plan.run_host(pinned, copy_in=False)
+    barrier()
+    t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for _ in range(args.steps):
+        xf_host, cost_host = plan.run_host(pinned, copy_in=False)
+    t1.record()
+    barrier()
+    e2e_ms = t0.elapsed_time(t1)
+    checksum = float(cost_host.double().mean())
+
+    times = torch.tensor([total_ms, e2e_ms], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+    total_ms, e2e_ms = times.tolist()
+    units = float(envs) * T * args.steps * world
+    value = units / (total_ms * 1e-3)
+    e2e_value = units / (e2e_ms * 1e-3)
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except OSError:
+            pass
+        fpe = w["flops"][integ if integ in w["flops"] else "euler"]
+        per_gpu = float(envs) * T / (kernel_ms * 1e-3)
+        achieved = per_gpu * fpe / 1e12
+        sm_max = clk.get("sm_max_mhz") or peaks.get("sm_max_mhz") or 1965.0
+        nominal = 148 * 128 * 2 * sm_max * 1e6 / 1e12
+        rec_bytes = 0.0
+        if args.record_stride > 0:
+            rec_bytes = (n + m) * 4.0 / args.record_stride
+        hbm_peak = peaks.get("hbm_gbs", 6650.0)
+        roof = {"bound": "fp32", "achieved": achieved, "peak": fma_peak_tflops, "unit": "TFLOP/s",
+                "frac": achieved / fma_peak_tflops, "traffic": None,
+                "peak_source": "measured: hjb_fma_peak_probe FFMA-only kernel in this run (FP32 CUDA-core peak is not "
+                               "in MEASURED_PEAKS.json)",
+                "peak_nominal": nominal, "frac_of_nominal": achieved / nominal,
+                "flops_per_env_step": fpe, "flop_model": "SURVEY.md 8d v1",
+                "hbm": {"achieved_gbs": per_gpu * (rec_bytes + 0.0) / 1e9 + (envs * (2 * n + 1) * 4 / (kernel_ms * 1e-3)) / 1e9,
+                        "peak_gbs": hbm_peak, "peak_source": "MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback"}}
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            cores = os.cpu_count() or 1
+            epc = max(256, int(4e6 // T))
+            v, wall = cpu_rollout_throughput(w, integ, cores, epc, T)
+            cpu = {"value": v, "unit": "env-steps/s", "cores": cores, "kind": "port",
+                   "sample": f"{cores} procs x {epc} envs x {T} {integ} steps, oracle/rollout_oracle.py NumPy fp64, {wall:.1f} s"}
+        line = {
+            "metric": "closed-loop env-steps/s", "value": value, "unit": "env-steps/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": w["label"], "envs_per_gpu": envs, "horizon": T, "integrator": integ,
+                       "record": "final state + per-env cost" if args.record_stride == 0 else f"every {args.record_stride} steps",
+                       "trig": "accurate" if args.accurate_trig else "mufu", "parallelism": f"env-shard x{world}",
+                       "l2": "inputs larger than L2 (x0 >= 400 MB per launch)" if envs * n * 4 > 126e6 else "small workload",
+                       "seed": "1234 + rank"},
+            "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": plan.h2d_bytes(),
+                    "d2h_bytes_per_step": plan.d2h_bytes(), "ms_per_step": e2e_ms / args.steps, "checksum_mean_cost": checksum},
+            "gpu_launches": args.steps,
+            "kernel_ms": kernel_ms,
+            "roofline": roof, "cpu_baseline": cpu, "clocks": clk,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default=DEFAULT_WORKLOAD)
+    ap.add_argument("--integrator", default="euler", choices=["euler", "rk4"])
+    ap.add_argument("--envs", type=int, default=0, help="environments per GPU (default: the workload's)")
+    ap.add_argument("--horizon", type=int, default=0)
+    ap.add_argument("--record-stride", type=int, default=0)
+    ap.add_argument("--accurate-trig", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.workload in ROLLOUTS:
+        run_rollout(args, ROLLOUTS[args.workload], args.integrator)
+    else:
+        raise SystemExit(f"unknown workload {args.workload}; choose from {sorted(ROLLOUTS)}")
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,161 @@
+/*
+ * hjb_b200.h — C ABI of libhjb_b200.so: the B200 (sm_100a) implementation of the data-parallel hot path of
+ * HaoxiangYou/Q_Learning_with_HJB.
+ *
+ * The reference has no FFI layer: its boundary is the Python class interface (Dynamics / Controller /
+ * VHJBController).  Each entry point below cites the reference method(s) whose per-environment /
+ * per-sample Python loop it replaces (paths under the reference root).  The Python classes in
+ * q_learning_with_hjb_b200/{dynamics,controller} bind these symbols with ctypes.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every array pointer is a DEVICE pointer (fp32 unless stated) owned by
+ *     the caller; the library allocates nothing persistent;
+ *   - `stream` is a cudaStream_t passed as void*; all work is stream-ordered, no hidden synchronisation;
+ *   - parameter structs are HOST pointers, read during the call (they are copied into the kernel's
+ *     parameter space), so they may be freed right after the call returns;
+ *   - return value: 0 on success, a negative hjb_status on a usage error, a positive cudaError_t on a CUDA
+ *     failure; nothing throws across the ABI.  hjb_status_string() renders either;
+ *   - trajectories are TIME-MAJOR: xs[t][env][i].  One thread integrates one environment, so a warp's 32
+ *     states of one time step are contiguous and every store is coalesced; the reference's per-environment
+ *     view xs_env[t, i] is the strided slice xs[:, env, :] (the Python layer returns it as a zero-copy
+ *     permute).
+ */
+#ifndef HJB_B200_H
+#define HJB_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HJB_ABI_VERSION 1
+#define HJB_MAX_N 10 /* largest state dimension (NearHoverQuadcopter) */
+#define HJB_MAX_M 3  /* largest control dimension */
+
+typedef enum hjb_status {
+  HJB_OK = 0,
+  HJB_ERR_BAD_ARG = -1,      /* null pointer / negative size / inconsistent dims */
+  HJB_ERR_UNSUPPORTED = -2,  /* (system, controller, integrator, n, m) combination has no kernel */
+  HJB_ERR_NO_DEVICE = -3     /* no sm_100 device visible */
+} hjb_status;
+
+/* ---- systems: x' = f(x) + g(x) u ----------------------------------------------------------------- */
+typedef enum hjb_system_kind {
+  HJB_SYS_LINEAR = 0,   /* dynamics/linear.py:7-22          f = A x, g = B; n in {2,4}, m in {1,2}        */
+  HJB_SYS_CARTPOLE = 1, /* dynamics/cartpole.py:19-64       x = [p, th, dp, dth], wraps th               */
+  HJB_SYS_ACROBOT = 2,  /* dynamics/acrobot.py:39-81        x = [q1, q2, dq1, dq2], wraps q1, q2          */
+  HJB_SYS_QUAD2D = 3,   /* dynamics/quadrotors.py:17-70     x = [x, y, th, dx, dy, dth], wraps th        */
+  HJB_SYS_QUAD10D = 4   /* dynamics/quadrotors.py:118-170   10-D near-hover quadcopter, wraps x[3], x[4]  */
+} hjb_system_kind;
+
+/* Physical parameters, in the order the reference's config dataclasses / module dict name them:
+ *   CARTPOLE par = {mc, mp, l, g}                    (configs/dynamics/dynamics_config.py:35-43)
+ *   ACROBOT  par = {l1, l2, m1, m2, I1, I2, g}       (dynamics/acrobot.py:8-16)
+ *   QUAD2D   par = {g, m, r, I}                      (configs/dynamics/dynamics_config.py:45-51)
+ *   QUAD10D  par = {g, m, kT, n0}                    (configs/dynamics/dynamics_config.py:53-59)
+ *   LINEAR   A (n x n, row-major), B (n x m, row-major); par unused                                  */
+typedef struct hjb_system {
+  int32_t kind; /* hjb_system_kind */
+  int32_t n, m;
+  float dt;
+  float umin[HJB_MAX_M], umax[HJB_MAX_M]; /* Dynamics.simulate clips u to these (dynamics_basic.py:118) */
+  float par[8];
+  float A[16], B[8];
+} hjb_system;
+
+/* ---- controllers ---------------------------------------------------------------------------------- */
+typedef enum hjb_control_kind {
+  /* u = -K wrap(x - xf) + uf, clipped to [umin, umax] iff `clip`:
+   *   controller/lqr.py:29-30 (xf = 0, uf = 0, clip), examples/cartpole_balancing.ipynb cell 4:24-25 (no clip),
+   *   controller/quadrotors_model_based_controller.py:36-38 and :73-75 (clip)                         */
+  HJB_CTL_FEEDBACK = 0,
+  /* controller/cartpole_energy_shaping.py:65-110; K = LQR gain about xf = [0, pi, 0, 0],
+   * aux = {Ke0, Ke1, Ke2, eps_energy, eps_state}                                                       */
+  HJB_CTL_CARTPOLE_ES = 1,
+  /* controller/acrobot_energy_shaping.py:74-121; K, P = LQR gain / cost-to-go about xf = [pi, 0, 0, 0],
+   * aux = {Ks0, Ks1, Ks2, eps}                                                                          */
+  HJB_CTL_ACROBOT_ES = 2
+} hjb_control_kind;
+
+typedef struct hjb_control {
+  int32_t kind; /* hjb_control_kind */
+  int32_t clip; /* FEEDBACK only */
+  float K[HJB_MAX_M * HJB_MAX_N]; /* m x n, row-major */
+  float P[16];                    /* ACROBOT_ES: 4 x 4 row-major */
+  float xf[HJB_MAX_N], uf[HJB_MAX_M];
+  float aux[8];
+} hjb_control;
+
+/* ---- running cost l(x,u) = dx^T Q dx + (u-uf)^T R (u-uf), dx = wrap(x - xf) -----------------------
+ * controller/vhjb.py:162-165 (same form in every notebook).  `u` is the controller output as returned,
+ * i.e. BEFORE Dynamics.simulate clips it (examples/cartpole_balancing.ipynb cell 15:33-35).            */
+typedef struct hjb_cost {
+  float Q[HJB_MAX_N * HJB_MAX_N]; /* n x n row-major */
+  float R[HJB_MAX_M * HJB_MAX_M]; /* m x m row-major */
+  float xf[HJB_MAX_N], uf[HJB_MAX_M];
+} hjb_cost;
+
+typedef enum hjb_integrator {
+  HJB_INT_EULER = 0,   /* the reference's integrator (dynamics_basic.py:120)                              */
+  HJB_INT_RK4 = 1,     /* classical RK4 of the same xdot, u held over the step, one wrap after the step  */
+  HJB_INT_DISCRETE = 2 /* LINEAR only: x <- A x + B u with A, B already discretised (exact ZOH,
+                          examples/double_integrator_optimal_time.ipynb cell 4)                           */
+} hjb_integrator;
+
+typedef struct hjb_rollout_opts {
+  int32_t integrator;    /* hjb_integrator */
+  int32_t record_stride; /* 0: no trajectory output; s > 0: record x after every s-th step (and x0)      */
+  int32_t fast_trig;     /* 1: MUFU sin/cos/rcp (__sinf ...), 0: IEEE-accurate libdevice versions        */
+  int32_t box_enabled;   /* freeze an environment once wrap(x - box_xf) leaves [box_lo, box_hi]
+                            (controller/vhjb.py:176-181; examples/drone_hovering.ipynb cell 15:27)        */
+  float box_xf[HJB_MAX_N], box_lo[HJB_MAX_N], box_hi[HJB_MAX_N];
+} hjb_rollout_opts;
+
+/*
+ * Batched closed-loop rollout — replaces the per-environment loop
+ *     for t in range(T): u = controller.get_control_efforts(x); x = dynamics.simulate(x, u)
+ * (scripts/test_vhjb_policy.py:146-151, controller/cartpole_energy_shaping.py:123-125,
+ *  controller/acrobot_energy_shaping.py:133-135, controller/quadrotors_model_based_controller.py:310-312,
+ *  examples notebooks' test_learned_policy) for N environments in ONE launch.
+ *
+ *   x0       [N, n]                 initial states
+ *   xs       [T/s + 1, N, n] | null recorded states, time-major (s = record_stride); xs[0] = x0
+ *   us       [T/s, N, m]     | null controller outputs at steps 0, s, 2s, ...
+ *   x_final  [N, n]          | null state after the last step
+ *   cost     [N]             | null sum_t l(x_t, u_t) * dt  (requires `cost_spec`)
+ *   steps    [N] int32       | null number of steps actually integrated (< T only with box_enabled)
+ */
+int hjb_rollout(const hjb_system* sys, const hjb_control* ctl, const hjb_cost* cost_spec,
+                const hjb_rollout_opts* opts, const float* x0, int64_t N, int32_t T, float* xs, float* us,
+                float* x_final, float* cost, int32_t* steps, void* stream);
+
+/*
+ * Batched single-step pieces of the same path, for per-step use and per-step parity checks:
+ *   f [B, n], g [B, n, m]  Dynamics.get_control_affine_matrix (dynamics_basic.py:64-94 and overrides)
+ *   xdot [B, n]            Dynamics.dynamics_step             (dynamics_basic.py:96-105), needs u
+ *   x_next [B, n]          Dynamics.simulate                  (dynamics_basic.py:107-122), needs u
+ * Any output may be null; u [B, m] may be null if only f / g are requested.
+ */
+int hjb_dynamics(const hjb_system* sys, int32_t integrator, int32_t fast_trig, const float* x, const float* u,
+                 int64_t B, float* f, float* g, float* xdot, float* x_next, void* stream);
+
+/* Batched Controller.get_control_efforts (controller/controller_basic.py:4-5 and subclasses): x [B, n] -> u [B, m]. */
+int hjb_control_efforts(const hjb_system* sys, const hjb_control* ctl, int32_t fast_trig, const float* x, int64_t B,
+                        float* u, void* stream);
+
+/* Batched Dynamics.states_wrap (cartpole.py:52-64, acrobot.py:72-81, quadrotors.py:48-70,151-170), in place. */
+int hjb_states_wrap(const hjb_system* sys, float* x, int64_t B, void* stream);
+
+/* ---- misc ------------------------------------------------------------------------------------------ */
+int hjb_abi_version(void);
+const char* hjb_status_string(int status);
+/* FP32 FMA micro-benchmark used as the CUDA-core roofline denominator: runs `iters` dependent FMAs on 8
+ * independent chains per thread over a full-chip grid and writes one float per thread to `sink` (>= grid*block
+ * floats).  Returns the number of FLOPs executed through *flops. */
+int hjb_fma_peak_probe(float* sink, int64_t sink_len, int32_t iters, double* flops, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HJB_B200_H */

@@ -1,0 +1,228 @@
+// extern "C" entry points of libhjb_b200.so (see include/hjb_b200.h): argument checking, folding of the
+// public parameter structs into the device parameter blocks (derived constants in double precision), and
+// dispatch to the kernel instantiations.
+#include <cmath>
+#include <cstring>
+
+#include "rollout_kernel.cuh"
+#include "step_kernels.cuh"
+
+namespace hjb {
+
+static bool dims_ok(const hjb_system* s) {
+  switch (s->kind) {
+    case HJB_SYS_LINEAR: return (s->n == 2 && s->m == 1) || (s->n == 4 && (s->m == 1 || s->m == 2));
+    case HJB_SYS_CARTPOLE: return s->n == 4 && s->m == 1;
+    case HJB_SYS_ACROBOT: return s->n == 4 && s->m == 1;
+    case HJB_SYS_QUAD2D: return s->n == 6 && s->m == 2;
+    case HJB_SYS_QUAD10D: return s->n == 10 && s->m == 3;
+    default: return false;
+  }
+}
+
+static void make_dev_sys(const hjb_system* s, DevSys& d) {
+  std::memset(&d, 0, sizeof(d));
+  d.n = s->n;
+  d.m = s->m;
+  d.dt = s->dt;
+  for (int k = 0; k < HJB_MAX_M; ++k) { d.umin[k] = s->umin[k]; d.umax[k] = s->umax[k]; }
+  const float* p = s->par;
+  switch (s->kind) {
+    case HJB_SYS_LINEAR:
+      std::memcpy(d.A, s->A, sizeof(d.A));
+      std::memcpy(d.B, s->B, sizeof(d.B));
+      break;
+    case HJB_SYS_CARTPOLE: {  // par = {mc, mp, l, g}
+      const double mc = p[0], mp = p[1], l = p[2], g = p[3];
+      d.c[0] = (float)(mc + mp);
+      d.c[1] = (float)(mp * l);
+      d.c[2] = (float)(mp * l * l);
+      d.c[3] = (float)(mp * g * l);
+      d.c[4] = (float)((mc + mp) * (mp * l * l));
+      d.c[5] = (float)(1.0 / l);
+      d.c[6] = (float)(g / l);
+      break;
+    }
+    case HJB_SYS_ACROBOT: {  // par = {l1, l2, m1, m2, I1, I2, g}
+      const double l1 = p[0], l2 = p[1], m1 = p[2], m2 = p[3], I1 = p[4], I2 = p[5], g = p[6];
+      d.c[0] = (float)(I1 + I2 + m2 * l1 * l1);
+      d.c[1] = (float)(m2 * l1 * l2 / 2);
+      d.c[2] = (float)I2;
+      d.c[3] = (float)((m1 * l1 / 2 + m2 * l1) * g);
+      d.c[4] = (float)(m2 * g * l2 / 2);
+      break;
+    }
+    case HJB_SYS_QUAD2D: {  // par = {g, m, r, I}
+      d.c[0] = p[0];
+      d.c[1] = (float)(1.0 / (double)p[1]);
+      d.c[2] = (float)((double)p[2] / (double)p[3]);
+      break;
+    }
+    case HJB_SYS_QUAD10D: {  // par = {g, m, kT, n0}
+      d.c[0] = p[0];
+      d.c[1] = (float)((double)p[2] / (double)p[1]);
+      d.c[2] = p[3];
+      break;
+    }
+  }
+}
+
+static void make_dev_ctl(const hjb_system* s, const hjb_control* c, DevCtl& d) {
+  std::memset(&d, 0, sizeof(d));
+  d.clip = c->clip;
+  std::memcpy(d.K, c->K, sizeof(d.K));
+  std::memcpy(d.P, c->P, sizeof(d.P));
+  std::memcpy(d.xf, c->xf, sizeof(d.xf));
+  std::memcpy(d.uf, c->uf, sizeof(d.uf));
+  std::memcpy(d.aux, c->aux, sizeof(d.aux));
+  if (c->kind == HJB_CTL_CARTPOLE_ES) {
+    // aux in = {Ke0, Ke1, Ke2, eps_energy, eps_state}; E(xf) = 0.5 dth_f^2 - cos(th_f)
+    d.aux[4] = c->aux[4] * c->aux[4];
+    d.aux[5] = (float)(0.5 * (double)c->xf[3] * (double)c->xf[3] - std::cos((double)c->xf[1]));
+  } else if (c->kind == HJB_CTL_ACROBOT_ES) {
+    // aux in = {Ks0, Ks1, Ks2, eps}; E(xf) per dynamics/acrobot.py:60-70 in double
+    const float* p = s->par;
+    const double l1 = p[0], l2 = p[1], m1 = p[2], m2 = p[3], I1 = p[4], I2 = p[5], g = p[6];
+    const double q1 = c->xf[0], q2 = c->xf[1], dq1 = c->xf[2], dq2 = c->xf[3];
+    const double a = m2 * l1 * l2 / 2, c1 = std::cos(q1), c2 = std::cos(q2);
+    const double T1 = 0.5 * I1 * dq1 * dq1;
+    const double T2 = 0.5 * (m2 * l1 * l1 + I2 + 2 * a * c2) * dq1 * dq1 + 0.5 * I2 * dq2 * dq2 + (I2 + a * c2) * dq1 * dq2;
+    const double U = -m1 * g * l1 / 2 * c1 - m2 * g * (l1 * c1 + l2 / 2 * std::cos(q1 + q2));
+    d.aux[4] = (float)(T1 + T2 + U);
+  }
+}
+
+static int cost_mode(const hjb_system* s, const hjb_cost* c) {
+  if (!c) return COST_NONE;
+  for (int i = 0; i < s->n; ++i)
+    for (int j = 0; j < s->n; ++j)
+      if (i != j && c->Q[i * s->n + j] != 0.f) return COST_DENSE;
+  for (int i = 0; i < s->m; ++i)
+    for (int j = 0; j < s->m; ++j)
+      if (i != j && c->R[i * s->m + j] != 0.f) return COST_DENSE;
+  return COST_DIAG;
+}
+
+static int to_status(cudaError_t e) { return e == cudaSuccess ? HJB_OK : (e == cudaErrorNotSupported ? HJB_ERR_UNSUPPORTED : (int)e); }
+
+}  // namespace hjb
+
+using namespace hjb;
+
+extern "C" {
+
+int hjb_abi_version(void) { return HJB_ABI_VERSION; }
+
+const char* hjb_status_string(int status) {
+  switch (status) {
+    case HJB_OK: return "ok";
+    case HJB_ERR_BAD_ARG: return "hjb: bad argument";
+    case HJB_ERR_UNSUPPORTED: return "hjb: unsupported (system, controller, integrator, n, m) combination";
+    case HJB_ERR_NO_DEVICE: return "hjb: no CUDA device";
+    default: return status > 0 ? cudaGetErrorString((cudaError_t)status) : "hjb: unknown status";
+  }
+}
+
+int hjb_rollout(const hjb_system* sys, const hjb_control* ctl, const hjb_cost* cost_spec, const hjb_rollout_opts* opts,
+                const float* x0, int64_t N, int32_t T, float* xs, float* us, float* x_final, float* cost,
+                int32_t* steps, void* stream) {
+  if (!sys || !ctl || !opts || N < 0 || T < 0) return HJB_ERR_BAD_ARG;
+  if (!dims_ok(sys)) return HJB_ERR_UNSUPPORTED;
+  if (N == 0) return HJB_OK;
+  if (!x0) return HJB_ERR_BAD_ARG;
+  if (cost && !cost_spec) return HJB_ERR_BAD_ARG;
+  if ((xs || us) && opts->record_stride <= 0) return HJB_ERR_BAD_ARG;
+
+  RolloutArgs a;
+  std::memset(&a, 0, sizeof(a));
+  make_dev_sys(sys, a.sys);
+  make_dev_ctl(sys, ctl, a.ctl);
+  if (cost_spec) {
+    std::memcpy(a.cost.Q, cost_spec->Q, sizeof(a.cost.Q));
+    std::memcpy(a.cost.R, cost_spec->R, sizeof(a.cost.R));
+    std::memcpy(a.cost.xf, cost_spec->xf, sizeof(a.cost.xf));
+    std::memcpy(a.cost.uf, cost_spec->uf, sizeof(a.cost.uf));
+  }
+  if (opts->box_enabled) {
+    std::memcpy(a.box.xf, opts->box_xf, sizeof(a.box.xf));
+    std::memcpy(a.box.lo, opts->box_lo, sizeof(a.box.lo));
+    std::memcpy(a.box.hi, opts->box_hi, sizeof(a.box.hi));
+  }
+  a.x0 = x0; a.xs = xs; a.us = us; a.x_final = x_final; a.cost_out = cost; a.steps_out = steps;
+  a.N = N; a.T = T;
+  a.stride = opts->record_stride > 0 ? opts->record_stride : 1;
+  a.n_rec = T / a.stride;
+
+  RolloutVariant v;
+  v.integrator = opts->integrator;
+  v.rec = (xs || us);
+  v.cost = cost ? cost_mode(sys, cost_spec) : COST_NONE;
+  v.box = opts->box_enabled != 0;
+  const bool fast = opts->fast_trig != 0;
+  cudaStream_t st = (cudaStream_t)stream;
+
+  cudaError_t e = cudaErrorNotSupported;
+  switch (sys->kind) {
+    case HJB_SYS_LINEAR:
+      if (ctl->kind != HJB_CTL_FEEDBACK) break;
+      if (sys->n == 2 && sys->m == 1) e = rollout_linear21_fb(a, v, fast, st);
+      else if (sys->n == 4 && sys->m == 1) e = rollout_linear41_fb(a, v, fast, st);
+      else if (sys->n == 4 && sys->m == 2) e = rollout_linear42_fb(a, v, fast, st);
+      break;
+    case HJB_SYS_CARTPOLE:
+      if (ctl->kind == HJB_CTL_FEEDBACK) e = rollout_cartpole_fb(a, v, fast, st);
+      else if (ctl->kind == HJB_CTL_CARTPOLE_ES) e = rollout_cartpole_es(a, v, fast, st);
+      break;
+    case HJB_SYS_ACROBOT:
+      if (ctl->kind == HJB_CTL_FEEDBACK) e = rollout_acrobot_fb(a, v, fast, st);
+      else if (ctl->kind == HJB_CTL_ACROBOT_ES) e = rollout_acrobot_es(a, v, fast, st);
+      break;
+    case HJB_SYS_QUAD2D:
+      if (ctl->kind == HJB_CTL_FEEDBACK) e = rollout_quad2d_fb(a, v, fast, st);
+      break;
+    case HJB_SYS_QUAD10D:
+      if (ctl->kind == HJB_CTL_FEEDBACK) e = rollout_quad10d_fb(a, v, fast, st);
+      break;
+  }
+  return to_status(e);
+}
+
+int hjb_dynamics(const hjb_system* sys, int32_t integrator, int32_t fast_trig, const float* x, const float* u, int64_t B,
+                 float* f, float* g, float* xdot, float* x_next, void* stream) {
+  if (!sys || B < 0) return HJB_ERR_BAD_ARG;
+  if (!dims_ok(sys)) return HJB_ERR_UNSUPPORTED;
+  if (B == 0) return HJB_OK;
+  if (!x || ((xdot || x_next) && !u)) return HJB_ERR_BAD_ARG;
+  DynArgs a;
+  make_dev_sys(sys, a.sys);
+  a.x = x; a.u = u; a.f = f; a.g = g; a.xdot = xdot; a.x_next = x_next; a.B = B;
+  return to_status(step_dynamics(sys->kind, a, integrator, fast_trig != 0, (cudaStream_t)stream));
+}
+
+int hjb_control_efforts(const hjb_system* sys, const hjb_control* ctl, int32_t fast_trig, const float* x, int64_t B,
+                        float* u, void* stream) {
+  if (!sys || !ctl || B < 0) return HJB_ERR_BAD_ARG;
+  if (!dims_ok(sys)) return HJB_ERR_UNSUPPORTED;
+  if (B == 0) return HJB_OK;
+  if (!x || !u) return HJB_ERR_BAD_ARG;
+  CtlArgs a;
+  make_dev_sys(sys, a.sys);
+  make_dev_ctl(sys, ctl, a.ctl);
+  a.x = x; a.u = u; a.B = B;
+  return to_status(step_control(sys->kind, ctl->kind, a, fast_trig != 0, (cudaStream_t)stream));
+}
+
+int hjb_states_wrap(const hjb_system* sys, float* x, int64_t B, void* stream) {
+  if (!sys || B < 0) return HJB_ERR_BAD_ARG;
+  if (!dims_ok(sys)) return HJB_ERR_UNSUPPORTED;
+  if (B == 0) return HJB_OK;
+  if (!x) return HJB_ERR_BAD_ARG;
+  return to_status(step_wrap(sys->kind, sys->n, x, B, (cudaStream_t)stream));
+}
+
+int hjb_fma_peak_probe(float* sink, int64_t sink_len, int32_t iters, double* flops, void* stream) {
+  if (!sink || sink_len <= 0 || iters <= 0) return HJB_ERR_BAD_ARG;
+  return to_status(fma_probe(sink, sink_len, iters, flops, (cudaStream_t)stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,242 @@
+// K1 — batched closed-loop rollout: one thread = one environment, whole horizon in one launch.
+//
+// State, RK4 stages and the cost accumulator live in registers; system constants, gains and cost
+// matrices are read from the kernel parameter space (constant bank operands, no register cost).
+// Trajectories are written time-major ([t][env][i]) so that a warp's stores of one step are contiguous;
+// stores are vectorised (16 B for n = 4, 8 B for even n) and streaming (st.global.cs).
+#pragma once
+#include "systems.cuh"
+
+namespace hjb {
+
+enum CostMode { COST_NONE = 0, COST_DIAG = 1, COST_DENSE = 2 };
+
+struct RolloutArgs {
+  DevSys sys;
+  DevCtl ctl;
+  DevCost cost;
+  DevBox box;
+  const float* x0;
+  float* xs;
+  float* us;
+  float* x_final;
+  float* cost_out;
+  int32_t* steps_out;
+  int64_t N;
+  int32_t T;
+  int32_t stride;  // record stride (>= 1 when xs/us requested)
+  int32_t n_rec;   // T / stride recorded intervals
+};
+
+template <class S, int COST>
+__device__ __forceinline__ float running_cost(const DevCost& pc, const float* x, const float* u) {
+  float dx[S::N], du[S::M];
+#pragma unroll
+  for (int i = 0; i < S::N; ++i) dx[i] = x[i] - pc.xf[i];
+  S::wrap(dx);
+#pragma unroll
+  for (int k = 0; k < S::M; ++k) du[k] = u[k] - pc.uf[k];
+  float l = 0.f;
+  if constexpr (COST == COST_DIAG) {
+#pragma unroll
+    for (int i = 0; i < S::N; ++i) l = fmaf(pc.Q[i * S::N + i] * dx[i], dx[i], l);
+#pragma unroll
+    for (int k = 0; k < S::M; ++k) l = fmaf(pc.R[k * S::M + k] * du[k], du[k], l);
+  } else {
+#pragma unroll
+    for (int i = 0; i < S::N; ++i) {
+      float row = 0.f;
+#pragma unroll
+      for (int j = 0; j < S::N; ++j) row = fmaf(pc.Q[i * S::N + j], dx[j], row);
+      l = fmaf(dx[i], row, l);
+    }
+#pragma unroll
+    for (int k = 0; k < S::M; ++k) {
+      float row = 0.f;
+#pragma unroll
+      for (int j = 0; j < S::M; ++j) row = fmaf(pc.R[k * S::M + j], du[j], row);
+      l = fmaf(du[k], row, l);
+    }
+  }
+  return l;
+}
+
+// one integration step of Dynamics.simulate AFTER the clip: x <- wrap(step(x, u))
+template <class S, int INTEG>
+__device__ __forceinline__ void integrate(const DevSys& ps, float* x, const typename S::Trig& tr0, const float* u) {
+  constexpr int N = S::N;
+  if constexpr (INTEG == HJB_INT_DISCRETE) {
+    float d[N];
+    S::xdot(ps, x, tr0, u, d);
+#pragma unroll
+    for (int i = 0; i < N; ++i) x[i] = d[i];
+  } else if constexpr (INTEG == HJB_INT_EULER) {
+    float d[N];
+    S::xdot(ps, x, tr0, u, d);
+#pragma unroll
+    for (int i = 0; i < N; ++i) x[i] = fmaf(d[i], ps.dt, x[i]);
+  } else {
+    const float h = ps.dt, hh = 0.5f * ps.dt;
+    float k[N], acc[N], xt[N];
+    typename S::Trig tr;
+    S::xdot(ps, x, tr0, u, k);
+#pragma unroll
+    for (int i = 0; i < N; ++i) { acc[i] = k[i]; xt[i] = fmaf(hh, k[i], x[i]); }
+    S::trig(xt, tr);
+    S::xdot(ps, xt, tr, u, k);
+#pragma unroll
+    for (int i = 0; i < N; ++i) { acc[i] = fmaf(2.f, k[i], acc[i]); xt[i] = fmaf(hh, k[i], x[i]); }
+    S::trig(xt, tr);
+    S::xdot(ps, xt, tr, u, k);
+#pragma unroll
+    for (int i = 0; i < N; ++i) { acc[i] = fmaf(2.f, k[i], acc[i]); xt[i] = fmaf(h, k[i], x[i]); }
+    S::trig(xt, tr);
+    S::xdot(ps, xt, tr, u, k);
+    const float h6 = ps.dt * (1.0f / 6.0f);
+#pragma unroll
+    for (int i = 0; i < N; ++i) x[i] = fmaf(h6, acc[i] + k[i], x[i]);
+  }
+  S::wrap(x);
+}
+
+template <class S>
+__device__ __forceinline__ bool inside_box(const DevBox& b, const float* x) {
+  float dx[S::N];
+#pragma unroll
+  for (int i = 0; i < S::N; ++i) dx[i] = x[i] - b.xf[i];
+  S::wrap(dx);
+  bool in = true;
+#pragma unroll
+  for (int i = 0; i < S::N; ++i) in = in && !(dx[i] > b.hi[i]) && !(dx[i] < b.lo[i]);
+  return in;
+}
+
+template <class S, class C, int INTEG, bool REC, int COST, bool BOX>
+__global__ void __launch_bounds__(256) rollout_kernel(const __grid_constant__ RolloutArgs a) {
+  constexpr int N = S::N, M = S::M;
+  const int64_t env = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (env >= a.N) return;
+
+  float x[N];
+  load_row<N>(a.x0, env, x);
+  float J = 0.f;
+  int32_t nsteps = 0;
+  bool alive = true;
+
+  int64_t rec = 0;      // next trajectory slot
+  int32_t phase = 0;    // steps since the last recorded state
+  if constexpr (REC) {
+    if (a.xs) store_row<N>(a.xs, env, x);
+    rec = 1;
+  }
+
+  for (int32_t t = 0; t < a.T; ++t) {
+    if constexpr (BOX) alive = alive && inside_box<S>(a.box, x);
+    typename S::Trig tr;
+    S::trig(x, tr);
+    float u[M];
+    C::template control<S>(a.sys, a.ctl, x, tr, u);
+    if constexpr (REC) {
+      if (phase == 0 && a.us && rec <= a.n_rec) store_row<M>(a.us, (rec - 1) * a.N + env, u);
+    }
+    float xn[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) xn[i] = x[i];
+    float l = 0.f;
+    if constexpr (COST != COST_NONE) l = running_cost<S, COST>(a.cost, x, u);
+    clip_u<S>(a.sys, u);  // Dynamics.simulate's own clip (dynamics_basic.py:118)
+    integrate<S, INTEG>(a.sys, xn, tr, u);
+    if constexpr (BOX) {
+      if (alive) {
+#pragma unroll
+        for (int i = 0; i < N; ++i) x[i] = xn[i];
+        J = fmaf(l, a.sys.dt, J);
+        ++nsteps;
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < N; ++i) x[i] = xn[i];
+      if constexpr (COST != COST_NONE) J = fmaf(l, a.sys.dt, J);
+    }
+    if constexpr (REC) {
+      if (++phase == a.stride) {
+        phase = 0;
+        if (a.xs) store_row<N>(a.xs, rec * a.N + env, x);
+        ++rec;
+      }
+    }
+  }
+  if (a.x_final) store_row<N>(a.x_final, env, x);
+  if (a.cost_out) a.cost_out[env] = J;
+  if (a.steps_out) a.steps_out[env] = BOX ? nsteps : a.T;
+}
+
+// ------------------------------------------------------------------------------------------------
+// launchers (one translation unit per problem instantiates these)
+// ------------------------------------------------------------------------------------------------
+struct RolloutVariant {
+  int integrator;  // hjb_integrator
+  bool rec;
+  int cost;        // CostMode
+  bool box;
+};
+
+template <class S, class C, int INTEG, bool REC, int COST, bool BOX>
+inline cudaError_t launch_one(const RolloutArgs& a, cudaStream_t st) {
+  const int block = 256;
+  const int64_t grid = (a.N + block - 1) / block;
+  if (grid > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
+  rollout_kernel<S, C, INTEG, REC, COST, BOX><<<(unsigned)grid, block, 0, st>>>(a);
+  return cudaGetLastError();
+}
+
+template <class S, class C, int INTEG, bool REC, int COST>
+inline cudaError_t launch_box(const RolloutArgs& a, const RolloutVariant& v, cudaStream_t st) {
+  return v.box ? launch_one<S, C, INTEG, REC, COST, true>(a, st) : launch_one<S, C, INTEG, REC, COST, false>(a, st);
+}
+template <class S, class C, int INTEG, bool REC>
+inline cudaError_t launch_cost(const RolloutArgs& a, const RolloutVariant& v, cudaStream_t st) {
+  switch (v.cost) {
+    case COST_NONE: return launch_box<S, C, INTEG, REC, COST_NONE>(a, v, st);
+    case COST_DIAG: return launch_box<S, C, INTEG, REC, COST_DIAG>(a, v, st);
+    default: return launch_box<S, C, INTEG, REC, COST_DENSE>(a, v, st);
+  }
+}
+template <class S, class C, int INTEG>
+inline cudaError_t launch_rec(const RolloutArgs& a, const RolloutVariant& v, cudaStream_t st) {
+  return v.rec ? launch_cost<S, C, INTEG, true>(a, v, st) : launch_cost<S, C, INTEG, false>(a, v, st);
+}
+// ALLOW_DISCRETE: only LINEAR systems have the exact-ZOH update
+template <class S, class C, bool ALLOW_DISCRETE>
+inline cudaError_t launch_rollout(const RolloutArgs& a, const RolloutVariant& v, cudaStream_t st) {
+  switch (v.integrator) {
+    case HJB_INT_EULER: return launch_rec<S, C, HJB_INT_EULER>(a, v, st);
+    case HJB_INT_RK4: return launch_rec<S, C, HJB_INT_RK4>(a, v, st);
+    case HJB_INT_DISCRETE:
+      if constexpr (ALLOW_DISCRETE) return launch_rec<S, C, HJB_INT_DISCRETE>(a, v, st);
+      else return cudaErrorNotSupported;
+    default: return cudaErrorInvalidValue;
+  }
+}
+
+// problem ids dispatched by api.cu; each is defined in its own rollout_<name>.cu
+#define HJB_DECLARE_PROBLEM(name) \
+  cudaError_t rollout_##name(const RolloutArgs& a, const RolloutVariant& v, bool fast, cudaStream_t st)
+
+HJB_DECLARE_PROBLEM(linear21_fb);
+HJB_DECLARE_PROBLEM(linear41_fb);
+HJB_DECLARE_PROBLEM(linear42_fb);
+HJB_DECLARE_PROBLEM(cartpole_fb);
+HJB_DECLARE_PROBLEM(cartpole_es);
+HJB_DECLARE_PROBLEM(acrobot_fb);
+HJB_DECLARE_PROBLEM(acrobot_es);
+HJB_DECLARE_PROBLEM(quad2d_fb);
+HJB_DECLARE_PROBLEM(quad10d_fb);
+
+#define HJB_DEFINE_PROBLEM(name, SYS_T, CTL, ALLOW_DISCRETE)                                              \
+  cudaError_t rollout_##name(const RolloutArgs& a, const RolloutVariant& v, bool fast, cudaStream_t st) { \
+    if (fast) return launch_rollout<SYS_T(true), CTL, ALLOW_DISCRETE>(a, v, st);                          \
+    return launch_rollout<SYS_T(false), CTL, ALLOW_DISCRETE>(a, v, st);                                   \
+  }
+
+}  // namespace hjb

@@ -1,0 +1,326 @@
+// Control-affine systems x' = f(x) + g(x) u and the model-based controllers, as device functions.
+//
+// Each system S<FAST> provides
+//   N, M                 state / control dimension (compile time -> everything stays in registers)
+//   Trig                 sin/cos of the state's angles, computed once per evaluation point and shared
+//                        between the control law and the dynamics of the same state
+//   trig(x)              fills Trig
+//   xdot(p, x, tr, u, d) d = f(x) + g(x) u with g's structural zeros skipped (the fused fast path)
+//   fg(p, x, tr, f, g)   explicit f [N] and g [N*M] (row-major) for the API / the vhjb pass
+//   wrap(x)              states_wrap in place
+// Reference formulas: dynamics/{linear,cartpole,acrobot,quadrotors}.py through the manipulator form of
+// dynamics/dynamics_basic.py:64-94, with the 2x2 M^-1 written in closed form.
+#pragma once
+#include "hjb_common.cuh"
+
+namespace hjb {
+
+// ------------------------------------------------------------------------------------------------
+// LINEAR  (dynamics/linear.py:20-22)   f = A x, g = B, wrap = identity
+// ------------------------------------------------------------------------------------------------
+template <int N_, int M_, bool FAST>
+struct LinearSys {
+  static constexpr int N = N_, M = M_;
+  static constexpr bool kFast = FAST;
+  static constexpr int KIND = HJB_SYS_LINEAR;
+  struct Trig {};
+  static __device__ __forceinline__ void trig(const float*, Trig&) {}
+  // A x + B u   (also the exact-ZOH update when A, B are the discretised matrices)
+  static __device__ __forceinline__ void xdot(const DevSys& p, const float* x, const Trig&, const float* u, float* d) {
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      float acc = 0.f;
+#pragma unroll
+      for (int j = 0; j < N; ++j) acc = fmaf(p.A[i * N + j], x[j], acc);
+#pragma unroll
+      for (int k = 0; k < M; ++k) acc = fmaf(p.B[i * M + k], u[k], acc);
+      d[i] = acc;
+    }
+  }
+  static __device__ __forceinline__ void fg(const DevSys& p, const float* x, const Trig&, float* f, float* g) {
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      float acc = 0.f;
+#pragma unroll
+      for (int j = 0; j < N; ++j) acc = fmaf(p.A[i * N + j], x[j], acc);
+      f[i] = acc;
+#pragma unroll
+      for (int k = 0; k < M; ++k) g[i * M + k] = p.B[i * M + k];
+    }
+  }
+  static __device__ __forceinline__ void wrap(float*) {}
+};
+
+// ------------------------------------------------------------------------------------------------
+// CARTPOLE  (dynamics/cartpole.py:19-64)   x = [p, th, dp, dth]
+//   M = [[M11, k c],[k c, M22]], C dq = [-k dth^2 s, 0], G = [0, gamma s], B = [1, 0]
+//   c = {M11, kappa, M22, gamma, M11*M22}
+// ------------------------------------------------------------------------------------------------
+template <bool FAST>
+struct CartpoleSys {
+  static constexpr int N = 4, M = 1;
+  static constexpr bool kFast = FAST;
+  static constexpr int KIND = HJB_SYS_CARTPOLE;
+  struct Trig { float s, c; };
+  static __device__ __forceinline__ void trig(const float* x, Trig& t) { sincos_<FAST>(x[1], t.s, t.c); }
+  static __device__ __forceinline__ void xdot(const DevSys& p, const float* x, const Trig& t, const float* u, float* d) {
+    const float m12 = p.c[1] * t.c;
+    const float inv = rcp_<FAST>(fmaf(-m12, m12, p.c[4]));
+    const float h1 = fmaf(p.c[1] * t.s, x[3] * x[3], u[0]);   // kappa dth^2 s + u
+    const float h2 = -p.c[3] * t.s;                            // -gamma s
+    d[0] = x[2];
+    d[1] = x[3];
+    d[2] = fmaf(p.c[2], h1, -m12 * h2) * inv;
+    d[3] = fmaf(p.c[0], h2, -m12 * h1) * inv;
+  }
+  static __device__ __forceinline__ void fg(const DevSys& p, const float* x, const Trig& t, float* f, float* g) {
+    const float m12 = p.c[1] * t.c;
+    const float inv = rcp_<FAST>(fmaf(-m12, m12, p.c[4]));
+    const float h1 = p.c[1] * t.s * x[3] * x[3];
+    const float h2 = -p.c[3] * t.s;
+    f[0] = x[2];
+    f[1] = x[3];
+    f[2] = fmaf(p.c[2], h1, -m12 * h2) * inv;
+    f[3] = fmaf(p.c[0], h2, -m12 * h1) * inv;
+    g[0] = 0.f;
+    g[1] = 0.f;
+    g[2] = p.c[2] * inv;
+    g[3] = -m12 * inv;
+  }
+  static __device__ __forceinline__ void wrap(float* x) { x[1] = wrap_pi(x[1]); }
+};
+
+// ------------------------------------------------------------------------------------------------
+// ACROBOT  (dynamics/acrobot.py:39-81)   x = [q1, q2, dq1, dq2]
+//   c = {M11_0, a, I2, G1c, G12c}
+//   M = [[M11_0 + 2 a c2, I2 + a c2],[I2 + a c2, I2]]
+//   C dq = [-a s2 dq2 (2 dq1 + dq2), a s2 dq1^2],  G = [G1c s1 + G12c s12, G12c s12],  B = [0, 1]
+// ------------------------------------------------------------------------------------------------
+template <bool FAST>
+struct AcrobotSys {
+  static constexpr int N = 4, M = 1;
+  static constexpr bool kFast = FAST;
+  static constexpr int KIND = HJB_SYS_ACROBOT;
+  struct Trig { float s1, c1, s2, c2, s12, c12; };
+  static __device__ __forceinline__ void trig(const float* x, Trig& t) {
+    sincos_<FAST>(x[0], t.s1, t.c1);
+    sincos_<FAST>(x[1], t.s2, t.c2);
+    sincos_<FAST>(x[0] + x[1], t.s12, t.c12);
+  }
+  struct Terms { float m11, m12, m22, h1, h2; };  // h = C dq + G
+  static __device__ __forceinline__ void terms(const DevSys& p, const float* x, const Trig& t, Terms& r) {
+    const float ac2 = p.c[1] * t.c2;
+    r.m11 = fmaf(2.f, ac2, p.c[0]);
+    r.m12 = p.c[2] + ac2;
+    r.m22 = p.c[2];
+    const float as2 = p.c[1] * t.s2;
+    const float g2 = p.c[4] * t.s12;
+    r.h1 = fmaf(p.c[3], t.s1, g2) - as2 * x[3] * fmaf(2.f, x[2], x[3]);
+    r.h2 = fmaf(as2 * x[2], x[2], g2);
+  }
+  static __device__ __forceinline__ void xdot(const DevSys& p, const float* x, const Trig& t, const float* u, float* d) {
+    Terms r;
+    terms(p, x, t, r);
+    const float inv = rcp_<FAST>(fmaf(r.m11, r.m22, -r.m12 * r.m12));
+    const float b1 = -r.h1;          // B u - h, B = [0, 1]
+    const float b2 = u[0] - r.h2;
+    d[0] = x[2];
+    d[1] = x[3];
+    d[2] = fmaf(r.m22, b1, -r.m12 * b2) * inv;
+    d[3] = fmaf(r.m11, b2, -r.m12 * b1) * inv;
+  }
+  static __device__ __forceinline__ void fg(const DevSys& p, const float* x, const Trig& t, float* f, float* g) {
+    Terms r;
+    terms(p, x, t, r);
+    const float inv = rcp_<FAST>(fmaf(r.m11, r.m22, -r.m12 * r.m12));
+    f[0] = x[2];
+    f[1] = x[3];
+    f[2] = fmaf(-r.m22, r.h1, r.m12 * r.h2) * inv;
+    f[3] = fmaf(-r.m11, r.h2, r.m12 * r.h1) * inv;
+    g[0] = 0.f;
+    g[1] = 0.f;
+    g[2] = -r.m12 * inv;
+    g[3] = r.m11 * inv;
+  }
+  // dynamics/acrobot.py:60-70
+  static __device__ __forceinline__ float energy(const DevSys& p, const float* x, const Trig& t, const Terms& r) {
+    float e = 0.5f * r.m11 * x[2] * x[2];
+    e = fmaf(0.5f * r.m22 * x[3], x[3], e);
+    e = fmaf(r.m12 * x[2], x[3], e);
+    e = fmaf(-p.c[3], t.c1, e);
+    e = fmaf(-p.c[4], t.c12, e);
+    return e;
+  }
+  static __device__ __forceinline__ void wrap(float* x) {
+    x[0] = wrap_pi(x[0]);
+    x[1] = wrap_pi(x[1]);
+  }
+};
+
+// ------------------------------------------------------------------------------------------------
+// QUAD2D  (dynamics/quadrotors.py:17-70)   x = [x, y, th, dx, dy, dth],  c = {g, 1/m, r/I}
+// ------------------------------------------------------------------------------------------------
+template <bool FAST>
+struct Quad2DSys {
+  static constexpr int N = 6, M = 2;
+  static constexpr bool kFast = FAST;
+  static constexpr int KIND = HJB_SYS_QUAD2D;
+  struct Trig { float s, c; };
+  static __device__ __forceinline__ void trig(const float* x, Trig& t) { sincos_<FAST>(x[2], t.s, t.c); }
+  static __device__ __forceinline__ void xdot(const DevSys& p, const float* x, const Trig& t, const float* u, float* d) {
+    const float sm = (u[0] + u[1]) * p.c[1];
+    d[0] = x[3];
+    d[1] = x[4];
+    d[2] = x[5];
+    d[3] = -t.s * sm;
+    d[4] = fmaf(t.c, sm, -p.c[0]);
+    d[5] = (u[0] - u[1]) * p.c[2];
+  }
+  static __device__ __forceinline__ void fg(const DevSys& p, const float* x, const Trig& t, float* f, float* g) {
+    f[0] = x[3]; f[1] = x[4]; f[2] = x[5];
+    f[3] = 0.f; f[4] = -p.c[0]; f[5] = 0.f;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) g[i] = 0.f;
+    g[6] = g[7] = -t.s * p.c[1];
+    g[8] = g[9] = t.c * p.c[1];
+    g[10] = p.c[2];
+    g[11] = -p.c[2];
+  }
+  static __device__ __forceinline__ void wrap(float* x) { x[2] = wrap_pi(x[2]); }
+};
+
+// ------------------------------------------------------------------------------------------------
+// QUAD10D  (dynamics/quadrotors.py:118-170)  x = [p(3), thx, thy, v(3), wx, wy],  c = {g, kT/m, n0}
+// ------------------------------------------------------------------------------------------------
+template <bool FAST>
+struct Quad10DSys {
+  static constexpr int N = 10, M = 3;
+  static constexpr bool kFast = FAST;
+  static constexpr int KIND = HJB_SYS_QUAD10D;
+  struct Trig { float tx, ty; };
+  static __device__ __forceinline__ void trig(const float* x, Trig& t) {
+    t.tx = tan_<FAST>(x[3]);
+    t.ty = tan_<FAST>(x[4]);
+  }
+  static __device__ __forceinline__ void xdot(const DevSys& p, const float* x, const Trig& t, const float* u, float* d) {
+#pragma unroll
+    for (int i = 0; i < 5; ++i) d[i] = x[5 + i];
+    d[5] = p.c[0] * t.tx;
+    d[6] = p.c[0] * t.ty;
+    d[7] = fmaf(p.c[1], u[0], -p.c[0]);
+    d[8] = p.c[2] * u[1];
+    d[9] = p.c[2] * u[2];
+  }
+  static __device__ __forceinline__ void fg(const DevSys& p, const float* x, const Trig& t, float* f, float* g) {
+#pragma unroll
+    for (int i = 0; i < 5; ++i) f[i] = x[5 + i];
+    f[5] = p.c[0] * t.tx;
+    f[6] = p.c[0] * t.ty;
+    f[7] = -p.c[0];
+    f[8] = 0.f;
+    f[9] = 0.f;
+#pragma unroll
+    for (int i = 0; i < 30; ++i) g[i] = 0.f;
+    g[7 * 3 + 0] = p.c[1];
+    g[8 * 3 + 1] = p.c[2];
+    g[9 * 3 + 2] = p.c[2];
+  }
+  static __device__ __forceinline__ void wrap(float* x) {
+    x[3] = wrap_pi(x[3]);
+    x[4] = wrap_pi(x[4]);
+  }
+};
+
+// ------------------------------------------------------------------------------------------------
+// controllers: control(ps, pc, x, tr, u) writes the controller OUTPUT (get_control_efforts), i.e. before
+// Dynamics.simulate's own clip.
+// ------------------------------------------------------------------------------------------------
+template <class S>
+__device__ __forceinline__ void clip_u(const DevSys& ps, float* u) {
+#pragma unroll
+  for (int k = 0; k < S::M; ++k) u[k] = clampf(u[k], ps.umin[k], ps.umax[k]);
+}
+
+// u = -K wrap(x - xf) + uf [clipped]   (lqr.py:29-30; cartpole_balancing.ipynb cell 4:24-25;
+// quadrotors_model_based_controller.py:36-38, 73-75)
+struct FeedbackCtl {
+  static constexpr int KIND = HJB_CTL_FEEDBACK;
+  template <class S>
+  static __device__ __forceinline__ void control(const DevSys& ps, const DevCtl& pc, const float* x,
+                                                 const typename S::Trig&, float* u) {
+    float dx[S::N];
+#pragma unroll
+    for (int i = 0; i < S::N; ++i) dx[i] = x[i] - pc.xf[i];
+    S::wrap(dx);
+#pragma unroll
+    for (int k = 0; k < S::M; ++k) {
+      float acc = pc.uf[k];
+#pragma unroll
+      for (int i = 0; i < S::N; ++i) acc = fmaf(-pc.K[k * S::N + i], dx[i], acc);
+      u[k] = acc;
+    }
+    if (pc.clip) clip_u<S>(ps, u);
+  }
+};
+
+// controller/cartpole_energy_shaping.py:65-110.  Both branches are evaluated and selected (no divergence).
+// aux = {Ke0, Ke1, Ke2, eps_energy, eps_state^2, E(xf)};  ps.c[5] = 1/l, ps.c[6] = g/l
+struct CartpoleESCtl {
+  static constexpr int KIND = HJB_CTL_CARTPOLE_ES;
+  template <class S>
+  static __device__ __forceinline__ void control(const DevSys& ps, const DevCtl& pc, const float* x,
+                                                 const typename S::Trig& t, float* u) {
+    static_assert(S::KIND == HJB_SYS_CARTPOLE, "cartpole energy shaping needs the cartpole");
+    float dx[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) dx[i] = x[i] - pc.xf[i];
+    S::wrap(dx);                                                     // :75
+    const float de = fmaf(0.5f * x[3], x[3], -t.c) - pc.aux[5];      // :78, :90-95
+    const bool near = (fabsf(de) < pc.aux[3]) && (fmaf(dx[1], dx[1], dx[3] * dx[3]) < pc.aux[4]);  // :79
+    float ulqr = 0.f;                                                // :80
+#pragma unroll
+    for (int i = 0; i < 4; ++i) ulqr = fmaf(-pc.K[i], dx[i], ulqr);
+    const float ubar = de * x[3] * t.c;                              // :99
+    const float a1 = fmaf(pc.aux[2], ubar, -fmaf(pc.aux[0], x[0], pc.aux[1] * x[2]));          // :100
+    const float a2 = -fmaf(t.c * ps.c[5], a1, ps.c[6] * t.s);                                    // :101
+    float ues = fmaf(ps.c[0], a1, ps.c[1] * t.c * a2);                                           // :102
+    ues = fmaf(-ps.c[1] * t.s, x[3] * x[3], ues);                                                // :103
+    u[0] = clampf(near ? ulqr : ues, ps.umin[0], ps.umax[0]);        // :86
+  }
+};
+
+// controller/acrobot_energy_shaping.py:74-121 (Spong collocated swing-up + LQR catch).
+// aux = {Ks0, Ks1, Ks2, eps, E(xf)}
+struct AcrobotESCtl {
+  static constexpr int KIND = HJB_CTL_ACROBOT_ES;
+  template <class S>
+  static __device__ __forceinline__ void control(const DevSys& ps, const DevCtl& pc, const float* x,
+                                                 const typename S::Trig& t, float* u) {
+    static_assert(S::KIND == HJB_SYS_ACROBOT, "acrobot energy shaping needs the acrobot");
+    float dx[4];
+    dx[0] = wrap_pi(x[0] - pc.xf[0]);                                // :109
+    dx[1] = wrap_pi(x[1] - pc.xf[1]);
+    dx[2] = x[2] - pc.xf[2];
+    dx[3] = x[3] - pc.xf[3];
+    float quad = 0.f;                                                // :114  dx^T P dx
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float row = 0.f;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) row = fmaf(pc.P[i * 4 + j], dx[j], row);
+      quad = fmaf(dx[i], row, quad);
+    }
+    float ulqr = 0.f;                                                // :115
+#pragma unroll
+    for (int i = 0; i < 4; ++i) ulqr = fmaf(-pc.K[i], dx[i], ulqr);
+    typename S::Terms r;
+    S::terms(ps, x, t, r);                                           // :83-86
+    const float ubar = (S::energy(ps, x, t, r) - pc.aux[4]) * x[2];  // :88
+    const float a2 = fmaf(pc.aux[2], ubar, -fmaf(pc.aux[0], wrap_pi(x[1]), pc.aux[1] * x[3]));  // :90
+    const float i11 = rcp_<S::kFast>(r.m11);
+    const float usw = fmaf(fmaf(-r.m12 * r.m12, i11, r.m22), a2, fmaf(-r.m12 * i11, r.h1, r.h2));  // :92
+    u[0] = clampf(quad < pc.aux[3] ? ulqr : usw, ps.umin[0], ps.umax[0]);  // :119
+  }
+};
+
+}  // namespace hjb

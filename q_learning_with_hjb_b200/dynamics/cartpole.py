@@ -1,0 +1,31 @@
+"""``Cartpole``: x = [p, theta, dp, dtheta], theta = pi upright (reference: dynamics/cartpole.py:10-64)."""
+import numpy as np
+
+from q_learning_with_hjb_b200 import _lib as L
+from q_learning_with_hjb_b200.dynamics.dynamics_basic import Dynamics
+
+
+class Cartpole(Dynamics):
+    KIND = L.SYS_CARTPOLE
+    WRAP_INDEX = (1,)
+
+    def __init__(self, config) -> None:
+        super().__init__(config)
+        self.mc, self.mp, self.l, self.g = config.mc, config.mp, config.l, config.g
+
+    # manipulator matrices, host side: used once by the model-based controllers to linearise about xf
+    def get_M(self, x):
+        k = self.mp * self.l * np.cos(x[1])
+        return np.array([[self.mc + self.mp, k], [k, self.mp * self.l ** 2]])
+
+    def get_C(self, x):
+        return np.array([[0.0, -self.mp * self.l * x[3] * np.sin(x[1])], [0.0, 0.0]])
+
+    def get_G(self, x):
+        return np.array([0.0, self.mp * self.g * self.l * np.sin(x[1])])
+
+    def get_B(self):
+        return np.array([1, 0])
+
+    def system_params(self):
+        return [self.mc, self.mp, self.l, self.g], np.zeros(0), np.zeros(0)

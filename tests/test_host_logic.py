@@ -1,0 +1,98 @@
+"""CPU-side checks of the product package: config loading, gains, C-ABI struct packing, library exports.
+No compute call is made (there is no GPU here and no CPU fallback)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from tests.helpers import PAIRS, make_controller, make_dynamics, oracle_pair
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    from q_learning_with_hjb_b200 import _lib as L
+    header = open(os.path.join(ROOT, "include", "hjb_b200.h")).read()
+    declared = set(re.findall(r"\b(hjb_[a-z0-9_]+)\s*\(", header))
+    assert declared, "no prototypes found in include/hjb_b200.h"
+    assert declared == set(L.SYMBOLS), f"_lib.SYMBOLS out of sync with the header: {declared ^ set(L.SYMBOLS)}"
+    handle = ctypes.CDLL(L.lib_path())
+    for name in declared:
+        assert hasattr(handle, name), f"{name} not exported by libhjb_b200.so"
+    assert L.lib().hjb_abi_version() == 1
+    assert L.lib().hjb_status_string(-2).startswith(b"hjb: unsupported")
+
+
+def test_struct_sizes_match_header_layout():
+    from q_learning_with_hjb_b200 import _lib as L
+    assert ctypes.sizeof(L.HjbSystem) == 4 * (4 + 3 + 3 + 8 + 16 + 8)
+    assert ctypes.sizeof(L.HjbControl) == 4 * (2 + 30 + 16 + 10 + 3 + 8)
+    assert ctypes.sizeof(L.HjbCost) == 4 * (100 + 9 + 10 + 3)
+    assert ctypes.sizeof(L.HjbRolloutOpts) == 4 * (4 + 30)
+
+
+@pytest.mark.parametrize("skind,ckind", PAIRS)
+def test_gains_and_specs_match_oracle(skind, ckind):
+    dyn = make_dynamics(skind)
+    ctl = make_controller(ckind, dyn)
+    osys, octl = oracle_pair(skind, ckind)
+    spec = ctl.control_spec()
+    n, m = dyn.get_dimension()
+    np.testing.assert_allclose(np.array(spec.K[:n * m]).reshape(m, n), octl.K, rtol=2e-7)
+    s = dyn.system_spec()
+    assert (s.n, s.m) == (osys.n, osys.m) and abs(s.dt - osys.dt) < 1e-9
+    np.testing.assert_allclose(np.array(s.umin[:m]), osys.umin, rtol=1e-7)
+    np.testing.assert_allclose(np.array(s.umax[:m]), osys.umax, rtol=1e-7)
+
+
+def test_initial_state_stream_matches_reference_semantics():
+    # same RNG stream as Dynamics.get_initial_state (dynamics_basic.py:28-29): seed 0, U(-std, std) + mean, wrapped
+    dyn = make_dynamics("cartpole")
+    x = dyn.get_initial_state()
+    np.testing.assert_allclose(x, [0.23430483, -3.12166627, 0.20552675, 0.00448832], atol=1e-8)
+    assert x.dtype == np.float64
+
+
+def test_states_wrap_numpy_is_in_place():
+    dyn = make_dynamics("quad10d")
+    x = np.arange(10, dtype=np.float64)
+    y = dyn.states_wrap(x)
+    assert y is x
+    np.testing.assert_allclose(x[3:5], [3, 4 - 2 * np.pi])
+    xb = np.tile(np.arange(10, dtype=np.float64), (3, 1))
+    dyn.states_wrap(xb)
+    np.testing.assert_allclose(xb[:, 4], 4 - 2 * np.pi)
+
+
+def test_compute_calls_fail_loudly_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    dyn = make_dynamics("cartpole")
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        dyn.simulate(np.zeros(4), np.zeros(1))
+    ctl = make_controller("cartpole_es", dyn)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        ctl.get_control_efforts(np.zeros(4))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        dyn.rollout(ctl, np.zeros((2, 4)), 10)
+
+
+def test_hover_controller_rejects_moving_goal():
+    from q_learning_with_hjb_b200.controller.quadrotors_model_based_controller import Quadrotors2DHoveringController
+    dyn = make_dynamics("quad2d")
+    with pytest.raises(ValueError):
+        Quadrotors2DHoveringController(dyn, np.array([0, 0, 0.1, 0, 0, 0]), np.eye(6), np.eye(2))
+
+
+def test_gin_files_bind_like_the_reference():
+    from q_learning_with_hjb_b200.configs import gin_compat as gin
+    from q_learning_with_hjb_b200.configs.controller.vhjb_controller_config import VHJBControllerConfig
+    cfgdir = os.path.join(ROOT, "q_learning_with_hjb_b200", "configs", "controller")
+    gin.parse_config_file(os.path.join(cfgdir, "quadrotors2DHovering_vhjb_controller.gin"))
+    cfg = VHJBControllerConfig()
+    assert list(cfg.features) == [128, 128, 64] and cfg.batch_size == 256 and cfg.epsilon == 1e-10
+    assert cfg.Q.shape == (6, 6) and cfg.Q.dtype == np.float32
+    np.testing.assert_allclose(cfg.uf, [4.905, 4.905], rtol=1e-6)

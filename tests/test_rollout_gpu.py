@@ -1,0 +1,382 @@
+"""GPU parity tests for hot path (a): the CUDA rollout kernels (through the ctypes C ABI) against the oracle
+and against the golden vectors produced by the unmodified reference.
+
+Tolerances (BASELINE.json north_star / SURVEY.md §8d): per-step dynamics and controls 1e-5 relative (fp32,
+angles compared modulo 2 pi); full trajectories 1e-5 over the whole horizon for the stable closed loops
+(cartpole LQR 500 steps, quad-2D 1000, quad-10D 1000, linear); acrobot (chaotic) 1e-5 over 50 steps and 1e-3
+over 90 steps, then distributional checks only.
+"""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import rollout_oracle as O
+from tests.helpers import (GOLDEN, PAIRS, WRAP_IDX, angle_diff, make_controller, make_dynamics, oracle_pair,
+                           rand_states, rel_err)
+
+pytestmark = pytest.mark.gpu
+
+STEP_TOL = 1e-5
+
+
+def _cuda():
+    import torch
+    assert torch.cuda.is_available(), "these tests need a CUDA device"
+    from q_learning_with_hjb_b200 import _lib
+    assert os.path.exists(_lib.lib_path()), "libhjb_b200.so missing - the CUDA path must be the one that runs"
+    return torch
+
+
+# ----------------------------------------------------------------------------------------------------
+# per-step parity
+# ----------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("skind", ["linear", "cartpole", "acrobot", "quad2d", "quad10d"])
+@pytest.mark.parametrize("fast", [False, True])
+def test_per_step_dynamics(skind, fast):
+    _cuda()
+    dyn = make_dynamics(skind)
+    dyn.fast_trig = fast
+    osys = O.std_system(skind)
+    x = rand_states(skind, 4096, 5)
+    if skind == "quad10d":   # tan blows up at +-pi/2: keep the relative test away from the poles
+        x[:, 3:5] = np.clip(x[:, 3:5], -1.2, 1.2)
+    rng = np.random.default_rng(6)
+    u = rng.uniform(-1.5, 1.5, size=(x.shape[0], osys.m)) * np.maximum(np.abs(osys.umin), np.abs(osys.umax))
+    x32, u32 = x.astype(np.float32), u.astype(np.float32)
+    xo, uo = x32.astype(np.float64), u32.astype(np.float64)   # the oracle sees exactly the fp32 inputs
+    f, g = dyn.get_control_affine_matrix(x32)
+    fo, go = osys.f_g(xo)
+    tol = STEP_TOL if not fast else 2e-5
+    assert rel_err(f, fo) < tol
+    assert rel_err(g, go) < tol
+    assert rel_err(dyn.dynamics_step(x32, u32), osys.xdot(xo, uo)) < tol
+    for integ in ("euler", "rk4"):
+        xn = dyn.simulate(x32, u32, integrator=integ)
+        assert rel_err(xn, osys.step(xo, uo, integ), WRAP_IDX[skind]) < tol, integ
+
+
+@pytest.mark.parametrize("skind,ckind", PAIRS)
+@pytest.mark.parametrize("fast", [False, True])
+def test_per_step_control(skind, ckind, fast):
+    _cuda()
+    dyn = make_dynamics(skind)
+    dyn.fast_trig = fast
+    ctl = make_controller(ckind, dyn)
+    osys, octl = oracle_pair(skind, ckind)
+    x = rand_states(skind, 4096, 7)
+    if ckind in ("cartpole_es", "acrobot_es"):   # exercise the LQR branch too
+        xf = np.array([0, np.pi, 0, 0]) if ckind == "cartpole_es" else np.array([np.pi, 0, 0, 0])
+        x[:2048] = xf + np.random.default_rng(8).uniform(-0.3, 0.3, size=(2048, 4))
+    x32 = x.astype(np.float32)
+    u = ctl.get_control_efforts(x32)
+    uo = octl.control(osys, x32.astype(np.float64))
+    # the wrap cut and the energy-shaping switch are discontinuities: states within fp32 rounding of them may
+    # legitimately land on the other side; allow a 1e-3 fraction of such samples
+    err = np.abs(u - uo) / np.maximum(1.0, np.abs(uo))
+    tol = STEP_TOL if not fast else 5e-5
+    assert np.mean(err.max(axis=1) > tol) <= 1e-3, float(err.max())
+
+
+def test_single_state_interface_matches_reference_shapes():
+    _cuda()
+    dyn = make_dynamics("cartpole")
+    ctl = make_controller("cartpole_es", dyn)
+    x = dyn.get_initial_state()
+    u = ctl.get_control_efforts(x)
+    assert u.shape == (1,) and u.dtype == np.float64
+    xn = dyn.simulate(x, u)
+    assert xn.shape == (4,)
+    f, g = dyn.get_control_affine_matrix(x)
+    assert f.shape == (4,) and g.shape == (4, 1)
+    assert dyn.simulate(x, 0).shape == (4,)       # scalar u is accepted (reference: cartpole.py:114-115)
+    osys, octl = oracle_pair("cartpole", "cartpole_es")
+    assert rel_err(u, octl.control(osys, x[None])[0]) < STEP_TOL
+    assert rel_err(xn, osys.step(x[None], u[None])[0], WRAP_IDX["cartpole"]) < STEP_TOL
+
+
+def test_states_wrap_on_device():
+    torch = _cuda()
+    dyn = make_dynamics("quad10d")
+    x = torch.linspace(-20, 20, 10 * 1000, device="cuda").reshape(1000, 10).contiguous()
+    ref = dyn.states_wrap(x.cpu().numpy().astype(np.float64))
+    dyn.states_wrap(x)
+    d = angle_diff(x.cpu().numpy(), ref, WRAP_IDX["quad10d"])
+    assert np.abs(d).max() < 1e-5
+    assert x[:, 3:5].min() >= -np.pi - 1e-6 and x[:, 3:5].max() <= np.pi + 1e-6
+
+
+# ----------------------------------------------------------------------------------------------------
+# trajectories
+# ----------------------------------------------------------------------------------------------------
+TRAJ = [("linear", "lqr", 500, 1e-5), ("cartpole", "cartpole_lqr", 500, 1e-5), ("quad2d", "quad2d_hover", 1000, 1e-5),
+        ("quad10d", "quad10d_hover", 1000, 1e-5)]
+
+
+def _x0(skind, count, seed=0):
+    np.random.seed(seed)
+    return make_dynamics(skind).get_initial_states(count).astype(np.float32)
+
+
+@pytest.mark.parametrize("skind,ckind,steps,tol", TRAJ)
+@pytest.mark.parametrize("integ", ["euler", "rk4"])
+def test_full_trajectory_parity(skind, ckind, steps, tol, integ):
+    _cuda()
+    dyn = make_dynamics(skind)
+    ctl = make_controller(ckind, dyn)
+    osys, octl = oracle_pair(skind, ckind)
+    x0 = _x0(skind, 512)
+    res = dyn.rollout(ctl, x0, steps, integrator=integ, record_stride=1)
+    xs, us, xf, _ = O.rollout(osys, octl, x0.astype(np.float64), steps, integ, record_stride=1)
+    assert res.xs.shape == xs.shape and res.us.shape == us.shape
+    assert rel_err(res.xs, xs, WRAP_IDX[skind]) < tol
+    assert rel_err(res.us, us) < 10 * tol        # u = -K dx amplifies the state error by |K|
+    assert rel_err(res.x_final, xf, WRAP_IDX[skind]) < tol
+    np.testing.assert_array_equal(res.xs[-1], res.x_final)
+    np.testing.assert_array_equal(res.xs_env[3], res.xs[:, 3])
+
+
+def test_acrobot_short_horizon_and_distribution():
+    _cuda()
+    dyn = make_dynamics("acrobot")
+    ctl = make_controller("acrobot_es", dyn)
+    osys, octl = oracle_pair("acrobot", "acrobot_es")
+    rng = np.random.default_rng(3)
+    x0 = rng.uniform(-0.1, 0.1, size=(256, 4)).astype(np.float32)
+    x0[0] = [0.001, 0, 0, 0]                      # the reference's demo start (acrobot_energy_shaping.py:131)
+    res = dyn.rollout(ctl, x0, 90, record_stride=1)
+    xs, us, _, _ = O.rollout(osys, octl, x0.astype(np.float64), 90, "euler", record_stride=1)
+    assert rel_err(res.xs[:51], xs[:51], (0, 1)) < 1e-5
+    assert rel_err(res.xs, xs, (0, 1)) < 1e-3
+    # long horizon: compare the distribution of outcomes, not trajectories
+    T = 2000
+    res = dyn.rollout(ctl, x0, T, record_stride=0)
+    _, _, xf, _ = O.rollout(osys, octl, x0.astype(np.float64), T, "euler", record_stride=0)
+    up = np.array([np.pi, 0, 0, 0])
+    caught_gpu = np.abs(angle_diff(res.x_final, up, (0, 1))).max(axis=1) < 0.05
+    caught_cpu = np.abs(angle_diff(xf, up, (0, 1))).max(axis=1) < 0.05
+    assert abs(caught_gpu.mean() - caught_cpu.mean()) < 0.1
+    assert caught_gpu.mean() > 0.5                # the swing-up works
+
+
+def test_cartpole_energy_shaping_swingup():
+    _cuda()
+    dyn = make_dynamics("cartpole")
+    ctl = make_controller("cartpole_es", dyn)
+    osys, octl = oracle_pair("cartpole", "cartpole_es")
+    rng = np.random.default_rng(4)
+    x0 = (rng.uniform(-1, 1, size=(256, 4)) * [1.0, 0.3, 0.5, 0.5]).astype(np.float32)   # hanging down
+    res = dyn.rollout(ctl, x0, 100, record_stride=1)
+    xs, _, _, _ = O.rollout(osys, octl, x0.astype(np.float64), 100, "euler", record_stride=1)
+    err = np.abs(angle_diff(res.xs, xs, (1,))).max(axis=(0, 2)) / np.maximum(1, np.abs(xs).max())
+    assert np.mean(err > 1e-4) < 0.02             # switching controller: a few envs may flip branch a step apart
+
+
+# ----------------------------------------------------------------------------------------------------
+# golden vectors from the unmodified reference, and the notebook known answers, through CUDA
+# ----------------------------------------------------------------------------------------------------
+GOLD_CASES = [("linear", "lqr"), ("cartpole", "cartpole_es"), ("acrobot", "acrobot_es"), ("quad2d", "quad2d_hover"),
+              ("quad10d", "quad10d_hover")]
+
+
+@pytest.mark.parametrize("skind,ckind", GOLD_CASES)
+def test_golden_reference_vectors(skind, ckind):
+    _cuda()
+    G = np.load(os.path.join(GOLDEN, "rollout_reference.npz"))
+    dyn = make_dynamics(skind)
+    ctl = make_controller(ckind, dyn)
+    x, u = G[f"{skind}/x"], G[f"{skind}/u"]
+    f, g = dyn.get_control_affine_matrix(x)
+    assert rel_err(f, G[f"{skind}/f"]) < STEP_TOL
+    assert rel_err(g, G[f"{skind}/g"]) < STEP_TOL
+    assert rel_err(dyn.simulate(x, u), G[f"{skind}/x_next"], WRAP_IDX[skind]) < STEP_TOL
+    uc = ctl.get_control_efforts(x)
+    err = np.abs(uc - G[f"{skind}/{ckind}/u_ctl"]) / np.maximum(1, np.abs(G[f"{skind}/{ckind}/u_ctl"]))
+    assert np.mean(err.max(axis=1) > STEP_TOL) <= 0.03
+    tx = G[f"{skind}/{ckind}/traj_x"]
+    steps = {"acrobot": 50}.get(skind, tx.shape[0] - 1)
+    if ckind == "cartpole_es":
+        steps = 100
+    res = dyn.rollout(ctl, tx[0], steps, record_stride=1)
+    assert rel_err(res.xs, tx[:steps + 1], WRAP_IDX[skind]) < (1e-4 if ckind == "cartpole_es" else 1e-5)
+
+
+def _skip_draws(dyn, skip):
+    np.random.seed(0)
+    for _ in range(skip):
+        np.random.uniform(size=(dyn.state_dim,), low=-dyn.x0_std, high=dyn.x0_std)
+
+
+def test_kat_notebook_costs_through_cuda():
+    _cuda()
+    from q_learning_with_hjb_b200.rollout import RunningCost
+    # cartpole_balancing.ipynb cell 16: mean lqr 9.140986134043468 (cost uses the UNCLIPPED controller output)
+    dyn = make_dynamics("cartpole")
+    ctl = make_controller("cartpole_lqr", dyn)
+    _skip_draws(dyn, 6001)
+    x0 = dyn.get_initial_states(10)
+    cost = RunningCost(np.eye(4), np.eye(1), ctl.xf, ctl.uf)
+    res = dyn.rollout(ctl, x0, 500, record_stride=0, cost=cost)
+    assert abs(res.cost.mean() - 9.140986134043468) < 1e-4 * 9.14
+    # drone_hovering.ipynb cell 16: lqr 1.335421313313018, mean lqr 9.983921427754535
+    dyn = make_dynamics("quad2d")
+    ctl = make_controller("quad2d_hover", dyn)
+    ctl.uf = np.array([4.905, 4.905])
+    _skip_draws(dyn, 12290)
+    x0 = dyn.get_initial_states(10)
+    cost = RunningCost(np.eye(6), np.eye(2), ctl.xf, ctl.uf)
+    res = dyn.rollout(ctl, x0, 200, record_stride=0, cost=cost)
+    assert abs(res.cost[0] - 1.335421313313018) < 1e-4 * 1.34
+    assert abs(res.cost.mean() - 9.983921427754535) < 1e-4 * 9.98
+    # 10D_quadcopte.ipynb cell 14: lqr cost 9.085334056081662
+    dyn = make_dynamics("quad10d")
+    ctl = make_controller("quad10d_hover", dyn)
+    _skip_draws(dyn, 4000)
+    x0 = dyn.get_initial_states(1)
+    cost = RunningCost(np.eye(10), np.eye(3), ctl.xf, ctl.uf)
+    res = dyn.rollout(ctl, x0, 400, record_stride=0, cost=cost)
+    assert abs(res.cost[0] - 9.085334056081662) < 1e-4 * 9.09
+
+
+def test_kat_double_integrator_saturated_lqr_exact_zoh():
+    # double_integrator_optimal_time.ipynb cell 21: saturated LQR (R = 0.01) time-to-origin 4.104 +- 1.2816...
+    _cuda()
+    import scipy.linalg
+    from q_learning_with_hjb_b200.controller.lqr import StateFeedback
+    dyn = make_dynamics("linear")
+    dyn.dt = 0.01
+    dyn.umin, dyn.umax = np.float32([-1]), np.float32([1])
+    A, B = np.array([[0.0, 1.0], [0.0, 0.0]]), np.array([[0.0], [1.0]])
+    R = np.array([[0.01]])
+    P = scipy.linalg.solve_continuous_are(A, B, np.eye(2), R)
+    ctl = StateFeedback(dyn, np.linalg.inv(R) @ B.T @ P, clip=True)
+    np.random.seed(0)
+    np.random.uniform(low=-1, high=1, size=(2 ** 16, 2))
+    for _ in range(6012):
+        np.random.uniform(low=-1, high=1, size=(2,))
+    x0 = np.stack([np.random.uniform(low=-1, high=1, size=(2,)) for _ in range(10)])
+    res = dyn.rollout(ctl, x0, 500, integrator="discrete", record_stride=1)
+    xs = res.xs_env.astype(np.float64)                       # [10, 501, 2]
+    ts = np.arange(0, 5, 0.01)
+    hit = (xs[:, 1:] ** 2).sum(-1) <= 1e-4                   # state AFTER step t
+    tto = np.array([ts[np.argmax(h)] if h.any() else 5.0 for h in hit])
+    assert abs(tto.mean() - 4.104) < 0.011                   # one dt of slack for fp32 threshold crossings
+    assert abs(tto.std() - 1.281602122345309) < 0.02
+
+
+# ----------------------------------------------------------------------------------------------------
+# record modes, cost, box, edge cases
+# ----------------------------------------------------------------------------------------------------
+def test_record_stride_cost_and_partial_tail():
+    _cuda()
+    from q_learning_with_hjb_b200.rollout import RunningCost
+    dyn = make_dynamics("quad2d")
+    ctl = make_controller("quad2d_hover", dyn)
+    osys, octl = oracle_pair("quad2d", "quad2d_hover")
+    x0 = _x0("quad2d", 300)                                  # not a multiple of the block size
+    Q = np.diag([1, 2, 3, 0.5, 0.25, 0.125]).astype(np.float64)
+    Qd = Q.copy(); Qd[0, 1] = Qd[1, 0] = 0.3                 # dense path
+    for Qm in (Q, Qd):
+        cost = RunningCost(Qm, np.array([[2.0, 0.1], [0.1, 1.0]]) if Qm is Qd else np.diag([2.0, 1.0]),
+                           np.zeros(6), ctl.uf)
+        ocost = O.OracleCost(np.asarray(cost.Q), np.asarray(cost.R), np.zeros(6), np.asarray(ctl.uf))
+        res = dyn.rollout(ctl, x0, 103, record_stride=10, cost=cost)      # 103 = 10 * 10 + 3: partial tail
+        xs, us, xf, J = O.rollout(osys, octl, x0.astype(np.float64), 103, "euler", record_stride=10, cost=ocost)
+        assert res.xs.shape == (11, 300, 6) and res.us.shape == (10, 300, 2)
+        assert rel_err(res.xs, xs, (2,)) < 1e-5
+        assert rel_err(res.us, us) < 1e-4
+        assert rel_err(res.x_final, xf, (2,)) < 1e-5
+        assert rel_err(res.cost, J) < 1e-5
+
+
+def test_box_termination_freezes_environments():
+    _cuda()
+    from q_learning_with_hjb_b200.rollout import Box, RunningCost
+    dyn = make_dynamics("quad2d")
+    ctl = make_controller("quad2d_hover", dyn)
+    osys, octl = oracle_pair("quad2d", "quad2d_hover")
+    x0 = _x0("quad2d", 256) * np.float32(1.5)
+    lo, hi = np.array([-2, -2, -1.5, -5, -5, -2.0]), np.array([2, 2, 1.5, 5, 5, 2.0])
+    cost = RunningCost(np.eye(6), np.eye(2), np.zeros(6), ctl.uf)
+    res = dyn.rollout(ctl, x0, 200, record_stride=0, cost=cost, box=Box(np.zeros(6), lo, hi))
+    # oracle with the same freeze rule (controller/vhjb.py:176-181)
+    x = x0.astype(np.float64)
+    alive = np.ones(len(x), bool); steps = np.zeros(len(x), int); J = np.zeros(len(x))
+    oc = O.OracleCost(np.eye(6), np.eye(2), np.zeros(6), np.asarray(ctl.uf))
+    for _ in range(200):
+        dx = osys.wrap(x)
+        alive &= ~((dx > hi).any(1) | (dx < lo).any(1))
+        u = octl.control(osys, x)
+        J += np.where(alive, oc.running(osys, x, u) * osys.dt, 0)
+        x = np.where(alive[:, None], osys.step(x, u), x)
+        steps += alive
+    same = res.steps == steps
+    assert same.mean() > 0.99                                 # a state within rounding of the box may differ
+    assert 0 < (steps < 200).sum() < len(x)                   # the test exercises both outcomes
+    assert rel_err(res.x_final[same], x[same], (2,)) < 1e-5
+    assert rel_err(res.cost[same], J[same]) < 1e-5
+
+
+def test_edge_cases_empty_single_and_zero_steps():
+    torch = _cuda()
+    dyn = make_dynamics("cartpole")
+    ctl = make_controller("cartpole_es", dyn)
+    res = dyn.rollout(ctl, np.zeros((0, 4), np.float32), 10)
+    assert res.xs.shape == (11, 0, 4) and res.x_final.shape == (0, 4)
+    x0 = np.float32([[0.1, 3.0, 0, 0]])
+    res = dyn.rollout(ctl, x0, 0)
+    np.testing.assert_array_equal(res.x_final, x0)
+    assert res.xs.shape == (1, 1, 4)
+    res1 = dyn.rollout(ctl, x0[0], 5)
+    assert res1.xs.shape == (6, 1, 4)
+    xd = torch.as_tensor(x0, device="cuda")
+    resd = dyn.rollout(ctl, xd, 5)
+    assert resd.xs.is_cuda and torch.equal(resd.xs.cpu(), torch.as_tensor(res1.xs))
+
+
+def test_unsupported_combination_is_an_error():
+    _cuda()
+    dyn = make_dynamics("quad2d")
+    bad = make_controller("cartpole_es", make_dynamics("cartpole"))
+    bad.dynamics = dyn
+    with pytest.raises(RuntimeError, match="unsupported"):
+        dyn.rollout(bad, np.zeros((4, 6), np.float32), 3)
+    with pytest.raises(ValueError):
+        dyn.rollout(make_controller("quad2d_hover", dyn), np.zeros((4, 6), np.float32), 3, integrator="discrete")
+
+
+# ----------------------------------------------------------------------------------------------------
+# size-independent properties at the BASELINE sizes
+# ----------------------------------------------------------------------------------------------------
+def test_full_size_composition_and_sharding_properties():
+    """C4 (quad-2D hover, 16M envs): a T-step rollout equals two chained T/2-step rollouts BIT-exactly, and a
+    rollout of a batch equals the concatenation of the rollouts of its shards (what multi-GPU sharding relies on)."""
+    torch = _cuda()
+    dyn = make_dynamics("quad2d")
+    dyn.fast_trig = True
+    ctl = make_controller("quad2d_hover", dyn)
+    N = 1 << 24
+    g = torch.Generator(device="cuda").manual_seed(1234)
+    x0 = (torch.rand((N, 6), device="cuda", generator=g) * 2 - 1).contiguous()
+    full = dyn.rollout(ctl, x0, 200, record_stride=0).x_final.clone()
+    half = dyn.rollout(ctl, x0, 100, record_stride=0).x_final.clone()
+    chained = dyn.rollout(ctl, half, 100, record_stride=0).x_final
+    assert torch.equal(full, chained)
+    a = dyn.rollout(ctl, x0[: N // 2].contiguous(), 200, record_stride=0).x_final.clone()
+    b = dyn.rollout(ctl, x0[N // 2:].contiguous(), 200, record_stride=0).x_final
+    assert torch.equal(full, torch.cat([a, b]))
+    assert torch.isfinite(full).all()
+    assert full.abs().max() < 3.0                 # the hover LQR contracts every start in the unit box
+
+
+def test_full_size_cartpole_c1_matches_oracle():
+    """C1 exactly as BASELINE.json states it: 4096 initial states x 500 steps (Euler = reference, and RK4)."""
+    _cuda()
+    dyn = make_dynamics("cartpole")
+    ctl = make_controller("cartpole_lqr", dyn)
+    osys, octl = oracle_pair("cartpole", "cartpole_lqr")
+    x0 = _x0("cartpole", 4096)
+    for integ in ("euler", "rk4"):
+        res = dyn.rollout(ctl, x0, 500, integrator=integ, record_stride=1)
+        xs, us, _, _ = O.rollout(osys, octl, x0.astype(np.float64), 500, integ, record_stride=1)
+        assert rel_err(res.xs, xs, (1,)) < 1e-5
