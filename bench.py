@@ -103,22 +103,26 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
-                                          "-i", str(self.gpu), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+                                          "-i", str(self.gpu), "-lms", "50"], stdout=subprocess.PIPE, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except OSError:
             self.proc = None
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
 
-    def stop(self):
+    def stop(self, t_begin=None, t_end=None):
+        """Summarise the samples that arrived inside [t_begin, t_end] (host wall clock around the timed region)."""
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.12)
+        time.sleep(0.06)
         self.proc.terminate()
+        rows = [r for (ts, r) in self.rows if t_begin is None or (t_begin - 0.02 <= ts <= t_end + 0.08)]
+        if not rows:
+            rows = [r for (_, r) in self.rows]
         sm, smax, reasons = [], None, set()
-        for r in self.rows:
+        for r in rows:
             try:
                 sm.append(float(r[1])); smax = float(r[2])
             except (ValueError, IndexError):
@@ -220,19 +224,20 @@ def run_rollout(args, w, integ):
     fma_peak_tflops = flops.value / (e0.elapsed_time(e1) * 1e-3) / 1e12
 
     # ---- device-resident timing (`value`) ----
+    clocks = ClockSampler(local); clocks.start()
     for _ in range(max(args.warmup, 3)):
         plan.launch(x0_dev)
     barrier()
-    clocks = ClockSampler(local); clocks.start()
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     barrier()
     t_begin = torch.cuda.Event(enable_timing=True); t_end = torch.cuda.Event(enable_timing=True)
+    wall0 = time.time()
     t_begin.record()
     for a, b in evs:
         a.record(); plan.launch(x0_dev); b.record()
     t_end.record()
     barrier()
-    clk = clocks.stop()
+    clk = clocks.stop(wall0, time.time())
     total_ms = t_begin.elapsed_time(t_end)
     kernel_ms = float(np.mean([a.elapsed_time(b) for a, b in evs]))
 
@@ -278,7 +283,8 @@ def run_rollout(args, w, integ):
                                "in MEASURED_PEAKS.json)",
                 "peak_nominal": nominal, "frac_of_nominal": achieved / nominal,
                 "flops_per_env_step": fpe, "flop_model": "SURVEY.md 8d v1",
-                "hbm": {"achieved_gbs": per_gpu * (rec_bytes + 0.0) / 1e9 + (envs * (2 * n + 1) * 4 / (kernel_ms * 1e-3)) / 1e9,
+                # algorithmic HBM bytes: x0 read + x_final/cost write per env, plus the recorded trajectory
+                "hbm": {"achieved_gbs": (per_gpu * rec_bytes + envs * (2 * n + 1) * 4 / (kernel_ms * 1e-3)) / 1e9,
                         "peak_gbs": hbm_peak, "peak_source": "MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback"}}
         cpu = None
         if world == 1 and not args.no_cpu_baseline:

@@ -244,6 +244,43 @@ class OracleController:
         raise ValueError(self.kind)
 
 
+def control_scale(sys: OracleSystem, ctl: OracleController, x: np.ndarray) -> np.ndarray:
+    """Per-sample magnitude of the largest intermediate term of the control law, [B] — the scale against which
+    an fp32 evaluation of the law can be expected to be accurate (cancellation between large terms is a property
+    of the law, not of the implementation).  Used only to normalise errors in the parity tests."""
+    x = np.asarray(x, dtype=np.float64)
+    K = np.abs(np.asarray(ctl.K, dtype=np.float64))
+    if ctl.kind == "feedback":
+        dx = np.abs(sys.wrap(x - ctl.xf))
+        return (dx @ K.T + np.abs(ctl.uf)).max(axis=1)
+    if ctl.kind == "cartpole_es":
+        p = sys.par
+        xf = np.array([0.0, np.pi, 0.0, 0.0])
+        lqr = (np.abs(sys.wrap(x - xf)) @ K.T)[:, 0]
+        E = 0.5 * x[:, 3] ** 2 + 1 + 1
+        Ke = np.abs(np.asarray(ctl.Ke, dtype=np.float64))
+        a1 = Ke[0] * np.abs(x[:, 0]) + Ke[1] * np.abs(x[:, 2]) + Ke[2] * E * np.abs(x[:, 3])
+        a2 = a1 / p["l"] + p["g"] / p["l"]
+        es = (p["mc"] + p["mp"]) * a1 + p["mp"] * p["l"] * a2 + p["mp"] * p["l"] * x[:, 3] ** 2
+        return np.maximum(lqr, es)
+    if ctl.kind == "acrobot_es":
+        xf = np.array([np.pi, 0.0, 0.0, 0.0])
+        d = x - xf
+        dx = np.abs(np.concatenate([wrap_angle(d[:, :2]), d[:, 2:]], axis=1))
+        lqr = (dx @ K.T)[:, 0]
+        M, Cdq, G = sys.acrobot_terms(x)
+        pp = sys.par
+        a = pp["m2"] * pp["l1"] * pp["l2"] / 2
+        Emag = 0.5 * np.abs(M[:, 0, 0]) * x[:, 2] ** 2 + 0.5 * pp["I2"] * x[:, 3] ** 2 + np.abs(M[:, 0, 1] * x[:, 2] * x[:, 3]) \
+            + 200.0 + 100.0
+        Ks = np.abs(np.asarray(ctl.Ke, dtype=np.float64))
+        a2 = Ks[0] * np.pi + Ks[1] * np.abs(x[:, 3]) + Ks[2] * Emag * np.abs(x[:, 2])
+        hmag = np.abs(G) + np.abs(a * x[:, 3:4] * (2 * np.abs(x[:, 2:3]) + np.abs(x[:, 3:4]))) + np.abs(a * x[:, 2:3] ** 2)
+        sw = np.abs(M[:, 1, 1]) * a2 + hmag[:, 1] + hmag[:, 0]
+        return np.maximum(lqr, sw)
+    raise ValueError(ctl.kind)
+
+
 # ------------------------------------------------------------------------------------------------
 # closed-loop rollout
 # ------------------------------------------------------------------------------------------------
@@ -280,7 +317,7 @@ def rollout(sys: OracleSystem, ctl: OracleController, x0: np.ndarray, steps: int
         u = ctl.control(sys, x)
         if cost is not None:
             J += cost.running(sys, x, u) * sys.dt
-        if record_stride and t % record_stride == 0:
+        if record_stride and t % record_stride == 0 and t // record_stride < steps // record_stride:
             us.append(u.copy())
         x = sys.step(x, u, integrator)
         if record_stride and (t + 1) % record_stride == 0:

@@ -1,0 +1,14 @@
+#!/bin/bash
+# ncu evidence for the rollout kernel (run under gpurun, one GPU).  Each ncu pass runs only after the same
+# command has exited 0 without ncu.  Outputs land in gpurun_out/ (copy summaries into profiles/).
+set -u
+CMD="python bench.py --steps 2 --warmup 3 --no-cpu-baseline ${BENCH_ARGS:-}"
+TAG=${TAG:-rollout}
+$CMD > gpurun_out/${TAG}_plain.log 2>&1 &&
+ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv \
+    --log-file gpurun_out/${TAG}_launches.csv $CMD > gpurun_out/${TAG}_ncu_launches.log 2>&1
+$CMD > gpurun_out/${TAG}_plain2.log 2>&1 &&
+ncu --set full --clock-control none --import-source on -k regex:rollout_kernel -s 3 -c 1 \
+    -o gpurun_out/${TAG}_full -f $CMD > gpurun_out/${TAG}_ncu_full.log 2>&1
+tail -2 gpurun_out/${TAG}_plain.log
+tail -3 gpurun_out/${TAG}_ncu_full.log

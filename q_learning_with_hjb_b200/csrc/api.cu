@@ -20,6 +20,28 @@ static bool dims_ok(const hjb_system* s) {
   }
 }
 
+// indices of the angle components per system kind (states_wrap)
+static int angle_indices(int kind, int* idx) {
+  switch (kind) {
+    case HJB_SYS_CARTPOLE: idx[0] = 1; return 1;
+    case HJB_SYS_ACROBOT: idx[0] = 0; idx[1] = 1; return 2;
+    case HJB_SYS_QUAD2D: idx[0] = 2; return 1;
+    case HJB_SYS_QUAD10D: idx[0] = 3; idx[1] = 4; return 2;
+    default: return 0;
+  }
+}
+static bool is_angle(int kind, int i) {
+  int idx[2];
+  const int na = angle_indices(kind, idx);
+  for (int k = 0; k < na; ++k)
+    if (idx[k] == i) return true;
+  return false;
+}
+static double wrap_pi_host(double a) {
+  const double two_pi = 6.283185307179586476925286766559;
+  return a - two_pi * std::floor((a + 0.5 * two_pi) / two_pi);
+}
+
 static void make_dev_sys(const hjb_system* s, DevSys& d) {
   std::memset(&d, 0, sizeof(d));
   d.n = s->n;
@@ -67,9 +89,22 @@ static void make_dev_sys(const hjb_system* s, DevSys& d) {
   }
 }
 
-static void make_dev_ctl(const hjb_system* s, const hjb_control* c, DevCtl& d) {
+// Fills the controller block AND the internal-coordinate angle offsets of `ds` (FEEDBACK: the goal angles).
+static void make_dev_ctl(const hjb_system* s, const hjb_control* c, DevSys& ds, DevCtl& d) {
   std::memset(&d, 0, sizeof(d));
   d.clip = c->clip;
+  ds.aoff[0] = ds.aoff[1] = 0.f;
+  if (c->kind == HJB_CTL_FEEDBACK) {
+    int idx[2];
+    const int na = angle_indices(s->kind, idx);
+    for (int k = 0; k < na; ++k) ds.aoff[k] = c->xf[idx[k]];
+    for (int k = 0; k < s->m; ++k) {
+      double acc = c->uf[k];
+      for (int i = 0; i < s->n; ++i)
+        if (!is_angle(s->kind, i)) acc += (double)c->K[k * s->n + i] * (double)c->xf[i];
+      d.u0[k] = (float)acc;
+    }
+  }
   std::memcpy(d.K, c->K, sizeof(d.K));
   std::memcpy(d.P, c->P, sizeof(d.P));
   std::memcpy(d.xf, c->xf, sizeof(d.xf));
@@ -92,8 +127,44 @@ static void make_dev_ctl(const hjb_system* s, const hjb_control* c, DevCtl& d) {
   }
 }
 
+static void make_dev_cost(const hjb_system* s, const hjb_cost* c, const DevSys& ds, DevCost& d) {
+  std::memset(&d, 0, sizeof(d));
+  std::memcpy(d.Q, c->Q, sizeof(d.Q));
+  std::memcpy(d.R, c->R, sizeof(d.R));
+  std::memcpy(d.xf, c->xf, sizeof(d.xf));
+  std::memcpy(d.uf, c->uf, sizeof(d.uf));
+  int idx[2];
+  const int na = angle_indices(s->kind, idx);
+  for (int k = 0; k < na; ++k) d.dang[k] = (float)wrap_pi_host((double)ds.aoff[k] - (double)c->xf[idx[k]]);
+  for (int i = 0; i < s->n; ++i) {
+    const double q = c->Q[i * s->n + i];
+    d.sq[i] = (float)std::sqrt(q > 0 ? q : 0.0);
+    d.c0[i] = is_angle(s->kind, i) ? 0.f : (float)(-std::sqrt(q > 0 ? q : 0.0) * (double)c->xf[i]);
+  }
+  for (int k = 0; k < s->m; ++k) {
+    const double r = c->R[k * s->m + k];
+    d.sr[k] = (float)std::sqrt(r > 0 ? r : 0.0);
+    d.r0[k] = (float)(-std::sqrt(r > 0 ? r : 0.0) * (double)c->uf[k]);
+  }
+}
+
+static void make_dev_box(const hjb_system* s, const hjb_rollout_opts* o, const DevSys& ds, DevBox& d) {
+  std::memset(&d, 0, sizeof(d));
+  std::memcpy(d.xf, o->box_xf, sizeof(d.xf));
+  std::memcpy(d.lo, o->box_lo, sizeof(d.lo));
+  std::memcpy(d.hi, o->box_hi, sizeof(d.hi));
+  int idx[2];
+  const int na = angle_indices(s->kind, idx);
+  for (int k = 0; k < na; ++k) d.dang[k] = (float)wrap_pi_host((double)ds.aoff[k] - (double)o->box_xf[idx[k]]);
+}
+
+// COST_DIAG needs diagonal Q, R with non-negative entries (it uses their square roots)
 static int cost_mode(const hjb_system* s, const hjb_cost* c) {
   if (!c) return COST_NONE;
+  for (int i = 0; i < s->n; ++i)
+    if (c->Q[i * s->n + i] < 0.f) return COST_DENSE;
+  for (int i = 0; i < s->m; ++i)
+    if (c->R[i * s->m + i] < 0.f) return COST_DENSE;
   for (int i = 0; i < s->n; ++i)
     for (int j = 0; j < s->n; ++j)
       if (i != j && c->Q[i * s->n + j] != 0.f) return COST_DENSE;
@@ -136,18 +207,9 @@ int hjb_rollout(const hjb_system* sys, const hjb_control* ctl, const hjb_cost* c
   RolloutArgs a;
   std::memset(&a, 0, sizeof(a));
   make_dev_sys(sys, a.sys);
-  make_dev_ctl(sys, ctl, a.ctl);
-  if (cost_spec) {
-    std::memcpy(a.cost.Q, cost_spec->Q, sizeof(a.cost.Q));
-    std::memcpy(a.cost.R, cost_spec->R, sizeof(a.cost.R));
-    std::memcpy(a.cost.xf, cost_spec->xf, sizeof(a.cost.xf));
-    std::memcpy(a.cost.uf, cost_spec->uf, sizeof(a.cost.uf));
-  }
-  if (opts->box_enabled) {
-    std::memcpy(a.box.xf, opts->box_xf, sizeof(a.box.xf));
-    std::memcpy(a.box.lo, opts->box_lo, sizeof(a.box.lo));
-    std::memcpy(a.box.hi, opts->box_hi, sizeof(a.box.hi));
-  }
+  make_dev_ctl(sys, ctl, a.sys, a.ctl);
+  if (cost_spec) make_dev_cost(sys, cost_spec, a.sys, a.cost);
+  if (opts->box_enabled) make_dev_box(sys, opts, a.sys, a.box);
   a.x0 = x0; a.xs = xs; a.us = us; a.x_final = x_final; a.cost_out = cost; a.steps_out = steps;
   a.N = N; a.T = T;
   a.stride = opts->record_stride > 0 ? opts->record_stride : 1;
@@ -207,7 +269,7 @@ int hjb_control_efforts(const hjb_system* sys, const hjb_control* ctl, int32_t f
   if (!x || !u) return HJB_ERR_BAD_ARG;
   CtlArgs a;
   make_dev_sys(sys, a.sys);
-  make_dev_ctl(sys, ctl, a.ctl);
+  make_dev_ctl(sys, ctl, a.sys, a.ctl);
   a.x = x; a.u = u; a.B = B;
   return to_status(step_control(sys->kind, ctl->kind, a, fast_trig != 0, (cudaStream_t)stream));
 }

@@ -31,10 +31,13 @@ struct DevSys {
   //  QUAD10D  c = {g, kT/m, n0}
   float c[8];
   float A[16], B[8];  // LINEAR
+  // internal-coordinate angle offsets (see systems.cuh): the goal angles of a FEEDBACK controller, else 0
+  float aoff[2];
 };
 
 struct DevCtl {
   int clip;
+  float u0[HJB_MAX_M];  // FEEDBACK: uf + sum_{i not an angle} K_i xf_i (host-folded in double)
   float K[HJB_MAX_M * HJB_MAX_N];
   float P[16];
   float xf[HJB_MAX_N], uf[HJB_MAX_M];
@@ -47,10 +50,15 @@ struct DevCost {
   float Q[HJB_MAX_N * HJB_MAX_N];
   float R[HJB_MAX_M * HJB_MAX_M];
   float xf[HJB_MAX_N], uf[HJB_MAX_M];
+  // diagonal fast path: l = sum_i (sq_i z_i + c0_i)^2 + sum_k (sr_k u_k + r0_k)^2 with sq = sqrt(Q_ii),
+  // c0 = -sq xf (0 on angle components), sr = sqrt(R_kk), r0 = -sr uf
+  float sq[HJB_MAX_N], c0[HJB_MAX_N], sr[HJB_MAX_M], r0[HJB_MAX_M];
+  float dang[2];  // aoff - xf on the angle components (0 when the cost and the controller share the goal)
 };
 
 struct DevBox {
   float xf[HJB_MAX_N], lo[HJB_MAX_N], hi[HJB_MAX_N];
+  float dang[2];  // aoff - xf on the angle components
 };
 
 // ---------------------------------------------------------------------------------------------

@@ -28,21 +28,51 @@ struct RolloutArgs {
   int32_t n_rec;   // T / stride recorded intervals
 };
 
+// error coordinate of internal state z w.r.t. a goal whose non-angle part is xf and whose angle part differs
+// from the internal offset by dang: d_i = z_i - xf_i, d_th = wrap(z_th + dang) (no wrap needed when dang == 0)
+template <class S>
+__device__ __forceinline__ void error_coords(const float* z, const float* xf, const float* dang, float* d) {
+#pragma unroll
+  for (int i = 0; i < S::N; ++i) d[i] = z[i] - xf[i];
+#pragma unroll
+  for (int k = 0; k < S::NANG; ++k) {
+    const int i = S::ang(k);
+    d[i] = z[i];
+    if (dang[k] != 0.f) d[i] = wrap_pi(z[i] + dang[k]);
+  }
+}
+
+// l(x, u) = dx^T Q dx + (u - uf)^T R (u - uf)
 template <class S, int COST>
-__device__ __forceinline__ float running_cost(const DevCost& pc, const float* x, const float* u) {
-  float dx[S::N], du[S::M];
-#pragma unroll
-  for (int i = 0; i < S::N; ++i) dx[i] = x[i] - pc.xf[i];
-  S::wrap(dx);
-#pragma unroll
-  for (int k = 0; k < S::M; ++k) du[k] = u[k] - pc.uf[k];
-  float l = 0.f;
+__device__ __forceinline__ float running_cost(const DevCost& pc, const float* z, const float* u, float l) {
   if constexpr (COST == COST_DIAG) {
 #pragma unroll
-    for (int i = 0; i < S::N; ++i) l = fmaf(pc.Q[i * S::N + i] * dx[i], dx[i], l);
+    for (int i = 0; i < S::N; ++i) {
+      bool is_ang = false;
 #pragma unroll
-    for (int k = 0; k < S::M; ++k) l = fmaf(pc.R[k * S::M + k] * du[k], du[k], l);
+      for (int k = 0; k < S::NANG; ++k) is_ang = is_ang || (S::ang(k) == i);
+      float y;
+      if (is_ang) {
+        float d = z[i];
+#pragma unroll
+        for (int k = 0; k < S::NANG; ++k)
+          if (S::ang(k) == i && pc.dang[k] != 0.f) d = wrap_pi(z[i] + pc.dang[k]);
+        y = d * pc.sq[i];
+      } else {
+        y = fmaf(z[i], pc.sq[i], pc.c0[i]);
+      }
+      l = fmaf(y, y, l);
+    }
+#pragma unroll
+    for (int k = 0; k < S::M; ++k) {
+      const float y = fmaf(u[k], pc.sr[k], pc.r0[k]);
+      l = fmaf(y, y, l);
+    }
   } else {
+    float dx[S::N], du[S::M];
+    error_coords<S>(z, pc.xf, pc.dang, dx);
+#pragma unroll
+    for (int k = 0; k < S::M; ++k) du[k] = u[k] - pc.uf[k];
 #pragma unroll
     for (int i = 0; i < S::N; ++i) {
       float row = 0.f;
@@ -61,7 +91,7 @@ __device__ __forceinline__ float running_cost(const DevCost& pc, const float* x,
   return l;
 }
 
-// one integration step of Dynamics.simulate AFTER the clip: x <- wrap(step(x, u))
+// one integration step of Dynamics.simulate AFTER the clip, on the internal state: z <- wrap(step(z, u))
 template <class S, int INTEG>
 __device__ __forceinline__ void integrate(const DevSys& ps, float* x, const typename S::Trig& tr0, const float* u) {
   constexpr int N = S::N;
@@ -82,29 +112,27 @@ __device__ __forceinline__ void integrate(const DevSys& ps, float* x, const type
     S::xdot(ps, x, tr0, u, k);
 #pragma unroll
     for (int i = 0; i < N; ++i) { acc[i] = k[i]; xt[i] = fmaf(hh, k[i], x[i]); }
-    S::trig(xt, tr);
+    S::trig(ps, xt, tr);
     S::xdot(ps, xt, tr, u, k);
 #pragma unroll
     for (int i = 0; i < N; ++i) { acc[i] = fmaf(2.f, k[i], acc[i]); xt[i] = fmaf(hh, k[i], x[i]); }
-    S::trig(xt, tr);
+    S::trig(ps, xt, tr);
     S::xdot(ps, xt, tr, u, k);
 #pragma unroll
     for (int i = 0; i < N; ++i) { acc[i] = fmaf(2.f, k[i], acc[i]); xt[i] = fmaf(h, k[i], x[i]); }
-    S::trig(xt, tr);
+    S::trig(ps, xt, tr);
     S::xdot(ps, xt, tr, u, k);
     const float h6 = ps.dt * (1.0f / 6.0f);
 #pragma unroll
     for (int i = 0; i < N; ++i) x[i] = fmaf(h6, acc[i] + k[i], x[i]);
   }
-  S::wrap(x);
+  wrap_state<S>(x);
 }
 
 template <class S>
-__device__ __forceinline__ bool inside_box(const DevBox& b, const float* x) {
+__device__ __forceinline__ bool inside_box(const DevBox& b, const float* z) {
   float dx[S::N];
-#pragma unroll
-  for (int i = 0; i < S::N; ++i) dx[i] = x[i] - b.xf[i];
-  S::wrap(dx);
+  error_coords<S>(z, b.xf, b.dang, dx);
   bool in = true;
 #pragma unroll
   for (int i = 0; i < S::N; ++i) in = in && !(dx[i] > b.hi[i]) && !(dx[i] < b.lo[i]);
@@ -117,57 +145,67 @@ __global__ void __launch_bounds__(256) rollout_kernel(const __grid_constant__ Ro
   const int64_t env = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (env >= a.N) return;
 
-  float x[N];
-  load_row<N>(a.x0, env, x);
-  float J = 0.f;
+  float z[N];  // internal state
+  {
+    float x[N];
+    load_row<N>(a.x0, env, x);
+    if constexpr (REC) {
+      if (a.xs) store_row<N>(a.xs, env, x);
+    }
+    to_internal<S>(a.sys, x, z);
+  }
+  float J = 0.f;  // sum of l (times dt at the end)
   int32_t nsteps = 0;
   bool alive = true;
-
-  int64_t rec = 0;      // next trajectory slot
+  int64_t rec = 1;      // next trajectory slot
   int32_t phase = 0;    // steps since the last recorded state
-  if constexpr (REC) {
-    if (a.xs) store_row<N>(a.xs, env, x);
-    rec = 1;
-  }
 
   for (int32_t t = 0; t < a.T; ++t) {
-    if constexpr (BOX) alive = alive && inside_box<S>(a.box, x);
+    if constexpr (BOX) alive = alive && inside_box<S>(a.box, z);
     typename S::Trig tr;
-    S::trig(x, tr);
+    S::trig(a.sys, z, tr);
     float u[M];
-    C::template control<S>(a.sys, a.ctl, x, tr, u);
+    C::template control<S>(a.sys, a.ctl, z, tr, u);
     if constexpr (REC) {
       if (phase == 0 && a.us && rec <= a.n_rec) store_row<M>(a.us, (rec - 1) * a.N + env, u);
     }
-    float xn[N];
-#pragma unroll
-    for (int i = 0; i < N; ++i) xn[i] = x[i];
-    float l = 0.f;
-    if constexpr (COST != COST_NONE) l = running_cost<S, COST>(a.cost, x, u);
-    clip_u<S>(a.sys, u);  // Dynamics.simulate's own clip (dynamics_basic.py:118)
-    integrate<S, INTEG>(a.sys, xn, tr, u);
     if constexpr (BOX) {
+      float zn[N];
+#pragma unroll
+      for (int i = 0; i < N; ++i) zn[i] = z[i];
+      float l = 0.f;
+      if constexpr (COST != COST_NONE) l = running_cost<S, COST>(a.cost, z, u, 0.f);
+      clip_u<S>(a.sys, u);
+      integrate<S, INTEG>(a.sys, zn, tr, u);
       if (alive) {
 #pragma unroll
-        for (int i = 0; i < N; ++i) x[i] = xn[i];
-        J = fmaf(l, a.sys.dt, J);
+        for (int i = 0; i < N; ++i) z[i] = zn[i];
+        J += l;
         ++nsteps;
       }
     } else {
-#pragma unroll
-      for (int i = 0; i < N; ++i) x[i] = xn[i];
-      if constexpr (COST != COST_NONE) J = fmaf(l, a.sys.dt, J);
+      if constexpr (COST != COST_NONE) J = running_cost<S, COST>(a.cost, z, u, J);
+      clip_u<S>(a.sys, u);  // Dynamics.simulate's own clip (dynamics_basic.py:118)
+      integrate<S, INTEG>(a.sys, z, tr, u);
     }
     if constexpr (REC) {
       if (++phase == a.stride) {
         phase = 0;
-        if (a.xs) store_row<N>(a.xs, rec * a.N + env, x);
+        if (a.xs) {
+          float x[N];
+          to_external<S>(a.sys, z, x);
+          store_row<N>(a.xs, rec * a.N + env, x);
+        }
         ++rec;
       }
     }
   }
-  if (a.x_final) store_row<N>(a.x_final, env, x);
-  if (a.cost_out) a.cost_out[env] = J;
+  if (a.x_final) {
+    float x[N];
+    to_external<S>(a.sys, z, x);
+    store_row<N>(a.x_final, env, x);
+  }
+  if (a.cost_out) a.cost_out[env] = J * a.sys.dt;
   if (a.steps_out) a.steps_out[env] = BOX ? nsteps : a.T;
 }
 

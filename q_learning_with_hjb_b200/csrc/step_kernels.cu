@@ -13,12 +13,16 @@ __global__ void __launch_bounds__(256) dynamics_kernel(const __grid_constant__ D
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= a.B) return;
   float x[N], u[M];
-  load_row<N>(a.x, i, x);
+  {
+    float xr[N];
+    load_row<N>(a.x, i, xr);
+    to_internal<S>(a.sys, xr, x);   // aoff = 0 here: only wraps the angles (f, g are periodic in them)
+  }
 #pragma unroll
   for (int k = 0; k < M; ++k) u[k] = 0.f;
   if (a.u) load_row<M>(a.u, i, u);
   typename S::Trig tr;
-  S::trig(x, tr);
+  S::trig(a.sys, x, tr);
   if (a.f || a.g) {
     float f[N], g[N * M];
     S::fg(a.sys, x, tr, f, g);
@@ -33,7 +37,9 @@ __global__ void __launch_bounds__(256) dynamics_kernel(const __grid_constant__ D
   if (a.x_next) {
     clip_u<S>(a.sys, u);           // simulate clips (dynamics_basic.py:118)
     integrate<S, INTEG>(a.sys, x, tr, u);
-    store_row<N>(a.x_next, i, x);
+    float xo[N];
+    to_external<S>(a.sys, x, xo);
+    store_row<N>(a.x_next, i, xo);
   }
 }
 
@@ -86,9 +92,13 @@ __global__ void __launch_bounds__(256) control_kernel(const __grid_constant__ Ct
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= a.B) return;
   float x[S::N], u[S::M];
-  load_row<S::N>(a.x, i, x);
+  {
+    float xr[S::N];
+    load_row<S::N>(a.x, i, xr);
+    to_internal<S>(a.sys, xr, x);
+  }
   typename S::Trig tr;
-  S::trig(x, tr);
+  S::trig(a.sys, x, tr);
   C::template control<S>(a.sys, a.ctl, x, tr, u);
   store_row<S::M>(a.u, i, u);
 }
@@ -138,7 +148,7 @@ __global__ void __launch_bounds__(256) wrap_kernel(WrapArgs a) {
   if (i >= a.B) return;
   float x[S::N];
   load_row<S::N>(a.x, i, x);
-  S::wrap(x);
+  wrap_state<S>(x);
   store_row<S::N>(a.x, i, x);
 }
 

@@ -1,13 +1,19 @@
 // Control-affine systems x' = f(x) + g(x) u and the model-based controllers, as device functions.
 //
+// INTERNAL COORDINATES.  Kernels keep a state z in registers: z_i = x_i for the non-angle components and
+// z_th = wrap(x_th - aoff_th) for the angle components, where aoff (DevSys::aoff) is the goal angle of a
+// feedback controller (0 otherwise).  Everything downstream is periodic in the angles, so this is the same
+// dynamical system, but (i) the controller's and the cost's error coordinate wrap(x - xf) IS z_th — no
+// subtraction, no second wrap per step — and (ii) near the goal z_th is small, so fp32 keeps ~1e-10 absolute
+// resolution where the raw angle (e.g. th ~ pi for the cart-pole) would be quantised at 2.4e-7.
+// x is materialised (to_external) only when a state is written out.
+//
 // Each system S<FAST> provides
-//   N, M                 state / control dimension (compile time -> everything stays in registers)
-//   Trig                 sin/cos of the state's angles, computed once per evaluation point and shared
-//                        between the control law and the dynamics of the same state
-//   trig(x)              fills Trig
-//   xdot(p, x, tr, u, d) d = f(x) + g(x) u with g's structural zeros skipped (the fused fast path)
-//   fg(p, x, tr, f, g)   explicit f [N] and g [N*M] (row-major) for the API / the vhjb pass
-//   wrap(x)              states_wrap in place
+//   N, M, NANG, ang(k)   dimensions; indices of the angle components
+//   Trig / trig(p, z, t) sin/cos of the state's angles, computed once per evaluation point and shared between
+//                        the control law and the dynamics of the same state
+//   xdot(p, z, tr, u, d) d = f + g u with g's structural zeros skipped (the fused fast path)
+//   fg(p, z, tr, f, g)   explicit f [N] and g [N*M] (row-major) for the API / the vhjb pass
 // Reference formulas: dynamics/{linear,cartpole,acrobot,quadrotors}.py through the manipulator form of
 // dynamics/dynamics_basic.py:64-94, with the 2x2 M^-1 written in closed form.
 #pragma once
@@ -15,16 +21,40 @@
 
 namespace hjb {
 
+// states_wrap on the angle components (cartpole.py:52-64, acrobot.py:72-81, quadrotors.py:48-70,151-170)
+template <class S>
+__device__ __forceinline__ void wrap_state(float* z) {
+#pragma unroll
+  for (int k = 0; k < S::NANG; ++k) z[S::ang(k)] = wrap_pi(z[S::ang(k)]);
+}
+template <class S>
+__device__ __forceinline__ void to_internal(const DevSys& p, const float* x, float* z) {
+#pragma unroll
+  for (int i = 0; i < S::N; ++i) z[i] = x[i];
+#pragma unroll
+  for (int k = 0; k < S::NANG; ++k) z[S::ang(k)] = wrap_pi(x[S::ang(k)] - p.aoff[k]);
+}
+// x_th = wrap(z_th + aoff); with aoff == 0 the state is returned bit-for-bit
+template <class S>
+__device__ __forceinline__ void to_external(const DevSys& p, const float* z, float* x) {
+#pragma unroll
+  for (int i = 0; i < S::N; ++i) x[i] = z[i];
+#pragma unroll
+  for (int k = 0; k < S::NANG; ++k)
+    if (p.aoff[k] != 0.f) x[S::ang(k)] = wrap_pi(z[S::ang(k)] + p.aoff[k]);
+}
+
 // ------------------------------------------------------------------------------------------------
 // LINEAR  (dynamics/linear.py:20-22)   f = A x, g = B, wrap = identity
 // ------------------------------------------------------------------------------------------------
 template <int N_, int M_, bool FAST>
 struct LinearSys {
-  static constexpr int N = N_, M = M_;
+  static constexpr int N = N_, M = M_, NANG = 0;
   static constexpr bool kFast = FAST;
   static constexpr int KIND = HJB_SYS_LINEAR;
+  static __device__ __forceinline__ constexpr int ang(int) { return 0; }
   struct Trig {};
-  static __device__ __forceinline__ void trig(const float*, Trig&) {}
+  static __device__ __forceinline__ void trig(const DevSys&, const float*, Trig&) {}
   // A x + B u   (also the exact-ZOH update when A, B are the discretised matrices)
   static __device__ __forceinline__ void xdot(const DevSys& p, const float* x, const Trig&, const float* u, float* d) {
 #pragma unroll
@@ -48,21 +78,23 @@ struct LinearSys {
       for (int k = 0; k < M; ++k) g[i * M + k] = p.B[i * M + k];
     }
   }
-  static __device__ __forceinline__ void wrap(float*) {}
 };
 
 // ------------------------------------------------------------------------------------------------
 // CARTPOLE  (dynamics/cartpole.py:19-64)   x = [p, th, dp, dth]
 //   M = [[M11, k c],[k c, M22]], C dq = [-k dth^2 s, 0], G = [0, gamma s], B = [1, 0]
-//   c = {M11, kappa, M22, gamma, M11*M22}
+//   c = {M11, kappa, M22, gamma, M11*M22, 1/l, g/l}
 // ------------------------------------------------------------------------------------------------
 template <bool FAST>
 struct CartpoleSys {
-  static constexpr int N = 4, M = 1;
+  static constexpr int N = 4, M = 1, NANG = 1;
   static constexpr bool kFast = FAST;
   static constexpr int KIND = HJB_SYS_CARTPOLE;
+  static __device__ __forceinline__ constexpr int ang(int) { return 1; }
   struct Trig { float s, c; };
-  static __device__ __forceinline__ void trig(const float* x, Trig& t) { sincos_<FAST>(x[1], t.s, t.c); }
+  static __device__ __forceinline__ void trig(const DevSys& p, const float* z, Trig& t) {
+    sincos_<FAST>(z[1] + p.aoff[0], t.s, t.c);
+  }
   static __device__ __forceinline__ void xdot(const DevSys& p, const float* x, const Trig& t, const float* u, float* d) {
     const float m12 = p.c[1] * t.c;
     const float inv = rcp_<FAST>(fmaf(-m12, m12, p.c[4]));
@@ -87,7 +119,6 @@ struct CartpoleSys {
     g[2] = p.c[2] * inv;
     g[3] = -m12 * inv;
   }
-  static __device__ __forceinline__ void wrap(float* x) { x[1] = wrap_pi(x[1]); }
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -98,14 +129,16 @@ struct CartpoleSys {
 // ------------------------------------------------------------------------------------------------
 template <bool FAST>
 struct AcrobotSys {
-  static constexpr int N = 4, M = 1;
+  static constexpr int N = 4, M = 1, NANG = 2;
   static constexpr bool kFast = FAST;
   static constexpr int KIND = HJB_SYS_ACROBOT;
+  static __device__ __forceinline__ constexpr int ang(int k) { return k; }
   struct Trig { float s1, c1, s2, c2, s12, c12; };
-  static __device__ __forceinline__ void trig(const float* x, Trig& t) {
-    sincos_<FAST>(x[0], t.s1, t.c1);
-    sincos_<FAST>(x[1], t.s2, t.c2);
-    sincos_<FAST>(x[0] + x[1], t.s12, t.c12);
+  static __device__ __forceinline__ void trig(const DevSys& p, const float* z, Trig& t) {
+    const float q1 = z[0] + p.aoff[0], q2 = z[1] + p.aoff[1];
+    sincos_<FAST>(q1, t.s1, t.c1);
+    sincos_<FAST>(q2, t.s2, t.c2);
+    sincos_<FAST>(q1 + q2, t.s12, t.c12);
   }
   struct Terms { float m11, m12, m22, h1, h2; };  // h = C dq + G
   static __device__ __forceinline__ void terms(const DevSys& p, const float* x, const Trig& t, Terms& r) {
@@ -151,10 +184,6 @@ struct AcrobotSys {
     e = fmaf(-p.c[4], t.c12, e);
     return e;
   }
-  static __device__ __forceinline__ void wrap(float* x) {
-    x[0] = wrap_pi(x[0]);
-    x[1] = wrap_pi(x[1]);
-  }
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -162,11 +191,14 @@ struct AcrobotSys {
 // ------------------------------------------------------------------------------------------------
 template <bool FAST>
 struct Quad2DSys {
-  static constexpr int N = 6, M = 2;
+  static constexpr int N = 6, M = 2, NANG = 1;
   static constexpr bool kFast = FAST;
   static constexpr int KIND = HJB_SYS_QUAD2D;
+  static __device__ __forceinline__ constexpr int ang(int) { return 2; }
   struct Trig { float s, c; };
-  static __device__ __forceinline__ void trig(const float* x, Trig& t) { sincos_<FAST>(x[2], t.s, t.c); }
+  static __device__ __forceinline__ void trig(const DevSys& p, const float* z, Trig& t) {
+    sincos_<FAST>(z[2] + p.aoff[0], t.s, t.c);
+  }
   static __device__ __forceinline__ void xdot(const DevSys& p, const float* x, const Trig& t, const float* u, float* d) {
     const float sm = (u[0] + u[1]) * p.c[1];
     d[0] = x[3];
@@ -186,7 +218,6 @@ struct Quad2DSys {
     g[10] = p.c[2];
     g[11] = -p.c[2];
   }
-  static __device__ __forceinline__ void wrap(float* x) { x[2] = wrap_pi(x[2]); }
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -194,13 +225,14 @@ struct Quad2DSys {
 // ------------------------------------------------------------------------------------------------
 template <bool FAST>
 struct Quad10DSys {
-  static constexpr int N = 10, M = 3;
+  static constexpr int N = 10, M = 3, NANG = 2;
   static constexpr bool kFast = FAST;
   static constexpr int KIND = HJB_SYS_QUAD10D;
+  static __device__ __forceinline__ constexpr int ang(int k) { return 3 + k; }
   struct Trig { float tx, ty; };
-  static __device__ __forceinline__ void trig(const float* x, Trig& t) {
-    t.tx = tan_<FAST>(x[3]);
-    t.ty = tan_<FAST>(x[4]);
+  static __device__ __forceinline__ void trig(const DevSys& p, const float* z, Trig& t) {
+    t.tx = tan_<FAST>(z[3] + p.aoff[0]);
+    t.ty = tan_<FAST>(z[4] + p.aoff[1]);
   }
   static __device__ __forceinline__ void xdot(const DevSys& p, const float* x, const Trig& t, const float* u, float* d) {
 #pragma unroll
@@ -225,15 +257,11 @@ struct Quad10DSys {
     g[8 * 3 + 1] = p.c[2];
     g[9 * 3 + 2] = p.c[2];
   }
-  static __device__ __forceinline__ void wrap(float* x) {
-    x[3] = wrap_pi(x[3]);
-    x[4] = wrap_pi(x[4]);
-  }
 };
 
 // ------------------------------------------------------------------------------------------------
-// controllers: control(ps, pc, x, tr, u) writes the controller OUTPUT (get_control_efforts), i.e. before
-// Dynamics.simulate's own clip.
+// controllers: control(ps, pc, z, tr, u) writes the controller OUTPUT (get_control_efforts), i.e. before
+// Dynamics.simulate's own clip.  z is the internal state.
 // ------------------------------------------------------------------------------------------------
 template <class S>
 __device__ __forceinline__ void clip_u(const DevSys& ps, float* u) {
@@ -242,29 +270,27 @@ __device__ __forceinline__ void clip_u(const DevSys& ps, float* u) {
 }
 
 // u = -K wrap(x - xf) + uf [clipped]   (lqr.py:29-30; cartpole_balancing.ipynb cell 4:24-25;
-// quadrotors_model_based_controller.py:36-38, 73-75)
+// quadrotors_model_based_controller.py:36-38, 73-75).
+// With aoff = xf's angles the wrapped error IS z on the angle components; on the others the subtraction is
+// folded on the host: u = u0 - K z, u0 = uf + sum_{i not an angle} K_i xf_i  (n FMAs per output).
 struct FeedbackCtl {
   static constexpr int KIND = HJB_CTL_FEEDBACK;
   template <class S>
-  static __device__ __forceinline__ void control(const DevSys& ps, const DevCtl& pc, const float* x,
+  static __device__ __forceinline__ void control(const DevSys& ps, const DevCtl& pc, const float* z,
                                                  const typename S::Trig&, float* u) {
-    float dx[S::N];
-#pragma unroll
-    for (int i = 0; i < S::N; ++i) dx[i] = x[i] - pc.xf[i];
-    S::wrap(dx);
 #pragma unroll
     for (int k = 0; k < S::M; ++k) {
-      float acc = pc.uf[k];
+      float acc = pc.u0[k];
 #pragma unroll
-      for (int i = 0; i < S::N; ++i) acc = fmaf(-pc.K[k * S::N + i], dx[i], acc);
+      for (int i = 0; i < S::N; ++i) acc = fmaf(-pc.K[k * S::N + i], z[i], acc);
       u[k] = acc;
     }
     if (pc.clip) clip_u<S>(ps, u);
   }
 };
 
-// controller/cartpole_energy_shaping.py:65-110.  Both branches are evaluated and selected (no divergence).
-// aux = {Ke0, Ke1, Ke2, eps_energy, eps_state^2, E(xf)};  ps.c[5] = 1/l, ps.c[6] = g/l
+// controller/cartpole_energy_shaping.py:65-110 (aoff = 0: z is the raw state).  Both branches are evaluated
+// and selected (no divergence).  aux = {Ke0, Ke1, Ke2, eps_energy, eps_state^2, E(xf)}; ps.c[5] = 1/l, ps.c[6] = g/l
 struct CartpoleESCtl {
   static constexpr int KIND = HJB_CTL_CARTPOLE_ES;
   template <class S>
@@ -274,7 +300,7 @@ struct CartpoleESCtl {
     float dx[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) dx[i] = x[i] - pc.xf[i];
-    S::wrap(dx);                                                     // :75
+    dx[1] = wrap_pi(dx[1]);                                          // :75
     const float de = fmaf(0.5f * x[3], x[3], -t.c) - pc.aux[5];      // :78, :90-95
     const bool near = (fabsf(de) < pc.aux[3]) && (fmaf(dx[1], dx[1], dx[3] * dx[3]) < pc.aux[4]);  // :79
     float ulqr = 0.f;                                                // :80
@@ -289,7 +315,7 @@ struct CartpoleESCtl {
   }
 };
 
-// controller/acrobot_energy_shaping.py:74-121 (Spong collocated swing-up + LQR catch).
+// controller/acrobot_energy_shaping.py:74-121 (Spong collocated swing-up + LQR catch; aoff = 0).
 // aux = {Ks0, Ks1, Ks2, eps, E(xf)}
 struct AcrobotESCtl {
   static constexpr int KIND = HJB_CTL_ACROBOT_ES;
