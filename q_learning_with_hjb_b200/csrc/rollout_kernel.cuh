@@ -175,7 +175,7 @@ __global__ void __launch_bounds__(256) rollout_kernel(const __grid_constant__ Ro
       for (int i = 0; i < N; ++i) zn[i] = z[i];
       float l = 0.f;
       if constexpr (COST != COST_NONE) l = running_cost<S, COST>(a.cost, z, u, 0.f);
-      clip_u<S>(a.sys, u);
+      if constexpr (!C::kClips) clip_u<S>(a.sys, u);
       integrate<S, INTEG>(a.sys, zn, tr, u);
       if (alive) {
 #pragma unroll
@@ -185,7 +185,8 @@ __global__ void __launch_bounds__(256) rollout_kernel(const __grid_constant__ Ro
       }
     } else {
       if constexpr (COST != COST_NONE) J = running_cost<S, COST>(a.cost, z, u, J);
-      clip_u<S>(a.sys, u);  // Dynamics.simulate's own clip (dynamics_basic.py:118)
+      // Dynamics.simulate's own clip (dynamics_basic.py:118); idempotent when the controller already clipped
+      if constexpr (!C::kClips) clip_u<S>(a.sys, u);
       integrate<S, INTEG>(a.sys, z, tr, u);
     }
     if constexpr (REC) {
@@ -275,6 +276,16 @@ HJB_DECLARE_PROBLEM(quad10d_fb);
   cudaError_t rollout_##name(const RolloutArgs& a, const RolloutVariant& v, bool fast, cudaStream_t st) { \
     if (fast) return launch_rollout<SYS_T(true), CTL, ALLOW_DISCRETE>(a, v, st);                          \
     return launch_rollout<SYS_T(false), CTL, ALLOW_DISCRETE>(a, v, st);                                   \
+  }
+// state-feedback problems: the controller's clip flag selects a compile-time variant
+#define HJB_DEFINE_FB_PROBLEM(name, SYS_T, ALLOW_DISCRETE)                                                \
+  cudaError_t rollout_##name(const RolloutArgs& a, const RolloutVariant& v, bool fast, cudaStream_t st) { \
+    if (a.ctl.clip) {                                                                                     \
+      if (fast) return launch_rollout<SYS_T(true), FeedbackCtl<true>, ALLOW_DISCRETE>(a, v, st);          \
+      return launch_rollout<SYS_T(false), FeedbackCtl<true>, ALLOW_DISCRETE>(a, v, st);                   \
+    }                                                                                                     \
+    if (fast) return launch_rollout<SYS_T(true), FeedbackCtl<false>, ALLOW_DISCRETE>(a, v, st);           \
+    return launch_rollout<SYS_T(false), FeedbackCtl<false>, ALLOW_DISCRETE>(a, v, st);                    \
   }
 
 }  // namespace hjb

@@ -9,5 +9,5 @@ namespace hjb {
 #define SYS_ACROBOT(F) AcrobotSys<F>
 #define SYS_QUAD2D(F) Quad2DSys<F>
 #define SYS_QUAD10D(F) Quad10DSys<F>
-HJB_DEFINE_PROBLEM(linear41_fb, SYS_LINEAR41, FeedbackCtl, true)
+HJB_DEFINE_FB_PROBLEM(linear41_fb, SYS_LINEAR41, true)
 }  // namespace hjb

@@ -9,5 +9,5 @@ namespace hjb {
 #define SYS_ACROBOT(F) AcrobotSys<F>
 #define SYS_QUAD2D(F) Quad2DSys<F>
 #define SYS_QUAD10D(F) Quad10DSys<F>
-HJB_DEFINE_PROBLEM(quad2d_fb, SYS_QUAD2D, FeedbackCtl, false)
+HJB_DEFINE_FB_PROBLEM(quad2d_fb, SYS_QUAD2D, false)
 }  // namespace hjb

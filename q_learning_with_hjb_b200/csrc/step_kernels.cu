@@ -115,8 +115,23 @@ static cudaError_t launch_ctl_fast(const CtlArgs& a, bool fast, cudaStream_t st)
   return fast ? launch_ctl<SysT<true>, C>(a, st) : launch_ctl<SysT<false>, C>(a, st);
 }
 
+template <class FB>
+static cudaError_t step_control_fb(int sys_kind, const CtlArgs& a, bool fast, cudaStream_t st);
+
 cudaError_t step_control(int sys_kind, int ctl_kind, const CtlArgs& a, bool fast, cudaStream_t st) {
-  if (ctl_kind == HJB_CTL_FEEDBACK) {
+  if (ctl_kind == HJB_CTL_FEEDBACK)
+    return a.ctl.clip ? step_control_fb<FeedbackCtl<true>>(sys_kind, a, fast, st)
+                      : step_control_fb<FeedbackCtl<false>>(sys_kind, a, fast, st);
+  if (ctl_kind == HJB_CTL_CARTPOLE_ES && sys_kind == HJB_SYS_CARTPOLE)
+    return launch_ctl_fast<CartpoleSys, CartpoleESCtl>(a, fast, st);
+  if (ctl_kind == HJB_CTL_ACROBOT_ES && sys_kind == HJB_SYS_ACROBOT)
+    return launch_ctl_fast<AcrobotSys, AcrobotESCtl>(a, fast, st);
+  return cudaErrorNotSupported;
+}
+
+template <class FeedbackCtl>
+static cudaError_t step_control_fb(int sys_kind, const CtlArgs& a, bool fast, cudaStream_t st) {
+  {
     switch (sys_kind) {
       case HJB_SYS_LINEAR:
         if (a.sys.n == 2 && a.sys.m == 1) return launch_ctl_fast<Lin21, FeedbackCtl>(a, fast, st);
@@ -130,11 +145,6 @@ cudaError_t step_control(int sys_kind, int ctl_kind, const CtlArgs& a, bool fast
       default: return cudaErrorNotSupported;
     }
   }
-  if (ctl_kind == HJB_CTL_CARTPOLE_ES && sys_kind == HJB_SYS_CARTPOLE)
-    return launch_ctl_fast<CartpoleSys, CartpoleESCtl>(a, fast, st);
-  if (ctl_kind == HJB_CTL_ACROBOT_ES && sys_kind == HJB_SYS_ACROBOT)
-    return launch_ctl_fast<AcrobotSys, AcrobotESCtl>(a, fast, st);
-  return cudaErrorNotSupported;
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -273,8 +273,10 @@ __device__ __forceinline__ void clip_u(const DevSys& ps, float* u) {
 // quadrotors_model_based_controller.py:36-38, 73-75).
 // With aoff = xf's angles the wrapped error IS z on the angle components; on the others the subtraction is
 // folded on the host: u = u0 - K z, u0 = uf + sum_{i not an angle} K_i xf_i  (n FMAs per output).
+template <bool CLIP>
 struct FeedbackCtl {
   static constexpr int KIND = HJB_CTL_FEEDBACK;
+  static constexpr bool kClips = CLIP;  // output already inside [umin, umax]: simulate's clip is then a no-op
   template <class S>
   static __device__ __forceinline__ void control(const DevSys& ps, const DevCtl& pc, const float* z,
                                                  const typename S::Trig&, float* u) {
@@ -285,7 +287,7 @@ struct FeedbackCtl {
       for (int i = 0; i < S::N; ++i) acc = fmaf(-pc.K[k * S::N + i], z[i], acc);
       u[k] = acc;
     }
-    if (pc.clip) clip_u<S>(ps, u);
+    if constexpr (CLIP) clip_u<S>(ps, u);
   }
 };
 
@@ -293,6 +295,7 @@ struct FeedbackCtl {
 // and selected (no divergence).  aux = {Ke0, Ke1, Ke2, eps_energy, eps_state^2, E(xf)}; ps.c[5] = 1/l, ps.c[6] = g/l
 struct CartpoleESCtl {
   static constexpr int KIND = HJB_CTL_CARTPOLE_ES;
+  static constexpr bool kClips = true;
   template <class S>
   static __device__ __forceinline__ void control(const DevSys& ps, const DevCtl& pc, const float* x,
                                                  const typename S::Trig& t, float* u) {
@@ -319,6 +322,7 @@ struct CartpoleESCtl {
 // aux = {Ks0, Ks1, Ks2, eps, E(xf)}
 struct AcrobotESCtl {
   static constexpr int KIND = HJB_CTL_ACROBOT_ES;
+  static constexpr bool kClips = true;
   template <class S>
   static __device__ __forceinline__ void control(const DevSys& ps, const DevCtl& pc, const float* x,
                                                  const typename S::Trig& t, float* u) {
