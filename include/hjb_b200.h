@@ -147,6 +147,88 @@ int hjb_control_efforts(const hjb_system* sys, const hjb_control* ctl, int32_t f
 /* Batched Dynamics.states_wrap (cartpole.py:52-64, acrobot.py:72-81, quadrotors.py:48-70,151-170), in place. */
 int hjb_states_wrap(const hjb_system* sys, float* x, int64_t B, void* stream);
 
+/* ==== vhjb: HJB-residual pass over sampled states (controller/vhjb.py:201-288) ====================== */
+typedef enum hjb_activation {
+  HJB_ACT_RELU = 0, /* controller/vhjb.py:55 */
+  HJB_ACT_TANH = 1, /* examples/cartpole_balancing.ipynb cell 6 */
+  HJB_ACT_SIN = 2   /* examples/double_integrator_optimal_time.ipynb cell 5 */
+} hjb_activation;
+
+typedef enum hjb_control_form {
+  HJB_U_CLIPPED = 0, /* u = clip(-1/2 R^-1 g^T dV/dx + uf, umin, umax)   controller/vhjb.py:220           */
+  HJB_U_BANGBANG = 1 /* u = -sign(g^T dV/dx)   examples/double_integrator_optimal_time.ipynb cell 11:17  */
+} hjb_control_form;
+
+typedef enum hjb_residual_form {
+  /* loss = sum |vdot / (l(x,u) + eps) + 1| (1 - done) / (sum (1 - done) + eps)
+   *        + reg * sum |V / (cost + eps) - 1| done / (sum done + eps)          controller/vhjb.py:227-253, 282-285 */
+  HJB_RES_NORMALIZED = 0,
+  /* loss = mean |vdot + l_i| with the running cost l_i given per sample in `costs`
+   *        examples/double_integrator_optimal_time.ipynb cell 11:20 (l_i = 1[|x|^2 > 1e-4], cell 7:4)             */
+  HJB_RES_MIN_TIME = 1
+} hjb_residual_form;
+
+/* Value network V(x) = |y|^2 + eps_s |z|^2, z = wrap(x - xf), h0 = (z - mean) / std,
+ * y = act(act(h0 W1) W2) W3, no biases (ValueFunctionApproximator, controller/vhjb.py:17-60).
+ * Kernels are stored Flax-style (in, out), row-major, back to back in ONE flat device buffer
+ * params = [W1 (n x 128) | W2 (128 x 128) | W3 (128 x 64)]; features must be {128, 128, 64}.              */
+typedef struct hjb_vnet {
+  int32_t n;
+  int32_t act; /* hjb_activation */
+  int32_t features[3];
+  int32_t _pad;
+  const float* params; /* DEVICE pointer, 128 n + 24576 floats */
+  float mean[HJB_MAX_N], std[HJB_MAX_N], xf[HJB_MAX_N];
+  float eps_s; /* config.epsilon_scalar */
+} hjb_vnet;
+
+typedef struct hjb_task {
+  float Q[HJB_MAX_N * HJB_MAX_N]; /* n x n row-major */
+  float R[HJB_MAX_M * HJB_MAX_M]; /* m x m row-major */
+  float Rinv[HJB_MAX_M * HJB_MAX_M];
+  float uf[HJB_MAX_M];
+  float eps;             /* config.epsilon */
+  int32_t control_form;  /* hjb_control_form */
+  int32_t residual_form; /* hjb_residual_form */
+} hjb_task;
+
+/* Number of floats in the flat parameter / gradient buffer of a value net on an n-dimensional state. */
+int64_t hjb_vhjb_param_count(int32_t n);
+/* Bytes of device scratch the vhjb entry points need (per-CTA partial sums; caller-owned). */
+int64_t hjb_vhjb_workspace_bytes(int32_t n);
+
+/* norm[0] = sum(1 - done) + eps, norm[1] = sum(done) + eps  (the denominators of controller/vhjb.py:241, 253);
+ * MIN_TIME callers pass norm[0] = batch size instead.  With several GPUs all-reduce(sum) the two counts (before
+ * eps is added: use eps = 0 here and add it after) so that every rank normalises by the GLOBAL batch. */
+int hjb_vhjb_count(const float* dones, int64_t B, float eps, float* norm, void* workspace, void* stream);
+
+/*
+ * Residual only (rows V1-V5 of SURVEY.md 8a): for each sampled state the value V, its input gradient p = dV/dx
+ * (get_v_gradient, controller/vhjb.py:201-202), the optimal control u (:204-221), and the residual argument r
+ * (:228-233: vdot / (l + eps) + 1, or vdot + l_i).  Any of V [B], p [B, n], u [B, m], r [B] may be null.
+ * sums (device, 2 floats, nullable): {sum |r| (1 - done), sum |V / (cost + eps) - 1| done} — un-normalised, so
+ * shards can be added; MIN_TIME: {sum |r|, 0}.
+ */
+int hjb_vhjb_residual(const hjb_system* sys, const hjb_vnet* net, const hjb_task* task, const float* xs,
+                      const float* dones, const float* costs, int64_t B, float* V, float* p, float* u, float* r,
+                      float* sums, void* workspace, void* stream);
+
+/*
+ * Loss and parameter gradient of one batch (params_update's value_and_grad, controller/vhjb.py:282-285):
+ *   grad (device, hjb_vhjb_param_count floats) = d/dparams [ L_hjb + reg * L_term ] restricted to this shard's
+ *   samples, ALREADY divided by norm[] — summing the grads of all shards gives the full-batch gradient.
+ *   sums (device, 2 floats) as in hjb_vhjb_residual.  norm (device, 2 floats) from hjb_vhjb_count.
+ * Deterministic: per-CTA partial sums are reduced in a fixed order.
+ */
+int hjb_vhjb_loss_grad(const hjb_system* sys, const hjb_vnet* net, const hjb_task* task, const float* xs,
+                       const float* dones, const float* costs, int64_t B, const float* norm, float reg, float* grad,
+                       float* sums, void* workspace, void* stream);
+
+/* optax.adam update (controller/vhjb.py:120, 286-287; defaults b1 = 0.9, b2 = 0.999, eps = 1e-8), in place on the
+ * flat buffers; `step` is the 1-based index of this update. */
+int hjb_adam(float* params, float* m, float* v, const float* grad, int64_t len, float lr, float b1, float b2,
+             float eps, int32_t step, void* stream);
+
 /* ---- misc ------------------------------------------------------------------------------------------ */
 int hjb_abi_version(void);
 const char* hjb_status_string(int status);

@@ -48,6 +48,24 @@ class HjbRolloutOpts(C.Structure):
                 ("box_xf", C.c_float * HJB_MAX_N), ("box_lo", C.c_float * HJB_MAX_N), ("box_hi", C.c_float * HJB_MAX_N)]
 
 
+ACTIVATIONS = {"relu": 0, "tanh": 1, "sin": 2}
+U_CLIPPED, U_BANGBANG = 0, 1
+RES_NORMALIZED, RES_MIN_TIME = 0, 1
+
+
+class HjbVnet(C.Structure):
+    _fields_ = [("n", C.c_int32), ("act", C.c_int32), ("features", C.c_int32 * 3), ("_pad", C.c_int32),
+                ("params", C.c_void_p),
+                ("mean", C.c_float * HJB_MAX_N), ("std", C.c_float * HJB_MAX_N), ("xf", C.c_float * HJB_MAX_N),
+                ("eps_s", C.c_float)]
+
+
+class HjbTask(C.Structure):
+    _fields_ = [("Q", C.c_float * (HJB_MAX_N * HJB_MAX_N)), ("R", C.c_float * (HJB_MAX_M * HJB_MAX_M)),
+                ("Rinv", C.c_float * (HJB_MAX_M * HJB_MAX_M)), ("uf", C.c_float * HJB_MAX_M),
+                ("eps", C.c_float), ("control_form", C.c_int32), ("residual_form", C.c_int32)]
+
+
 # every symbol include/hjb_b200.h declares: name -> (restype, argtypes)
 _P = C.c_void_p
 SYMBOLS = {
@@ -59,6 +77,14 @@ SYMBOLS = {
     "hjb_control_efforts": (C.c_int, [C.POINTER(HjbSystem), C.POINTER(HjbControl), C.c_int32, _P, C.c_int64, _P, _P]),
     "hjb_states_wrap": (C.c_int, [C.POINTER(HjbSystem), _P, C.c_int64, _P]),
     "hjb_fma_peak_probe": (C.c_int, [_P, C.c_int64, C.c_int32, C.POINTER(C.c_double), _P]),
+    "hjb_vhjb_param_count": (C.c_int64, [C.c_int32]),
+    "hjb_vhjb_workspace_bytes": (C.c_int64, [C.c_int32]),
+    "hjb_vhjb_count": (C.c_int, [_P, C.c_int64, C.c_float, _P, _P, _P]),
+    "hjb_vhjb_residual": (C.c_int, [C.POINTER(HjbSystem), C.POINTER(HjbVnet), C.POINTER(HjbTask), _P, _P, _P, C.c_int64,
+                                    _P, _P, _P, _P, _P, _P, _P]),
+    "hjb_vhjb_loss_grad": (C.c_int, [C.POINTER(HjbSystem), C.POINTER(HjbVnet), C.POINTER(HjbTask), _P, _P, _P, C.c_int64,
+                                     _P, C.c_float, _P, _P, _P, _P]),
+    "hjb_adam": (C.c_int, [_P, _P, _P, _P, C.c_int64, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int32, _P]),
 }
 
 

@@ -1,0 +1,418 @@
+"""``VHJBController`` — value-function learning with the HJB residual, on the CUDA library.
+
+Same public surface as the reference (controller/vhjb.py:75-343): ``running_cost / termination_cost /
+rollout_trajectory / get_trajectory_cost / get_v_gradient / get_control_efforts_with_additional_term /
+get_control_efforts / hjb_loss / termination_loss / params_update / train`` with the same argument order and
+return tuples.  What changes is where the arithmetic runs: the value-MLP forward, its input gradient, the optimal
+control, the Hamiltonian residual, both losses and the full parameter gradient are ONE fused sm_100a kernel
+(``hjb_vhjb_loss_grad``), Adam is ``hjb_adam``; the reference's JAX pytrees become
+
+  params            ``VhjbParams``: one flat fp32 device buffer [W1 | W2 | W3] (Flax (in, out) layout), with
+                    dict-style views ``params["Dense_0"]["kernel"]``
+  states            ``{}`` (BatchNorm is off in every reference config; ``using_batch_norm=True`` is rejected)
+  optimizer_state   ``AdamState(count, mu, nu)`` — the fields of optax's ScaleByAdamState
+
+``params_update`` updates these buffers IN PLACE and returns them (the reference rebinds the returned values, so
+both styles work).  Host-side bookkeeping stays on the host as in the reference: RNG seeding, the replay buffer
+(a ring of NumPy arrays instead of deque + torch DataLoader), the SGDR schedule, Riccati setup.
+
+Several GPUs: when ``torch.distributed`` is initialised, ``params_update`` treats ``xs`` as this rank's shard of
+the batch: the two done-counts and then the gradient are all-reduced (sum), every rank applies the same Adam step.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import List, Optional, Tuple
+
+import numpy as np
+
+from q_learning_with_hjb_b200 import _lib as L
+from q_learning_with_hjb_b200.controller.controller_basic import Controller
+
+FEATURES = (128, 128, 64)
+
+
+def lecun_normal(rng: np.random.Generator, fan_in: int, fan_out: int) -> np.ndarray:
+    """Flax ``Dense`` default kernel init (truncated normal at +-2 sigma rescaled to variance 1/fan_in)."""
+    std = np.sqrt(1.0 / fan_in) / 0.87962566103423978
+    w = rng.normal(size=(fan_in, fan_out))
+    bad = np.abs(w) > 2
+    while bad.any():
+        w[bad] = rng.normal(size=int(bad.sum()))
+        bad = np.abs(w) > 2
+    return (w * std).astype(np.float32)
+
+
+def sgdr_schedule(step: int, init: float, peak: float, end: float, cycles: int, warmup: int, total: int) -> float:
+    """optax.sgdr_schedule of ``cycles`` identical warm-up + cosine-decay cycles (vhjb.py:123-126)."""
+    cycle = step // total
+    if cycle >= cycles:
+        return float(end)
+    s = step - cycle * total
+    if s < warmup:
+        return float(init + (peak - init) * s / warmup)
+    frac = min((s - warmup) / max(1, total - warmup), 1.0)
+    return float(end + (peak - end) * 0.5 * (1.0 + np.cos(np.pi * frac)))
+
+
+class VhjbParams:
+    """Flat fp32 device buffer [W1 (n x 128) | W2 (128 x 128) | W3 (128 x 64)] with pytree-style views."""
+
+    def __init__(self, flat, n: int):
+        self.flat, self.n = flat, n
+        o1, o2 = n * FEATURES[0], n * FEATURES[0] + FEATURES[0] * FEATURES[1]
+        self._views = {
+            "Dense_0": {"kernel": flat[:o1].view(n, FEATURES[0])},
+            "Dense_1": {"kernel": flat[o1:o2].view(FEATURES[0], FEATURES[1])},
+            "Dense_2": {"kernel": flat[o2:].view(FEATURES[1], FEATURES[2])},
+        }
+
+    def __getitem__(self, key):
+        return self._views[key]
+
+    def keys(self):
+        return self._views.keys()
+
+    def kernels(self):
+        return [self._views[f"Dense_{i}"]["kernel"] for i in range(3)]
+
+    def clone(self) -> "VhjbParams":
+        return VhjbParams(self.flat.clone(), self.n)
+
+
+@dataclass
+class AdamState:
+    count: int
+    mu: object
+    nu: object
+
+
+class VhjbKernels:
+    """Thin stateful wrapper over the vhjb C entry points for one (dynamics, value-net, task) triple: packs the
+    parameter structs once, owns the device scratch."""
+
+    def __init__(self, dynamics, xf, uf, Q, R, mean, std, eps, eps_s, act="relu", control_form="clipped",
+                 residual_form="normalized"):
+        torch = L.require_cuda()
+        self.torch = torch
+        self.dyn = dynamics
+        self.n, self.m = dynamics.get_dimension()
+        self.P = int(L.lib().hjb_vhjb_param_count(self.n))
+        self.sys_spec = dynamics.system_spec()
+        self.net = L.HjbVnet()
+        self.net.n, self.net.act = self.n, L.ACTIVATIONS[act]
+        for i, f in enumerate(FEATURES):
+            self.net.features[i] = f
+        L.fill(self.net.mean, mean)
+        L.fill(self.net.std, std)
+        L.fill(self.net.xf, xf)
+        self.net.eps_s = float(eps_s)
+        self.task = L.HjbTask()
+        R = np.asarray(R, dtype=np.float64).reshape(self.m, self.m)
+        L.fill(self.task.Q, np.asarray(Q, dtype=np.float64).reshape(self.n, self.n))
+        L.fill(self.task.R, R)
+        L.fill(self.task.Rinv, np.linalg.inv(R))
+        L.fill(self.task.uf, uf)
+        self.task.eps = float(eps)
+        self.task.control_form = {"clipped": L.U_CLIPPED, "bangbang": L.U_BANGBANG}[control_form]
+        self.task.residual_form = {"normalized": L.RES_NORMALIZED, "min_time": L.RES_MIN_TIME}[residual_form]
+        self.residual_form = residual_form
+        self.eps = float(eps)
+        ws = int(L.lib().hjb_vhjb_workspace_bytes(self.n))
+        self.workspace = torch.empty(ws // 4, device="cuda", dtype=torch.float32)
+        self.norm = torch.empty(2, device="cuda", dtype=torch.float32)
+        # gradient and the two loss sums live back to back so that ONE all-reduce covers both
+        self.grad_and_sums = torch.zeros(self.P + 2, device="cuda", dtype=torch.float32)
+        self.grad = self.grad_and_sums[: self.P]
+        self.sums = self.grad_and_sums[self.P:]
+
+    def _bind(self, params_flat):
+        assert params_flat.is_cuda and params_flat.dtype == self.torch.float32 and params_flat.numel() == self.P
+        self.net.params = params_flat.data_ptr()
+
+    def counts(self, dones, eps: float):
+        """norm = [sum(1 - done) + eps, sum(done) + eps] on device (min_time: [B, eps])."""
+        L.check(L.lib().hjb_vhjb_count(L.ptr(dones), dones.numel(), float(eps), L.ptr(self.norm), L.ptr(self.workspace),
+                                       L.stream_ptr()), "hjb_vhjb_count")
+        return self.norm
+
+    def residual(self, params_flat, xs, dones, costs, want=("V", "p", "u", "r")):
+        torch = self.torch
+        self._bind(params_flat)
+        B = xs.shape[0]
+        out = {"V": None, "p": None, "u": None, "r": None}
+        shapes = {"V": (B,), "p": (B, self.n), "u": (B, self.m), "r": (B,)}
+        for k in want:
+            out[k] = torch.empty(shapes[k], device="cuda", dtype=torch.float32)
+        L.check(L.lib().hjb_vhjb_residual(self.sys_spec, self.net, self.task, L.ptr(xs), L.ptr(dones), L.ptr(costs), B,
+                                          L.ptr(out["V"]), L.ptr(out["p"]), L.ptr(out["u"]), L.ptr(out["r"]),
+                                          L.ptr(self.sums), L.ptr(self.workspace), L.stream_ptr()), "hjb_vhjb_residual")
+        return out, self.sums
+
+    def loss_grad(self, params_flat, xs, dones, costs, reg: float):
+        """grad (normalised by self.norm) and the un-normalised loss sums of this shard."""
+        self._bind(params_flat)
+        L.check(L.lib().hjb_vhjb_loss_grad(self.sys_spec, self.net, self.task, L.ptr(xs), L.ptr(dones), L.ptr(costs),
+                                           xs.shape[0], L.ptr(self.norm), float(reg), L.ptr(self.grad), L.ptr(self.sums),
+                                           L.ptr(self.workspace), L.stream_ptr()), "hjb_vhjb_loss_grad")
+        return self.grad, self.sums
+
+    def adam(self, params_flat, mu, nu, grad, step: int, lr: float, b1=0.9, b2=0.999, eps=1e-8):
+        L.check(L.lib().hjb_adam(L.ptr(params_flat), L.ptr(mu), L.ptr(nu), L.ptr(grad), params_flat.numel(), float(lr),
+                                 float(b1), float(b2), float(eps), int(step), L.stream_ptr()), "hjb_adam")
+
+    # ---- one full training step on this rank's shard (shared by VHJBController.params_update and bench.py) ----
+    def train_step(self, params_flat, opt: AdamState, xs, dones, costs, reg: float, lr: float, group=None):
+        """count -> [all-reduce] -> fused loss+grad -> [all-reduce] -> Adam.  Returns the device tensor
+        [hjb_sum, term_sum] (un-normalised, global) and the norm tensor; no host synchronisation."""
+        torch = self.torch
+        dist = torch.distributed if (torch.distributed.is_available() and torch.distributed.is_initialized()) else None
+        if self.residual_form == "min_time":
+            self.counts(dones, 0.0)                   # done == 0 everywhere: norm[0] = B (plain mean)
+        else:
+            self.counts(dones, 0.0)
+        if dist is not None:
+            dist.all_reduce(self.norm, group=group)
+        if self.residual_form == "min_time":
+            self.norm[1] = 1.0
+        else:
+            self.norm += self.eps
+        self.loss_grad(params_flat, xs, dones, costs, reg)
+        if dist is not None:
+            dist.all_reduce(self.grad_and_sums, group=group)
+        opt.count += 1
+        self.adam(params_flat, opt.mu, opt.nu, self.grad, opt.count, lr)
+        return self.sums, self.norm
+
+
+class VHJBController(Controller):
+    def __init__(self, dynamics, config, activation: str = "relu") -> None:
+        super().__init__()
+        torch = L.require_cuda()
+        self.torch = torch
+        if getattr(config, "using_batch_norm", False):
+            raise NotImplementedError("using_batch_norm=True is not supported (off in every reference config)")
+        if tuple(config.features) != FEATURES:
+            raise NotImplementedError(f"value-net features must be {list(FEATURES)} (the kernel's compiled shape)")
+        # seeds (vhjb.py:81-83): NumPy drives data sampling AND, here, the weight init (JAX's PRNG is not available)
+        np.random.seed(config.seed)
+        torch.manual_seed(config.seed)
+        self._rng = np.random.default_rng(config.seed)
+
+        self.epsilon = config.epsilon
+        self.dynamics = dynamics
+        self.state_dim, self.control_dim = dynamics.get_dimension()
+        self.umin, self.umax = dynamics.get_control_limit()
+        assert np.shape(self.umin)[0] == self.control_dim and np.shape(self.umax)[0] == self.control_dim
+        self.Q, self.R = config.Q, config.R
+        self.R_inv = np.linalg.inv(np.asarray(self.R, dtype=np.float64))
+        self.xf, self.uf = config.xf, config.uf
+        self.obs_min, self.obs_max = config.obs_min, config.obs_max
+        self.system_additional_init()
+
+        self.kernels = VhjbKernels(dynamics, self.xf, self.uf, self.Q, self.R, config.normalization_mean,
+                                   config.normalization_std, config.epsilon, config.epsilon_scalar, act=activation)
+        n = self.state_dim
+        dims = [n, *FEATURES]
+        flat = np.concatenate([lecun_normal(self._rng, dims[i], dims[i + 1]).reshape(-1) for i in range(3)])
+        self.model_params = VhjbParams(torch.as_tensor(flat).cuda(), n)
+        self.model_states = {}
+        self.train_mode = False
+        self.lr = config.lr
+        self.optimizer_states = AdamState(0, torch.zeros_like(self.model_params.flat), torch.zeros_like(self.model_params.flat))
+        self._sched = dict(init=config.regularization_init_value, peak=config.regularization_peak_value,
+                           end=config.regularization_end_value, cycles=config.regularization_num_of_cycles,
+                           warmup=config.regularization_warmup_steps_per_cycle,
+                           total=config.regularization_total_steps_per_cycle)
+        self.regularization_scheduler = lambda step: sgdr_schedule(int(step), **self._sched)
+        self.update_counter = 0
+        self.regularization = self.regularization_scheduler(self.update_counter)
+        self.epochs = config.epochs
+        self.batch_size = config.batch_size
+        self.maximum_timestep = config.maximum_step
+        self.num_of_trajectories_per_epoch = config.num_of_trajectories_per_epoch
+
+        # seed dataset (vhjb.py:136-151): interior points (done 0, cost 0), boundary points (done 1, clipped x^T P x)
+        def sample(mean, std, count):
+            return [self.dynamics.states_wrap(np.random.uniform(low=-1, high=1, size=self.state_dim) * std + mean)
+                    for _ in range(count)]
+        interior = sample(config.interior_states_mean, config.interior_states_std, config.num_of_interior_data)
+        boundary = sample(config.boundary_states_mean, config.boundary_states_std, config.num_of_boundary_data)
+        self.replay_buffer = ReplayBuffer(self.state_dim, config.maximum_buffer_size)
+        for x in interior:
+            self.replay_buffer.append(x, 0.0, 0.0)
+        for x in boundary:
+            self.replay_buffer.append(x, min(self.termination_cost(x), config.boundary_cost_clip), 1.0)
+
+    # ---- host-side setup ---------------------------------------------------------------------------------
+    def system_additional_init(self) -> None:
+        """Linearise about (xf, uf) (assumed an equilibrium) and solve the Riccati equation for the terminal cost
+        x^T P x (vhjb.py:156-160)."""
+        import scipy.linalg
+
+        Alin, Blin = self.dynamics.linearize(np.asarray(self.xf, dtype=np.float64), np.asarray(self.uf, dtype=np.float64))
+        self.P = scipy.linalg.solve_continuous_are(Alin, Blin, np.asarray(self.Q, dtype=np.float64),
+                                                   np.asarray(self.R, dtype=np.float64))
+
+    def running_cost(self, x, u):
+        x_diff = self.dynamics.states_wrap(np.array(x, dtype=np.float64) - self.xf)
+        u_diff = np.asarray(u, dtype=np.float64) - self.uf
+        return x_diff.T @ self.Q @ x_diff + u_diff.T @ self.R @ u_diff
+
+    def termination_cost(self, x):
+        x_diff = self.dynamics.states_wrap(np.array(x, dtype=np.float64) - self.xf)
+        return x_diff.T @ self.P @ x_diff
+
+    # ---- reference interface -------------------------------------------------------------------------------
+    def rollout_trajectory(self) -> List[Tuple[np.ndarray, float, float]]:
+        """One closed-loop trajectory under the current value net with out-of-box termination (vhjb.py:171-193)."""
+        trajectory = []
+        x = self.dynamics.get_initial_state()
+        done = 0.0
+        for _ in range(self.maximum_timestep):
+            dx = self.dynamics.states_wrap(x - self.xf)
+            if np.any(dx > self.obs_max) or np.any(dx < self.obs_min):
+                done = 1.0
+                trajectory.append((x, self.termination_cost(x), done))
+                break
+            u = self.get_control_efforts(x)
+            trajectory.append((x, self.running_cost(x, u) * self.dynamics.dt, done))
+            x = self.dynamics.simulate(x, u)
+        if done == 0.0:
+            trajectory.append((x, self.termination_cost(x), 1.0))
+        return trajectory
+
+    def get_trajectory_cost(self, trajectory):
+        return sum(cost for _, cost, _ in trajectory)
+
+    def _batch(self, x):
+        single = np.ndim(x) == 1
+        return L.dev_f32(x, (-1, self.state_dim)), single
+
+    def _residual(self, params, xs_dev, dones=None, costs=None, want=("V", "p", "u", "r")):
+        torch = self.torch
+        B = xs_dev.shape[0]
+        d = torch.zeros(B, device="cuda") if dones is None else L.dev_f32(dones, (B,))
+        c = torch.ones(B, device="cuda") if costs is None else L.dev_f32(costs, (B,))
+        return self.kernels.residual(params.flat, xs_dev, d, c, want)
+
+    def get_v_gradient(self, params, states, x):
+        xd, single = self._batch(x)
+        out, _ = self._residual(params, xd, want=("p",))
+        return (out["p"][0] if single else out["p"]), states
+
+    def get_control_efforts_with_additional_term(self, params, states, x):
+        """(u, dV/dx, states) — u = clip(-R^-1 g^T dV/dx / 2 + uf, umin, umax) (vhjb.py:204-221), on device."""
+        xd, single = self._batch(x)
+        out, _ = self._residual(params, xd, want=("p", "u"))
+        u, p = out["u"], out["p"]
+        return (u[0], p[0], states) if single else (u, p, states)
+
+    def get_control_efforts(self, x):
+        u, _, _ = self.get_control_efforts_with_additional_term(self.model_params, self.model_states, x)
+        return u.cpu().numpy().astype(np.float64)
+
+    def hjb_loss(self, params, states, xs, dones):
+        xd, _ = self._batch(xs)
+        self.kernels.counts(L.dev_f32(dones, (xd.shape[0],)), self.epsilon)
+        _, sums = self._residual(params, xd, dones, None, want=())
+        return float(sums[0] / self.kernels.norm[0]), states
+
+    def termination_loss(self, params, states, xs, dones, costs):
+        xd, _ = self._batch(xs)
+        self.kernels.counts(L.dev_f32(dones, (xd.shape[0],)), self.epsilon)
+        _, sums = self._residual(params, xd, dones, costs, want=())
+        return float(sums[1] / self.kernels.norm[1]), states
+
+    def params_update(self, params, states, optimizer_state, xs, dones, costs, regularization):
+        """One fused update (vhjb.py:255-288).  Returns (params, states, optimizer_state, total, hjb, term); the
+        three losses are 0-d device tensors (no host synchronisation here)."""
+        xd, _ = self._batch(xs)
+        B = xd.shape[0]
+        sums, norm = self.kernels.train_step(params.flat, optimizer_state, xd, L.dev_f32(dones, (B,)),
+                                             L.dev_f32(costs, (B,)), float(regularization), self.lr)
+        hjb = sums[0] / norm[0]
+        term = sums[1] / norm[1]
+        return params, states, optimizer_state, hjb + float(regularization) * term, hjb, term
+
+    def train(self):
+        """The reference's training loop (vhjb.py:290-343): per epoch, sample trajectories with the current policy
+        into the replay buffer, then one pass of shuffled minibatches (drop_last) of fused updates."""
+        avg_cost, std_cost, avg_len, avg_total, avg_hjb, avg_term = [], [], [], [], [], []
+        for epoch in range(self.epochs):
+            costs_list, lengths = [], 0
+            self.train_mode = False
+            for _ in range(self.num_of_trajectories_per_epoch):
+                traj = self.rollout_trajectory()
+                costs_list.append(self.get_trajectory_cost(traj))
+                lengths += len(traj)
+                for x, c, d in traj:
+                    self.replay_buffer.append(x, c, d)
+            self.train_mode = True
+            totals = hjbs = terms = 0.0
+            n_batches = 0
+            for xs, costs, dones in self.replay_buffer.batches(self.batch_size):
+                (self.model_params, self.model_states, self.optimizer_states, total, hjb, term) = self.params_update(
+                    self.model_params, self.model_states, self.optimizer_states, xs, dones, costs, self.regularization)
+                totals, hjbs, terms = totals + total, hjbs + hjb, terms + term
+                n_batches += 1
+                self.update_counter += 1
+                self.regularization = self.regularization_scheduler(self.update_counter)
+            if self.num_of_trajectories_per_epoch > 0:
+                avg_cost.append(sum(costs_list) / self.num_of_trajectories_per_epoch)
+                std_cost.append(float(np.var(np.array(costs_list)) ** 0.5))
+                avg_len.append(lengths / self.num_of_trajectories_per_epoch)
+            if n_batches:
+                avg_total.append(float(totals) / n_batches)
+                avg_hjb.append(float(hjbs) / n_batches)
+                avg_term.append(float(terms) / n_batches)
+            if (epoch + 1) % 10 == 0:
+                if self.num_of_trajectories_per_epoch > 0:
+                    print(f"epoch:{epoch + 1}, average trajectory cost:{avg_cost[-1]:.2f}, "
+                          f"average trajectory length:{avg_len[-1]:.2f}")
+                if n_batches:
+                    print(f"epoch:{epoch + 1}, total loss:{avg_total[-1]:.5f}, regulation: {self.regularization:.1f},"
+                          f"hjb loss:{avg_hjb[-1]:.5f}, termination loss:{avg_term[-1]:.5f}")
+        return avg_cost, std_cost, avg_len, avg_total, avg_hjb, avg_term
+
+
+class ReplayBuffer:
+    """Ring buffer of (state, cost, done) with the reference's sampling semantics (deque(maxlen) + DataLoader with
+    shuffle=True, drop_last=True; vhjb.py:62-73, :154)."""
+
+    def __init__(self, state_dim: int, max_size: int):
+        self.max_size = int(max_size)
+        cap = min(self.max_size, 1 << 16)
+        self.xs = np.zeros((cap, state_dim), dtype=np.float32)
+        self.costs = np.zeros(cap, dtype=np.float32)
+        self.dones = np.zeros(cap, dtype=np.float32)
+        self.size, self.head = 0, 0
+
+    def __len__(self):
+        return self.size
+
+    def _grow(self):
+        cap = min(self.max_size, 2 * self.xs.shape[0])
+        for name in ("xs", "costs", "dones"):
+            old = getattr(self, name)
+            new = np.zeros((cap, *old.shape[1:]), dtype=old.dtype)
+            new[: old.shape[0]] = old
+            setattr(self, name, new)
+
+    def append(self, x, cost, done):
+        if self.size < self.max_size and self.size == self.xs.shape[0]:
+            self._grow()
+        if self.size < self.max_size:
+            i = self.size
+            self.size += 1
+        else:  # full: overwrite the oldest (deque(maxlen) semantics)
+            i = self.head
+            self.head = (self.head + 1) % self.max_size
+        self.xs[i], self.costs[i], self.dones[i] = x, cost, done
+
+    def batches(self, batch_size: int):
+        perm = np.random.permutation(self.size)
+        for b in range(self.size // batch_size):
+            idx = perm[b * batch_size:(b + 1) * batch_size]
+            yield self.xs[idx], self.costs[idx], self.dones[idx]

@@ -42,7 +42,7 @@ static double wrap_pi_host(double a) {
   return a - two_pi * std::floor((a + 0.5 * two_pi) / two_pi);
 }
 
-static void make_dev_sys(const hjb_system* s, DevSys& d) {
+void make_dev_sys(const hjb_system* s, DevSys& d) {
   std::memset(&d, 0, sizeof(d));
   d.n = s->n;
   d.m = s->m;

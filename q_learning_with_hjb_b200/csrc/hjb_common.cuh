@@ -56,6 +56,9 @@ struct DevCost {
   float dang[2];  // aoff - xf on the angle components (0 when the cost and the controller share the goal)
 };
 
+// public struct -> device block (derived constants folded in double); defined in api.cu
+void make_dev_sys(const hjb_system* s, DevSys& d);
+
 struct DevBox {
   float xf[HJB_MAX_N], lo[HJB_MAX_N], hi[HJB_MAX_N];
   float dang[2];  // aoff - xf on the angle components

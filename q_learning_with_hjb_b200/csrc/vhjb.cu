@@ -1,0 +1,192 @@
+// vhjb entry points: argument folding, launch of the fused pass, deterministic cross-CTA reduction, done-counting
+// and the Adam update.  Kernel bodies: vhjb_simt.cuh; per-system instantiations: vhjb_<system>.cu.
+#include <cmath>
+#include <cstring>
+
+#include "vhjb_simt.cuh"
+
+namespace hjb {
+
+constexpr int kMaxCtas = 160;  // >= SM count (148 on B200)
+
+static int64_t pstride_of(int n) { return ((int64_t)vhjb_param_count(n) + 2 + 3) / 4 * 4; }
+
+// grad[j] = sum over CTAs (fixed order) of partial[cta][j]; j in [first, first + count)
+__global__ void __launch_bounds__(256) vhjb_reduce_kernel(const float* __restrict__ partial, int64_t pstride, int ncta,
+                                                          int first, int count, float* __restrict__ out) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= count) return;
+  float s = 0.f;
+  for (int c = 0; c < ncta; ++c) s += partial[(int64_t)c * pstride + first + j];
+  out[j] = s;
+}
+
+// ---- sum(1 - done), sum(done): two-stage, fixed order ----
+__global__ void __launch_bounds__(256) count_stage1(const float* __restrict__ dones, int64_t B, float* __restrict__ part) {
+  float s1 = 0.f;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < B; i += (int64_t)gridDim.x * blockDim.x)
+    s1 += __ldg(dones + i);
+  __shared__ float sh[8];
+#pragma unroll
+  for (int s = 16; s > 0; s >>= 1) s1 += __shfl_xor_sync(0xffffffffu, s1, s);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s1;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int w = 0; w < 8; ++w) t += sh[w];
+    part[blockIdx.x] = t;
+  }
+}
+__global__ void count_stage2(const float* __restrict__ part, int nblk, int64_t B, float eps, float* __restrict__ norm) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    double t = 0.0;
+    for (int i = 0; i < nblk; ++i) t += (double)part[i];
+    norm[0] = (float)((double)B - t + (double)eps);
+    norm[1] = (float)(t + (double)eps);
+  }
+}
+
+// ---- optax.adam ----
+__global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ w, float* __restrict__ m, float* __restrict__ v,
+                                                   const float* __restrict__ g, int64_t len, float lr, float b1, float b2,
+                                                   float eps, float bc1, float bc2) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= len) return;
+  const float gi = g[i];
+  const float mi = fmaf(b1, m[i], (1.f - b1) * gi);
+  const float vi = fmaf(b2, v[i], (1.f - b2) * gi * gi);
+  m[i] = mi;
+  v[i] = vi;
+  const float mhat = mi / bc1, vhat = vi / bc2;
+  w[i] = w[i] - lr * mhat / (sqrtf(vhat) + eps);
+}
+
+static int sm_count() {
+  static int cached = 0;
+  if (cached == 0) {
+    int dev = 0, sms = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess)
+      cached = sms;
+  }
+  return cached > 0 ? (cached < kMaxCtas ? cached : kMaxCtas) : 148;
+}
+
+static int run_vhjb(const hjb_system* sys, const hjb_vnet* net, const hjb_task* task, const float* xs, const float* dones,
+                    const float* costs, int64_t B, const float* norm, float reg, float* V, float* p, float* u, float* r,
+                    float* grad, float* sums, void* workspace, bool want_grad, cudaStream_t st) {
+  if (!sys || !net || !task || B < 0) return HJB_ERR_BAD_ARG;
+  if (net->n != sys->n || net->features[0] != VH1 || net->features[1] != VH2 || net->features[2] != VH3)
+    return HJB_ERR_UNSUPPORTED;
+  if (!net->params || !workspace) return HJB_ERR_BAD_ARG;
+  if (B > 0 && (!xs || !dones || !costs)) return HJB_ERR_BAD_ARG;
+  if (want_grad && (!grad || !norm)) return HJB_ERR_BAD_ARG;
+  const int n = sys->n, m = sys->m;
+
+  VhjbArgs a;
+  std::memset(&a, 0, sizeof(a));
+  make_dev_sys(sys, a.sys);  // aoff = 0: same folding as the rollout path
+  a.params = net->params;
+  for (int i = 0; i < n; ++i) {
+    a.mean[i] = net->mean[i];
+    a.inv_std[i] = (float)(1.0 / (double)net->std[i]);
+    a.xf[i] = net->xf[i];
+  }
+  a.eps_s = net->eps_s;
+  for (int i = 0; i < n * n; ++i) a.Q[i] = task->Q[i];
+  for (int i = 0; i < m; ++i)
+    for (int j = 0; j < m; ++j) {
+      a.R[i * m + j] = task->R[i * m + j];
+      a.Rsym[i * m + j] = task->R[i * m + j] + task->R[j * m + i];
+      a.Rinv[i * m + j] = task->Rinv[i * m + j];
+    }
+  for (int i = 0; i < m; ++i) a.uf[i] = task->uf[i];
+  a.eps = task->eps;
+  a.xs = xs; a.dones = dones; a.costs = costs; a.B = B;
+  a.norm = norm; a.reg = reg;
+  a.V = V; a.p = p; a.u = u; a.r = r;
+  a.partial = static_cast<float*>(workspace);
+  a.pstride = pstride_of(n);
+  a.n_tiles = (B + VBM - 1) / VBM;
+
+  VhjbLaunch l;
+  l.grad = want_grad;
+  int64_t grid = a.n_tiles < sm_count() ? a.n_tiles : sm_count();
+  if (grid < 1) grid = 1;
+  l.grid = (int)grid;
+
+  cudaError_t e = cudaErrorNotSupported;
+  switch (sys->kind) {
+    case HJB_SYS_LINEAR:
+      if (n == 2 && m == 1) e = vhjb_launch_linear21(a, l, net->act, task->control_form, task->residual_form, st);
+      break;
+    case HJB_SYS_CARTPOLE: e = vhjb_launch_cartpole(a, l, net->act, task->control_form, task->residual_form, st); break;
+    case HJB_SYS_QUAD2D: e = vhjb_launch_quad2d(a, l, net->act, task->control_form, task->residual_form, st); break;
+    case HJB_SYS_QUAD10D: e = vhjb_launch_quad10d(a, l, net->act, task->control_form, task->residual_form, st); break;
+    default: break;
+  }
+  if (e == cudaErrorNotSupported) return HJB_ERR_UNSUPPORTED;
+  if (e != cudaSuccess) return (int)e;
+  const int P = vhjb_param_count(n);
+  if (want_grad) {
+    vhjb_reduce_kernel<<<(P + 255) / 256, 256, 0, st>>>(a.partial, a.pstride, l.grid, 0, P, grad);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return (int)e;
+  }
+  if (sums) {
+    vhjb_reduce_kernel<<<1, 256, 0, st>>>(a.partial, a.pstride, l.grid, P, 2, sums);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return (int)e;
+  }
+  return HJB_OK;
+}
+
+}  // namespace hjb
+
+using namespace hjb;
+
+extern "C" {
+
+int64_t hjb_vhjb_param_count(int32_t n) { return n > 0 && n <= HJB_MAX_N ? vhjb_param_count(n) : -1; }
+
+int64_t hjb_vhjb_workspace_bytes(int32_t n) {
+  if (n <= 0 || n > HJB_MAX_N) return -1;
+  return (int64_t)kMaxCtas * pstride_of(n) * (int64_t)sizeof(float);
+}
+
+int hjb_vhjb_count(const float* dones, int64_t B, float eps, float* norm, void* workspace, void* stream) {
+  if (!norm || !workspace || B < 0 || (B > 0 && !dones)) return HJB_ERR_BAD_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int nblk = sm_count();
+  float* part = static_cast<float*>(workspace);
+  count_stage1<<<nblk, 256, 0, st>>>(dones, B, part);
+  count_stage2<<<1, 32, 0, st>>>(part, nblk, B, eps, norm);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? HJB_OK : (int)e;
+}
+
+int hjb_vhjb_residual(const hjb_system* sys, const hjb_vnet* net, const hjb_task* task, const float* xs, const float* dones,
+                      const float* costs, int64_t B, float* V, float* p, float* u, float* r, float* sums, void* workspace,
+                      void* stream) {
+  return run_vhjb(sys, net, task, xs, dones, costs, B, nullptr, 0.f, V, p, u, r, nullptr, sums, workspace, false,
+                  (cudaStream_t)stream);
+}
+
+int hjb_vhjb_loss_grad(const hjb_system* sys, const hjb_vnet* net, const hjb_task* task, const float* xs, const float* dones,
+                       const float* costs, int64_t B, const float* norm, float reg, float* grad, float* sums, void* workspace,
+                       void* stream) {
+  return run_vhjb(sys, net, task, xs, dones, costs, B, norm, reg, nullptr, nullptr, nullptr, nullptr, grad, sums, workspace,
+                  true, (cudaStream_t)stream);
+}
+
+int hjb_adam(float* params, float* m, float* v, const float* grad, int64_t len, float lr, float b1, float b2, float eps,
+             int32_t step, void* stream) {
+  if (!params || !m || !v || !grad || len < 0 || step < 1) return HJB_ERR_BAD_ARG;
+  if (len == 0) return HJB_OK;
+  const float bc1 = (float)(1.0 - std::pow((double)b1, (double)step));
+  const float bc2 = (float)(1.0 - std::pow((double)b2, (double)step));
+  adam_kernel<<<(unsigned)((len + 255) / 256), 256, 0, (cudaStream_t)stream>>>(params, m, v, grad, len, lr, b1, b2, eps, bc1, bc2);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? HJB_OK : (int)e;
+}
+
+}  // extern "C"

@@ -1,0 +1,8 @@
+// vhjb kernel instantiations for one system; see vhjb_simt.cuh.
+#include "vhjb_simt.cuh"
+
+namespace hjb {
+cudaError_t vhjb_launch_linear21(const VhjbArgs& a, const VhjbLaunch& l, int act, int uform, int rform, cudaStream_t st) {
+  return launch_vhjb_system<LinearSys<2, 1, false>, true>(a, l, act, uform, rform, st);
+}
+}  // namespace hjb

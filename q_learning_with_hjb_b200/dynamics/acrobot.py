@@ -66,3 +66,16 @@ class Acrobot(Dynamics):
 
     def system_params(self):
         return [self.l1, self.l2, self.m1, self.m2, self.I1, self.I2, self.g], np.zeros(0), np.zeros(0)
+
+    def linearize(self, xf, uf):
+        """(A, B) about an equilibrium (xf, uf); see Cartpole.linearize."""
+        Minv = np.linalg.inv(self.get_M(xf))
+        g1 = (self.m1 * self.l1 / 2 + self.m2 * self.l1) * self.g
+        g12 = self.m2 * self.g * self.l2 / 2
+        c1, c12 = np.cos(xf[0]), np.cos(xf[0] + xf[1])
+        dG_dq = np.array([[g1 * c1 + g12 * c12, g12 * c12], [g12 * c12, g12 * c12]])
+        A = np.zeros((4, 4))
+        A[0, 2] = A[1, 3] = 1.0
+        A[2:, :2] = -Minv @ dG_dq
+        B = np.concatenate([np.zeros(2), Minv @ self.get_B()]).reshape(4, 1)
+        return A, B

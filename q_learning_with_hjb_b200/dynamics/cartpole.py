@@ -29,3 +29,14 @@ class Cartpole(Dynamics):
 
     def system_params(self):
         return [self.mc, self.mp, self.l, self.g], np.zeros(0), np.zeros(0)
+
+    def linearize(self, xf, uf):
+        """(A, B) about an equilibrium (xf, uf), host side, once: A = [[0, I], [-M^-1 dG/dq, 0]], B = [0; M^-1 B]
+        (the M^-1 derivative multiplies B uf - G(qf) = 0 at an equilibrium; C dq vanishes with dq = 0)."""
+        Minv = np.linalg.inv(self.get_M(xf))
+        dG_dq = np.array([[0.0, 0.0], [0.0, self.mp * self.g * self.l * np.cos(xf[1])]])
+        A = np.zeros((4, 4))
+        A[0, 2] = A[1, 3] = 1.0
+        A[2:, :2] = -Minv @ dG_dq
+        B = np.concatenate([np.zeros(2), Minv @ self.get_B()]).reshape(4, 1)
+        return A, B

@@ -31,3 +31,7 @@ class LinearDynamics(Dynamics):
         Ad, Bd, *_ = scipy.signal.cont2discrete((np.asarray(self.A, np.float64), np.asarray(self.B, np.float64),
                                                   np.eye(n), np.zeros((n, m))), dt=self.dt if dt is None else dt)
         return Ad, Bd
+
+    def linearize(self, xf, uf):
+        """(A, B) of xdot ~ A (x - xf) + B (u - uf): the system matrices themselves."""
+        return np.asarray(self.A, dtype=np.float64), np.asarray(self.B, dtype=np.float64)

@@ -18,6 +18,20 @@ class Quadrotors2D(Dynamics):
     def system_params(self):
         return [self.g, self.m, self.r, self.I], np.zeros(0), np.zeros(0)
 
+    def linearize(self, xf, uf):
+        """(A, B) of xdot ~ A (x - xf) + B (u - uf) about (xf, uf), host side, once (at hover: the matrices of
+        controller/quadrotors_model_based_controller.py:25-31)."""
+        th, thrust = xf[2], (uf[0] + uf[1]) / self.m
+        A = np.zeros((6, 6))
+        A[:3, 3:] = np.eye(3)
+        A[3, 2] = -np.cos(th) * thrust
+        A[4, 2] = -np.sin(th) * thrust
+        B = np.zeros((6, 2))
+        B[3, :] = -np.sin(th) / self.m
+        B[4, :] = np.cos(th) / self.m
+        B[5, :] = [self.r / self.I, -self.r / self.I]
+        return A, B
+
 
 class NearHoverQuadcopter(Dynamics):
     """x = [p_x, p_y, p_z, theta_x, theta_y, v_x, v_y, v_z, omega_x, omega_y], u = [Tz, Sx, Sy]."""
@@ -30,3 +44,14 @@ class NearHoverQuadcopter(Dynamics):
 
     def system_params(self):
         return [self.g, self.m, self.kT, self.n0], np.zeros(0), np.zeros(0)
+
+    def linearize(self, xf, uf):
+        """(A, B) about (xf, uf) (at hover: controller/quadrotors_model_based_controller.py:58-68)."""
+        A = np.zeros((10, 10))
+        A[:5, 5:] = np.eye(5)
+        A[5, 3] = self.g / np.cos(xf[3]) ** 2
+        A[6, 4] = self.g / np.cos(xf[4]) ** 2
+        B = np.zeros((10, 3))
+        B[7, 0] = self.kT / self.m
+        B[8, 1] = B[9, 2] = self.n0
+        return A, B

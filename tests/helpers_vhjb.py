@@ -58,3 +58,46 @@ def exact_quadratic_weights(n, P, eps_s=1e-3):
     W3[:n, :n] = Lc.T
     W3[n:2 * n, :n] = -Lc.T
     return [W1, W2, W3]
+
+
+# ---- product-side construction (q_learning_with_hjb_b200) for the same problems ----
+def make_kernels(name: str):
+    """VhjbKernels + the matching oracle problem for a named problem."""
+    from q_learning_with_hjb_b200.controller.vhjb import VhjbKernels
+    from tests.helpers import make_dynamics
+    p = problem(name)
+    kind = {"linear": "linear", "cartpole": "cartpole", "cartpole_tanh": "cartpole", "quad2d": "quad2d",
+            "quad10d": "quad10d", "di_mintime": "linear"}[name]
+    dyn = make_dynamics(kind)
+    if name == "di_mintime":
+        dyn.dt = 0.01
+        dyn.umin, dyn.umax = np.float32([-1]), np.float32([1])
+    k = VhjbKernels(dyn, p.xf, p.uf, p.Q, p.R, p.mean, p.std, p.eps, p.eps_s, act=p.act,
+                    control_form={"clip": "clipped", "bang": "bangbang"}[p.control_form],
+                    residual_form=p.residual_form)
+    return k, p
+
+
+def flat_params(weights):
+    return np.concatenate([np.asarray(w, dtype=np.float32).reshape(-1) for w in weights])
+
+
+def smoke():
+    """One small fused vhjb loss+gradient step on cuda:0 against the torch-fp64 oracle (used by __graft_entry__)."""
+    import torch
+    k, p = make_kernels("quad10d")
+    W = V.init_weights(p.sys.n, seed=0)
+    W32 = [w.astype(np.float32) for w in W]
+    xs, dones, costs = sample_batch("quad10d", 2048, seed=1)
+    params = torch.as_tensor(flat_params(W32)).cuda()
+    xd, dd, cd = (torch.as_tensor(a).cuda() for a in (xs, dones, costs))
+    k.counts(dd, p.eps)
+    grad, sums = k.loss_grad(params, xd, dd, cd, 0.5)
+    orc = V.VhjbOracle(p, [w.astype(np.float64) for w in W32])
+    total, hjb, term, grads, _ = orc.loss_and_grad(xs, dones, costs, 0.5)
+    g = grad.cpu().numpy()
+    go = np.concatenate([x.reshape(-1) for x in grads])
+    gerr = np.abs(g - go).max() / np.abs(go).max()
+    herr = abs(float(sums[0] / k.norm[0]) - hjb) / hjb
+    assert gerr < 1e-4 and herr < 1e-4, (gerr, herr)
+    print(f"smoke: vhjb quad10d loss+grad 2048 states: grad err {gerr:.2e}, hjb loss err {herr:.2e}")

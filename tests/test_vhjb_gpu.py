@@ -1,0 +1,211 @@
+"""GPU parity tests for hot path (b): the fused vhjb kernels (through the ctypes C ABI) against the torch-float64
+oracle (oracle/vhjb_oracle.py).  Tolerance (north_star): HJB residual, loss and gradient within 1e-4.
+
+Per-sample quantities are discontinuous functions of the parameters (ReLU kinks move dV/dx by a finite jump, the
+input clip and |.| have kinks): a state whose pre-activation lies within fp32 rounding of a kink may land on the
+other side than float64 does.  Such samples are counted as outliers against a stated budget; losses and gradients
+(sums over the batch) are compared without any budget.
+"""
+import numpy as np
+import pytest
+
+from oracle import vhjb_oracle as V
+from tests.helpers_vhjb import exact_quadratic_weights, flat_params, make_kernels, problem, sample_batch
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+
+
+def _cuda():
+    import torch
+    assert torch.cuda.is_available()
+    return torch
+
+
+def _dev(torch, *arrays):
+    return [torch.as_tensor(np.ascontiguousarray(a, dtype=np.float32)).cuda() for a in arrays]
+
+
+def _setup(name, B, seed=0, wseed=0):
+    torch = _cuda()
+    k, p = make_kernels(name)
+    W32 = [w.astype(np.float32) for w in V.init_weights(p.sys.n, seed=wseed)]
+    xs, dones, costs = sample_batch(name, B, seed=seed)
+    orc = V.VhjbOracle(p, [w.astype(np.float64) for w in W32])
+    params = torch.as_tensor(flat_params(W32)).cuda()
+    return torch, k, p, orc, params, xs, dones, costs
+
+
+NAMES = ["linear", "cartpole", "cartpole_tanh", "quad2d", "quad10d", "di_mintime"]
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_residual_pieces_match_oracle(name):
+    B = 20000 + 17                                   # not a multiple of the 32-state tile
+    torch, k, p, orc, params, xs, dones, costs = _setup(name, B)
+    xd, dd, cd = _dev(torch, xs, dones, costs)
+    out, sums = k.residual(params, xd, dd, cd)
+    q = orc.pieces(xs, running=costs if p.residual_form == "min_time" else None)
+    ref = {key: q[key].detach().numpy() for key in ("V", "p", "u", "r")}
+    got = {key: out[key].cpu().numpy().astype(np.float64) for key in ("V", "p", "u", "r")}
+    budget = {"V": 0.0, "p": 2e-3, "u": 2e-3, "r": 2e-3} if p.act == "relu" else {"V": 0, "p": 1e-4, "u": 1e-4, "r": 1e-4}
+    for key in ("V", "p", "u", "r"):
+        a, b = got[key].reshape(B, -1), ref[key].reshape(B, -1)
+        scale = np.maximum(np.abs(b), np.abs(b).mean(axis=0, keepdims=True) + 1e-30)
+        err = (np.abs(a - b) / scale).max(axis=1)
+        frac = float(np.mean(err > TOL))
+        assert frac <= budget[key], (key, frac, float(np.median(err)))
+        assert np.median(err) < 1e-5
+    # un-normalised loss sums
+    hjb, term, _ = orc.losses(xs, dones, costs)
+    d = dones.astype(np.float64)
+    if p.residual_form == "normalized":
+        assert abs(float(sums[0]) / ((1 - d).sum() + p.eps) - float(hjb)) < TOL * float(hjb)
+        assert abs(float(sums[1]) / (d.sum() + p.eps) - float(term)) < TOL * float(term)
+    else:
+        assert abs(float(sums[0]) / B - float(hjb)) < TOL * float(hjb)
+
+
+@pytest.mark.parametrize("name", NAMES)
+@pytest.mark.parametrize("B", [256, 4096 + 5])
+def test_loss_and_gradient_match_oracle(name, B):
+    torch, k, p, orc, params, xs, dones, costs = _setup(name, B, seed=3, wseed=2)
+    xd, dd, cd = _dev(torch, xs, dones, costs)
+    reg = 0.37
+    if p.residual_form == "min_time":
+        k.norm.copy_(torch.tensor([float(B), 1.0]))
+    else:
+        k.counts(dd, p.eps)
+        d = dones.astype(np.float64)
+        np.testing.assert_allclose(k.norm.cpu().numpy(), [(1 - d).sum() + p.eps, d.sum() + p.eps], rtol=1e-6)
+    grad, sums = k.loss_grad(params, xd, dd, cd, reg)
+    total, hjb, term, grads, _ = orc.loss_and_grad(xs, dones, costs, reg)
+    g = grad.cpu().numpy().astype(np.float64)
+    go = np.concatenate([x.reshape(-1) for x in grads])
+    assert g.shape == go.shape
+    off = 0
+    for gi in grads:                                   # per-matrix normwise error
+        sl = slice(off, off + gi.size); off += gi.size
+        assert np.abs(g[sl] - go[sl]).max() <= TOL * np.abs(go[sl]).max(), (name, gi.shape)
+    norm = k.norm.cpu().numpy().astype(np.float64)
+    s = sums.cpu().numpy().astype(np.float64)
+    assert abs(s[0] / norm[0] - hjb) <= TOL * hjb
+    if p.residual_form == "normalized":
+        assert abs(s[1] / norm[1] - term) <= TOL * term
+        assert abs(s[0] / norm[0] + reg * s[1] / norm[1] - total) <= TOL * total
+
+
+def test_lqr_fixed_point_through_cuda():
+    """V = z^T P z represented exactly by the relu net => the HJB residual vanishes (no saturation)."""
+    import scipy.linalg
+    torch = _cuda()
+    k, p = make_kernels("linear")
+    A, Bm = p.sys.par["A"], p.sys.par["B"]
+    P = scipy.linalg.solve_continuous_are(A, Bm, p.Q, p.R)
+    params = torch.as_tensor(flat_params(exact_quadratic_weights(2, P, p.eps_s))).cuda()
+    xs = np.random.default_rng(0).uniform(-1, 1, size=(4096, 2)).astype(np.float32)
+    xs = xs[np.abs(xs @ P @ Bm).ravel() < 4.9]          # |u| = |B^T P x| < umax = 5: unsaturated
+    xd, dd, cd = _dev(torch, xs, np.zeros(len(xs)), np.ones(len(xs)))
+    out, _ = k.residual(params, xd, dd, cd)
+    np.testing.assert_allclose(out["V"].cpu().numpy(), np.einsum("bi,ij,bj->b", xs, P, xs), rtol=2e-5, atol=1e-6)
+    np.testing.assert_allclose(out["p"].cpu().numpy(), 2 * xs @ P, rtol=2e-5, atol=1e-5)
+    np.testing.assert_allclose(out["u"].cpu().numpy(), -(xs @ P @ Bm), rtol=2e-5, atol=1e-5)
+    assert np.abs(out["r"].cpu().numpy()).max() < 2e-4
+
+
+def test_adam_matches_optax_definition():
+    torch = _cuda()
+    k, p = make_kernels("linear")
+    rng = np.random.default_rng(0)
+    n = k.P
+    w = rng.normal(size=n).astype(np.float32); m = np.zeros(n); v = np.zeros(n)
+    wd = torch.as_tensor(w.copy()).cuda(); md = torch.zeros(n, device="cuda"); vd = torch.zeros(n, device="cuda")
+    w64 = w.astype(np.float64)
+    for step in range(1, 6):
+        g = (rng.normal(size=n) * 10.0 ** rng.integers(-6, 2)).astype(np.float32)
+        k.adam(wd, md, vd, torch.as_tensor(g).cuda(), step, 1e-3)
+        w64, m, v = V.adam_step(w64, m, v, g.astype(np.float64), step)
+        np.testing.assert_allclose(wd.cpu().numpy(), w64, rtol=1e-5, atol=1e-7)
+
+
+def test_deterministic_and_shard_additive():
+    """Bitwise reproducible; and the gradient of a batch equals the sum of the gradients of its two shards when both
+    use the global normaliser — what the multi-GPU all-reduce relies on."""
+    torch, k, p, orc, params, xs, dones, costs = _setup("quad10d", 8192, seed=5)
+    xd, dd, cd = _dev(torch, xs, dones, costs)
+    k.counts(dd, p.eps)
+    g1 = k.loss_grad(params, xd, dd, cd, 0.2)[0].clone()
+    s1 = k.sums.clone()
+    g2 = k.loss_grad(params, xd, dd, cd, 0.2)[0].clone()
+    assert torch.equal(g1, g2) and torch.equal(s1, k.sums)
+    h = 4096 + 96
+    ga = k.loss_grad(params, xd[:h].contiguous(), dd[:h].contiguous(), cd[:h].contiguous(), 0.2)[0].clone()
+    sa = k.sums.clone()
+    gb = k.loss_grad(params, xd[h:].contiguous(), dd[h:].contiguous(), cd[h:].contiguous(), 0.2)[0].clone()
+    sb = k.sums.clone()
+    assert (ga + gb - g1).abs().max() <= 2e-5 * g1.abs().max()
+    assert ((sa + sb) - s1).abs().max() <= 1e-5 * s1.abs().max()
+
+
+def test_controller_params_update_matches_oracle_and_trains():
+    """VHJBController (reference interface, cartpole gin files): one params_update == oracle loss/grad + Adam; a few
+    epochs of train() run and return the reference's six lists."""
+    import os
+    torch = _cuda()
+    from q_learning_with_hjb_b200.configs import gin_compat as gin
+    from q_learning_with_hjb_b200.configs.controller.vhjb_controller_config import VHJBControllerConfig
+    from q_learning_with_hjb_b200.controller.vhjb import VHJBController
+    from tests.helpers import PKG, make_dynamics
+    dyn = make_dynamics("cartpole")
+    gin.parse_config_file(os.path.join(PKG, "configs", "controller", "cartpole_vhjb_controller.gin"))
+    cfg = VHJBControllerConfig()
+    cfg.epochs, cfg.num_of_trajectories_per_epoch, cfg.maximum_step = 2, 3, 30
+    ctl = VHJBController(dyn, cfg)
+    assert len(ctl.replay_buffer) == 20 and ctl.P.shape == (4, 4)
+    W32 = [kk.cpu().numpy().copy() for kk in ctl.model_params.kernels()]
+    xs, dones, costs = sample_batch("cartpole", 256, seed=9)
+    p = problem("cartpole")
+    orc = V.VhjbOracle(p, [w.astype(np.float64) for w in W32])
+    total, hjb, term, grads, _ = orc.loss_and_grad(xs, dones, costs, 1e-5)
+    params, states, opt, t, h, tm = ctl.params_update(ctl.model_params, ctl.model_states, ctl.optimizer_states,
+                                                      xs, dones, costs, 1e-5)
+    assert abs(float(h) - hjb) <= TOL * hjb and abs(float(tm) - term) <= TOL * term and abs(float(t) - total) <= TOL * total
+    assert opt.count == 1 and states == {}
+    off = 0
+    for w, g in zip(W32, grads):   # first Adam step moves each weight by -lr * sign(g) (up to eps)
+        new = params.flat[off:off + w.size].cpu().numpy().reshape(w.shape); off += w.size
+        wn, _, _ = V.adam_step(w.astype(np.float64), 0, 0, g, 1)
+        big = np.abs(g) > 1e-6 * np.abs(g).max()
+        np.testing.assert_allclose(new[big], wn[big], rtol=0, atol=2e-6)
+    # single-state interface
+    x = dyn.get_initial_state()
+    u = ctl.get_control_efforts(x)
+    assert u.shape == (1,)
+    uq = V.VhjbOracle(p, [kk.cpu().numpy().astype(np.float64) for kk in ctl.model_params.kernels()]).pieces(x[None])["u"]
+    assert abs(u[0] - float(uq[0, 0])) < 1e-3 * max(1.0, abs(float(uq[0, 0])))
+    lists = ctl.train()
+    assert len(lists) == 6 and len(lists[0]) == 2 and all(np.isfinite(v) for v in lists[3])
+
+
+def test_full_size_batch_is_consistent_with_its_chunks():
+    """C5 per-GPU size (1,048,576 states, n = 10): loss sums and gradient equal the sum over 16 chunks."""
+    torch, k, p, orc, params, xs, dones, costs = _setup("quad10d", 1 << 20, seed=11)
+    xd, dd, cd = _dev(torch, xs, dones, costs)
+    k.counts(dd, p.eps)
+    g = k.loss_grad(params, xd, dd, cd, 0.1)[0].clone()
+    s = k.sums.clone()
+    acc_g, acc_s = torch.zeros_like(g), torch.zeros_like(s)
+    for c in range(16):
+        sl = slice(c << 16, (c + 1) << 16)
+        acc_g += k.loss_grad(params, xd[sl].contiguous(), dd[sl].contiguous(), cd[sl].contiguous(), 0.1)[0]
+        acc_s += k.sums
+    assert torch.isfinite(g).all() and g.abs().max() > 0
+    assert (acc_g - g).abs().max() <= 5e-5 * g.abs().max()
+    assert (acc_s - s).abs().max() <= 5e-5 * s.abs().max()
+    # and a 65,536-state chunk agrees with the float64 oracle
+    sl = slice(0, 1 << 16)
+    norm = k.norm.cpu().numpy().astype(np.float64)
+    out, sums = k.residual(params, xd[sl].contiguous(), dd[sl].contiguous(), cd[sl].contiguous(), want=())
+    hjb, term, _ = orc.losses(xs[sl], dones[sl], costs[sl])
+    d = dones[sl].astype(np.float64)
+    assert abs(float(sums[0]) / ((1 - d).sum() + p.eps) - float(hjb)) <= TOL * float(hjb)
