@@ -212,16 +212,7 @@ def run_rollout(args, w, integ):
         torch.cuda.synchronize()
 
     # ---- FP32 FMA peak probe (roofline denominator for the CUDA-core bound) ----
-    sink = torch.empty(148 * 8 * 256 * 2, device="cuda", dtype=torch.float32)
-    import ctypes as C
-    flops = C.c_double(0)
-    for _ in range(2):
-        L.check(L.lib().hjb_fma_peak_probe(L.ptr(sink), sink.numel(), 20000, C.byref(flops), L.stream_ptr()))
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    L.check(L.lib().hjb_fma_peak_probe(L.ptr(sink), sink.numel(), 20000, C.byref(flops), L.stream_ptr()))
-    e1.record(); torch.cuda.synchronize()
-    fma_peak_tflops = flops.value / (e0.elapsed_time(e1) * 1e-3) / 1e12
+    fma_peak_tflops = measure_fma_peak()
 
     # ---- device-resident timing (`value`) ----
     clocks = ClockSampler(local); clocks.start()
@@ -253,11 +244,23 @@ def run_rollout(args, w, integ):
     barrier()
     e2e_ms = t0.elapsed_time(t1)
     checksum = float(cost_host.double().mean())
+    h2d_bytes, d2h_bytes = plan.h2d_bytes(), plan.d2h_bytes()
 
     times = torch.tensor([total_ms, e2e_ms], device="cuda", dtype=torch.float64)
     if world > 1:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
     total_ms, e2e_ms = times.tolist()
+
+    # ---- the metric's second half: HJB-residual states/s (C5), measured in the same run ----
+    vhjb = None
+    if args.workload == DEFAULT_WORKLOAD and not args.no_vhjb:
+        del plan, x0_dev
+        torch.cuda.empty_cache()
+        vhjb = measure_vhjb(VHJB["vhjb_quad10d"], args.steps, args.warmup, rank, world, local,
+                            want_cpu=(world == 1 and not args.no_cpu_baseline))
+        if vhjb is not None:
+            vhjb["roofline"]["peak"] = fma_peak_tflops
+            vhjb["roofline"]["frac"] = vhjb["roofline"]["achieved"] / fma_peak_tflops
     units = float(envs) * T * args.steps * world
     value = units / (total_ms * 1e-3)
     e2e_value = units / (e2e_ms * 1e-3)
@@ -302,15 +305,216 @@ def run_rollout(args, w, integ):
                        "trig": "accurate" if args.accurate_trig else "mufu", "parallelism": f"env-shard x{world}",
                        "l2": "inputs larger than L2 (x0 >= 400 MB per launch)" if envs * n * 4 > 126e6 else "small workload",
                        "seed": "1234 + rank"},
-            "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": plan.h2d_bytes(),
-                    "d2h_bytes_per_step": plan.d2h_bytes(), "ms_per_step": e2e_ms / args.steps, "checksum_mean_cost": checksum},
+            "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": h2d_bytes,
+                    "d2h_bytes_per_step": d2h_bytes, "ms_per_step": e2e_ms / args.steps, "checksum_mean_cost": checksum},
             "gpu_launches": args.steps,
             "kernel_ms": kernel_ms,
             "roofline": roof, "cpu_baseline": cpu, "clocks": clk,
+            "vhjb": vhjb,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# vhjb: HJB-residual + value-net training step on sampled states
+# ---------------------------------------------------------------------------------------------------------------
+VHJB = {
+    "vhjb_quad10d": dict(problem="quad10d", states=1 << 20,
+                         label="C5: 10-D quadcopter vhjb value learning, 1,048,576 states per GPU per iteration "
+                               "(8M/iter on 8 GPUs), residual + loss-gradient + grad all-reduce + Adam"),
+    "vhjb_di": dict(problem="di_mintime", states=1 << 20,
+                    label="C2: double integrator minimum-time vhjb (sin net, bang-bang), 1M sampled states, "
+                          "residual + loss-gradient + Adam"),
+}
+# logical fp32 flops per state: 17 GEMMs of the full pass / 6 GEMMs of the residual-only pass
+VHJB_FLOPS_FULL = lambda n: 1280 * n + 294912
+VHJB_FLOPS_RES = lambda n: 512 * n + 98304
+
+
+def _cpu_vhjb_worker(args):
+    name, B, threads, full = args
+    import torch
+    torch.set_num_threads(threads)
+    from oracle import vhjb_oracle as V
+    from tests.helpers_vhjb import problem, sample_batch
+    V.set_dtype(torch.float32)          # the reference's JAX code computes in float32
+    p = problem(name)
+    orc = V.VhjbOracle(p, V.init_weights(p.sys.n, seed=0))
+    xs, dones, costs = sample_batch(name, B, seed=7)
+    t0 = time.perf_counter()
+    if full:
+        orc.loss_and_grad(xs, dones, costs, 1e-5)
+    else:
+        orc.losses(xs, dones, costs)
+    return time.perf_counter() - t0
+
+
+def cpu_vhjb_throughput(name, B, full=True):
+    """states/s of the torch-CPU restatement (oracle/vhjb_oracle.py, float32, all host threads)."""
+    cores = os.cpu_count() or 1
+    ctx = mp.get_context("spawn")
+    with ctx.Pool(1) as pool:
+        pool.map(_cpu_vhjb_worker, [(name, max(1024, B // 8), cores, full)])      # warm-up
+        dt = pool.map(_cpu_vhjb_worker, [(name, B, cores, full)])[0]
+    return B / dt, dt, cores
+
+
+def measure_vhjb(w, steps, warmup, rank, world, local, want_cpu):
+    """Returns the dict describing the vhjb measurement (rank 0) — used for the vhjb workloads' own JSON line and as
+    the secondary measurement attached to the default line."""
+    import torch
+    import torch.distributed as dist
+    from oracle import vhjb_oracle as V          # weights init + synthetic batch only (not on the timed path)
+    from tests.helpers_vhjb import flat_params, make_kernels, sample_batch
+    from q_learning_with_hjb_b200.controller.vhjb import AdamState
+
+    B = w["states"]
+    k, p = make_kernels(w["problem"])
+    n = p.sys.n
+    W = V.init_weights(n, seed=0)
+    params = torch.as_tensor(flat_params(W)).cuda()
+    opt = AdamState(0, torch.zeros_like(params), torch.zeros_like(params))
+    xs, dones, costs = sample_batch(w["problem"], B, seed=1234 + rank)
+    host = [torch.as_tensor(a).pin_memory() for a in (xs, dones, costs)]
+    dev = [h.cuda() for h in host]
+    stage = [torch.empty_like(d) for d in dev]
+    out_host = torch.empty(4, dtype=torch.float32).pin_memory()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, iters):
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(iters):
+            fn()
+        b.record()
+        barrier()
+        ms = torch.tensor([a.elapsed_time(b)], device="cuda", dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    def train():
+        k.train_step(params, opt, dev[0], dev[1], dev[2], 1e-5, 1e-3)
+
+    def residual_only():
+        k.residual(params, dev[0], dev[1], dev[2], want=())
+
+    def e2e():
+        for s, h in zip(stage, host):
+            s.copy_(h, non_blocking=True)
+        sums, norm = k.train_step(params, opt, stage[0], stage[1], stage[2], 1e-5, 1e-3)
+        out_host[:2].copy_(sums, non_blocking=True)
+        out_host[2:].copy_(norm, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    for _ in range(max(warmup, 3)):
+        train(); residual_only()
+    clocks = ClockSampler(local); clocks.start()
+    wall0 = time.time()
+    train_ms = timed(train, steps)
+    clk = clocks.stop(wall0, time.time())
+    res_ms = timed(residual_only, steps)
+    for _ in range(2):
+        e2e()
+    e2e_ms = timed(e2e, steps)
+    if rank != 0:
+        return None
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except OSError:
+        pass
+    train_rate = B * world * steps / (train_ms * 1e-3)
+    res_rate = B * world * steps / (res_ms * 1e-3)
+    e2e_rate = B * world * steps / (e2e_ms * 1e-3)
+    per_gpu = B * steps / (train_ms * 1e-3)
+    logical_tflops = per_gpu * VHJB_FLOPS_FULL(n) / 1e12
+    tf32_peak = peaks.get("bf16_tflops", 1590.0) / 2
+    d = {
+        "metric": "HJB-residual states/s (residual + loss-gradient + Adam train step)", "value": train_rate,
+        "unit": "states/s", "n_gpus": world, "steps": steps, "warmup": max(warmup, 3), "ms_per_step": train_ms / steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": w["label"], "states_per_gpu": B, "value_net": [n, 128, 128, 64],
+                   "activation": p.act, "parallelism": f"state-shard x{world}, grad all-reduce" if world > 1 else "single GPU",
+                   "l2": "states (>= 40 MB) streamed once per step; weights resident in shared memory", "seed": "1234 + rank"},
+        "residual_only_states_per_s": res_rate,
+        "e2e": {"value": e2e_rate, "unit": "states/s", "h2d_bytes_per_step": int(sum(h.numel() * 4 for h in host)),
+                "d2h_bytes_per_step": 16, "ms_per_step": e2e_ms / steps},
+        "gpu_launches": steps * 6,   # count x2, fused pass, reduce x2, adam
+        "roofline": {"bound": "fp32", "achieved": logical_tflops, "unit": "TFLOP/s",
+                     "peak": None, "frac": None, "traffic": None,
+                     "flops_per_state": VHJB_FLOPS_FULL(n), "kernel": "vhjb_kernel (CUDA-core fp32 version)",
+                     "tensor_peak_tf32": tf32_peak,
+                     "note": "this round's kernel runs the 17 GEMMs on CUDA cores in fp32; fraction is of the FP32 FMA peak"},
+        "clocks": clk,
+    }
+    if want_cpu:
+        v, dt, cores = cpu_vhjb_throughput(w["problem"], 1 << 16, full=True)
+        d["cpu_baseline"] = {"value": v, "unit": "states/s", "cores": cores, "kind": "port",
+                             "sample": f"65536 states, torch-CPU float32 restatement (oracle/vhjb_oracle.py), {cores} threads, {dt:.1f} s"}
+    return d
+
+
+def run_vhjb(args, w):
+    rank, world, local = dist_setup(args.gpus)
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        vals, t_all = [], 0.0
+        Bs = 1 << 16
+        for _ in range(args.steps):
+            v, dt, cores = cpu_vhjb_throughput(w["problem"], Bs, full=True)
+            vals.append(v); t_all += dt
+        value = float(np.mean(vals))
+        sample = f"{Bs} states per bench step, torch-CPU float32 restatement of controller/vhjb.py (oracle/vhjb_oracle.py), {cores} threads"
+        print(json.dumps({
+            "impl": "reference", "metric": "HJB-residual states/s (residual + loss-gradient + Adam train step)",
+            "value": value, "unit": "states/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * t_all / max(1, args.steps), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": {"workload": w["label"], "sample": sample},
+            "cpu_baseline": {"value": value, "unit": "states/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": "states/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}), flush=True)
+        return
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the product path is CUDA-only)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    d = measure_vhjb(w, args.steps, args.warmup, rank, world, local, want_cpu=(world == 1 and not args.no_cpu_baseline))
+    if rank == 0:
+        fma = measure_fma_peak()
+        d["roofline"]["peak"] = fma
+        d["roofline"]["frac"] = d["roofline"]["achieved"] / fma
+        d["roofline"]["peak_source"] = "measured: hjb_fma_peak_probe FFMA-only kernel in this run"
+        print(json.dumps(d), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def measure_fma_peak():
+    """FP32 FMA peak (TFLOP/s) of this GPU, measured with the library's FFMA-only probe kernel."""
+    import ctypes as C
+    import torch
+    from q_learning_with_hjb_b200 import _lib as L
+    sink = torch.empty(148 * 8 * 256 * 2, device="cuda", dtype=torch.float32)
+    flops = C.c_double(0)
+    for _ in range(2):
+        L.check(L.lib().hjb_fma_peak_probe(L.ptr(sink), sink.numel(), 20000, C.byref(flops), L.stream_ptr()))
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    L.check(L.lib().hjb_fma_peak_probe(L.ptr(sink), sink.numel(), 20000, C.byref(flops), L.stream_ptr()))
+    e1.record(); torch.cuda.synchronize()
+    return flops.value / (e0.elapsed_time(e1) * 1e-3) / 1e12
 
 
 def main():
@@ -326,11 +530,14 @@ def main():
     ap.add_argument("--record-stride", type=int, default=0)
     ap.add_argument("--accurate-trig", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-vhjb", action="store_true", help="skip the secondary vhjb measurement of the default line")
     args = ap.parse_args()
     if args.workload in ROLLOUTS:
         run_rollout(args, ROLLOUTS[args.workload], args.integrator)
+    elif args.workload in VHJB:
+        run_vhjb(args, VHJB[args.workload])
     else:
-        raise SystemExit(f"unknown workload {args.workload}; choose from {sorted(ROLLOUTS)}")
+        raise SystemExit(f"unknown workload {args.workload}; choose from {sorted(ROLLOUTS) + sorted(VHJB)}")
 
 
 if __name__ == "__main__":

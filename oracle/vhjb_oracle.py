@@ -72,6 +72,12 @@ class VhjbProblem:
                                          # (double_integrator nb cell 11:20, l_i = 1[|x|^2 > 1e-4] from cell 7:4)
 
 
+def set_dtype(dtype):
+    """float64 (default, the checker) or float32 (CPU-baseline timing: the reference's JAX code is float32)."""
+    global DT
+    DT = dtype
+
+
 def _t(a):
     return torch.as_tensor(np.asarray(a, dtype=np.float64), dtype=DT)
 
