@@ -1,0 +1,16 @@
+#!/bin/bash
+# ncu evidence (run under gpurun, one GPU):  TAG=<name> KERNEL=<regex> BENCH_ARGS="..." bash profiles/gpu_profile.sh
+# Each ncu pass runs only after the same command has exited 0 without ncu.  Outputs land in gpurun_out/;
+# profiles/summarize_ncu.py turns them into the committed summaries.
+set -u
+CMD="python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-vhjb ${BENCH_ARGS:-}"
+TAG=${TAG:-rollout}
+KERNEL=${KERNEL:-rollout_kernel}
+$CMD > gpurun_out/${TAG}_plain.log 2>&1 &&
+ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv \
+    --log-file gpurun_out/${TAG}_launches.csv $CMD > gpurun_out/${TAG}_ncu_launches.log 2>&1
+$CMD > gpurun_out/${TAG}_plain2.log 2>&1 &&
+ncu --set full --clock-control none --import-source on -k regex:${KERNEL} -s ${SKIP:-3} -c 1 \
+    -o gpurun_out/${TAG}_full -f $CMD > gpurun_out/${TAG}_ncu_full.log 2>&1
+tail -1 gpurun_out/${TAG}_plain.log | cut -c1-300
+tail -2 gpurun_out/${TAG}_ncu_full.log

@@ -166,21 +166,15 @@ class VhjbKernels:
     def train_step(self, params_flat, opt: AdamState, xs, dones, costs, reg: float, lr: float, group=None):
         """count -> [all-reduce] -> fused loss+grad -> [all-reduce] -> Adam.  Returns the device tensor
         [hjb_sum, term_sum] (un-normalised, global) and the norm tensor; no host synchronisation."""
-        torch = self.torch
-        dist = torch.distributed if (torch.distributed.is_available() and torch.distributed.is_initialized()) else None
-        if self.residual_form == "min_time":
-            self.counts(dones, 0.0)                   # done == 0 everywhere: norm[0] = B (plain mean)
-        else:
-            self.counts(dones, 0.0)
-        if dist is not None:
-            dist.all_reduce(self.norm, group=group)
-        if self.residual_form == "min_time":
+        from q_learning_with_hjb_b200 import parallel
+        self.counts(dones, 0.0)
+        if self.residual_form == "min_time":           # plain mean over the global batch; no boundary term
+            parallel.global_counts(self.norm, 0.0, group)
             self.norm[1] = 1.0
         else:
-            self.norm += self.eps
+            parallel.global_counts(self.norm, self.eps, group)
         self.loss_grad(params_flat, xs, dones, costs, reg)
-        if dist is not None:
-            dist.all_reduce(self.grad_and_sums, group=group)
+        parallel.sum_across_ranks(self.grad_and_sums, group)
         opt.count += 1
         self.adam(params_flat, opt.mu, opt.nu, self.grad, opt.count, lr)
         return self.sums, self.norm
