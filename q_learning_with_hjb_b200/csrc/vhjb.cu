@@ -3,11 +3,22 @@
 #include <cmath>
 #include <cstring>
 
+#include <cstdlib>
+
 #include "vhjb_simt.cuh"
+#include "vhjb_tc.cuh"
 
 namespace hjb {
 
 constexpr int kMaxCtas = 160;  // >= SM count (148 on B200)
+
+// Kernel selection: the tcgen05 kernel (vhjb_tc.cuh) wherever it is compiled (relu value nets), the CUDA-core
+// kernel (vhjb_simt.cuh) otherwise.  HJB_VHJB_IMPL=simt forces the CUDA-core kernel (A/B measurements, parity).
+static bool use_tensor_path(const hjb_vnet* net, int64_t B) {
+  if (net->act != HJB_ACT_RELU || B <= 0) return false;
+  const char* e = std::getenv("HJB_VHJB_IMPL");
+  return !(e && std::strcmp(e, "simt") == 0);
+}
 
 static int64_t pstride_of(int n) { return ((int64_t)vhjb_param_count(n) + 2 + 3) / 4 * 4; }
 
@@ -106,7 +117,9 @@ static int run_vhjb(const hjb_system* sys, const hjb_vnet* net, const hjb_task* 
   a.V = V; a.p = p; a.u = u; a.r = r;
   a.partial = static_cast<float*>(workspace);
   a.pstride = pstride_of(n);
-  a.n_tiles = (B + VBM - 1) / VBM;
+  const bool tensor = use_tensor_path(net, B);
+  const int tile = tensor ? tc::TS : VBM;
+  a.n_tiles = (B + tile - 1) / tile;
 
   VhjbLaunch l;
   l.grad = want_grad;
@@ -115,6 +128,17 @@ static int run_vhjb(const hjb_system* sys, const hjb_vnet* net, const hjb_task* 
   l.grid = (int)grid;
 
   cudaError_t e = cudaErrorNotSupported;
+  if (tensor) {
+    switch (sys->kind) {
+      case HJB_SYS_LINEAR:
+        if (n == 2 && m == 1) e = vhjb_tc_launch_linear21(a, l, net->act, task->control_form, task->residual_form, st);
+        break;
+      case HJB_SYS_CARTPOLE: e = vhjb_tc_launch_cartpole(a, l, net->act, task->control_form, task->residual_form, st); break;
+      case HJB_SYS_QUAD2D: e = vhjb_tc_launch_quad2d(a, l, net->act, task->control_form, task->residual_form, st); break;
+      case HJB_SYS_QUAD10D: e = vhjb_tc_launch_quad10d(a, l, net->act, task->control_form, task->residual_form, st); break;
+      default: break;
+    }
+  } else
   switch (sys->kind) {
     case HJB_SYS_LINEAR:
       if (n == 2 && m == 1) e = vhjb_launch_linear21(a, l, net->act, task->control_form, task->residual_form, st);
