@@ -224,6 +224,15 @@ int hjb_vhjb_loss_grad(const hjb_system* sys, const hjb_vnet* net, const hjb_tas
                        const float* dones, const float* costs, int64_t B, const float* norm, float reg, float* grad,
                        float* sums, void* workspace, void* stream);
 
+/*
+ * Range check of the last hjb_vhjb_loss_grad on this workspace (device float `count`, stream-ordered).  The
+ * tensor-core gradient pass carries per-state adjoints in fp16 with per-state power-of-two scaling (vhjb_tc.cuh);
+ * a state whose adjoint seed exceeds 2^26 times the batch-typical weight (only |x - xf| and |u - uf| ~ 1e-4 and
+ * below reach that with the reference's eps = 1e-10) is under-weighted and counted here.  0 for every other batch;
+ * callers that need those states exactly set HJB_VHJB_IMPL=simt (the fp32 CUDA-core kernel).
+ */
+int hjb_vhjb_saturation(const void* workspace, int32_t n, float* count, void* stream);
+
 /* optax.adam update (controller/vhjb.py:120, 286-287; defaults b1 = 0.9, b2 = 0.999, eps = 1e-8), in place on the
  * flat buffers; `step` is the 1-based index of this update. */
 int hjb_adam(float* params, float* m, float* v, const float* grad, int64_t len, float lr, float b1, float b2,

@@ -84,6 +84,7 @@ SYMBOLS = {
                                     _P, _P, _P, _P, _P, _P, _P]),
     "hjb_vhjb_loss_grad": (C.c_int, [C.POINTER(HjbSystem), C.POINTER(HjbVnet), C.POINTER(HjbTask), _P, _P, _P, C.c_int64,
                                      _P, C.c_float, _P, _P, _P, _P]),
+    "hjb_vhjb_saturation": (C.c_int, [_P, C.c_int32, _P, _P]),
     "hjb_adam": (C.c_int, [_P, _P, _P, _P, C.c_int64, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int32, _P]),
 }
 

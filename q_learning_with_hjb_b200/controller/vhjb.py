@@ -158,6 +158,14 @@ class VhjbKernels:
                                            L.ptr(self.workspace), L.stream_ptr()), "hjb_vhjb_loss_grad")
         return self.grad, self.sums
 
+    def saturated(self) -> int:
+        """Number of states of the last ``loss_grad`` whose adjoint seed left the tensor-core kernel's fp16 range
+        management (include/hjb_b200.h ``hjb_vhjb_saturation``); 0 except for states within ~1e-4 of the goal.
+        Synchronises the stream."""
+        out = self.torch.zeros(1, device="cuda", dtype=self.torch.float32)
+        L.check(L.lib().hjb_vhjb_saturation(L.ptr(self.workspace), self.n, L.ptr(out), L.stream_ptr()), "hjb_vhjb_saturation")
+        return int(out.item())
+
     def adam(self, params_flat, mu, nu, grad, step: int, lr: float, b1=0.9, b2=0.999, eps=1e-8):
         L.check(L.lib().hjb_adam(L.ptr(params_flat), L.ptr(mu), L.ptr(nu), L.ptr(grad), params_flat.numel(), float(lr),
                                  float(b1), float(b2), float(eps), int(step), L.stream_ptr()), "hjb_adam")

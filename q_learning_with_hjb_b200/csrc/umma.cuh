@@ -89,6 +89,22 @@ __device__ __forceinline__ void mma_ss(uint32_t d_tmem, uint64_t adesc, uint64_t
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(0u)
       : "memory");
 }
+// same, descriptors given as (lo, hi) 32-bit halves: lo = (smem address >> 4) | (LBO >> 4) << 16, hi = (SBO >> 4) | 1 << 14
+// (bit 46 = descriptor version 1) — one integer add per descriptor on the issuing thread
+__device__ __forceinline__ void mma_ss2(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi, uint32_t idesc,
+                                        uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      ".reg .b64 da, db;\n\t"
+      "mov.b64 da, {%1, %2};\n\t"
+      "mov.b64 db, {%3, %4};\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, {%7, %7, %7, %7}, p;\n\t"
+      "}\n" ::"r"(d_tmem),
+      "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate), "r"(0u)
+      : "memory");
+}
 __device__ __forceinline__ void mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
       "{\n\t"

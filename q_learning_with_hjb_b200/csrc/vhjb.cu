@@ -3,6 +3,7 @@
 #include <cmath>
 #include <cstring>
 
+#include <cstdio>
 #include <cstdlib>
 
 #include "vhjb_simt.cuh"
@@ -121,6 +122,14 @@ static int run_vhjb(const hjb_system* sys, const hjb_vnet* net, const hjb_task* 
   const int tile = tensor ? tc::TS : VBM;
   a.n_tiles = (B + tile - 1) / tile;
 
+  static long long* dbg_buf = nullptr;
+  const bool dbg = tensor && std::getenv("HJB_TC_DEBUG_TIMING") != nullptr;
+  if (dbg) {
+    if (!dbg_buf) cudaMalloc(&dbg_buf, 64 * sizeof(long long));
+    cudaMemsetAsync(dbg_buf, 0, 64 * sizeof(long long), st);
+    a.dbg = dbg_buf;
+  }
+
   VhjbLaunch l;
   l.grad = want_grad;
   int64_t grid = a.n_tiles < sm_count() ? a.n_tiles : sm_count();
@@ -150,6 +159,14 @@ static int run_vhjb(const hjb_system* sys, const hjb_vnet* net, const hjb_task* 
   }
   if (e == cudaErrorNotSupported) return HJB_ERR_UNSUPPORTED;
   if (e != cudaSuccess) return (int)e;
+  if (dbg) {  // developer probe: clock64 at (after wait_mma, end of pass) of every step of CTA 0's third tile
+    long long h[64];
+    cudaStreamSynchronize(st);
+    cudaMemcpy(h, dbg_buf, sizeof(h), cudaMemcpyDeviceToHost);
+    std::fprintf(stderr, "[hjb tc timing] grad=%d:", (int)want_grad);
+    for (int i = 1; i < 64 && h[i] != 0; ++i) std::fprintf(stderr, " %s%lld", (i & 1) ? "w" : "p", h[i] - h[i - 1]);
+    std::fprintf(stderr, "\n");
+  }
   const int P = vhjb_param_count(n);
   if (want_grad) {
     vhjb_reduce_kernel<<<(P + 255) / 256, 256, 0, st>>>(a.partial, a.pstride, l.grid, 0, P, grad);
@@ -158,6 +175,11 @@ static int run_vhjb(const hjb_system* sys, const hjb_vnet* net, const hjb_task* 
   }
   if (sums) {
     vhjb_reduce_kernel<<<1, 256, 0, st>>>(a.partial, a.pstride, l.grid, P, 2, sums);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return (int)e;
+  }
+  if (want_grad) {  // saturation count of the fp16 range management (vhjb_tc.cuh) -> workspace tail
+    vhjb_reduce_kernel<<<1, 256, 0, st>>>(a.partial, a.pstride, l.grid, P + 2, 1, a.partial + (int64_t)kMaxCtas * a.pstride);
     e = cudaGetLastError();
     if (e != cudaSuccess) return (int)e;
   }
@@ -174,7 +196,14 @@ int64_t hjb_vhjb_param_count(int32_t n) { return n > 0 && n <= HJB_MAX_N ? vhjb_
 
 int64_t hjb_vhjb_workspace_bytes(int32_t n) {
   if (n <= 0 || n > HJB_MAX_N) return -1;
-  return (int64_t)kMaxCtas * pstride_of(n) * (int64_t)sizeof(float);
+  return ((int64_t)kMaxCtas * pstride_of(n) + 4) * (int64_t)sizeof(float);
+}
+
+int hjb_vhjb_saturation(const void* workspace, int32_t n, float* count, void* stream) {
+  if (!workspace || !count || n <= 0 || n > HJB_MAX_N) return HJB_ERR_BAD_ARG;
+  const float* tail = static_cast<const float*>(workspace) + (int64_t)kMaxCtas * pstride_of(n);
+  cudaError_t e = cudaMemcpyAsync(count, tail, sizeof(float), cudaMemcpyDeviceToDevice, (cudaStream_t)stream);
+  return e == cudaSuccess ? HJB_OK : (int)e;
 }
 
 int hjb_vhjb_count(const float* dones, int64_t B, float eps, float* norm, void* workspace, void* stream) {

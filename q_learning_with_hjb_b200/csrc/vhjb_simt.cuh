@@ -44,6 +44,7 @@ struct VhjbArgs {
   float* partial;     // [gridDim.x][pstride]: per-CTA gradient partials followed by the two loss sums
   int64_t pstride;
   int64_t n_tiles;
+  long long* dbg;     // developer timing probe (HJB_TC_DEBUG_TIMING=1), else null
 };
 
 __host__ __device__ constexpr int vhjb_param_count(int n) { return n * VH1 + VH1 * VH2 + VH2 * VH3; }
@@ -459,6 +460,7 @@ __global__ void __launch_bounds__(VTHREADS, 1) vhjb_kernel(const __grid_constant
     if (lane == 0) {
       part[vhjb_param_count(N)] = hjb_sum;
       part[vhjb_param_count(N) + 1] = term_sum;
+      part[vhjb_param_count(N) + 2] = 0.f;   // saturation count (tensor-core kernel only)
     }
   }
 }

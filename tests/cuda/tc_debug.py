@@ -44,7 +44,7 @@ def run(name, B, reg=0.37, do_grad=True):
         sl = slice(off, off + gi.size); off += gi.size
         print(f"  {nm}: normwise err {np.abs(g[sl] - gi.reshape(-1)).max() / np.abs(gi).max():.2e} (|g|max {np.abs(gi).max():.3e}) nan {np.isnan(g[sl]).sum()}")
     norm = k.norm.cpu().numpy().astype(np.float64); s = sums.cpu().numpy().astype(np.float64)
-    print(f"  grad-pass sums: hjb relerr {abs(s[0] / norm[0] - hjb) / hjb:.2e}")
+    print(f"  grad-pass sums: hjb relerr {abs(s[0] / norm[0] - hjb) / hjb:.2e}  saturated states: {k.saturated()}")
 
 if __name__ == "__main__":
     names = sys.argv[1].split(",") if len(sys.argv) > 1 else ["quad10d"]
