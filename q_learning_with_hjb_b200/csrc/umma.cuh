@@ -105,6 +105,29 @@ __device__ __forceinline__ void mma_ss2(uint32_t d_tmem, uint32_t a_lo, uint32_t
       "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate), "r"(0u)
       : "memory");
 }
+// same with every descriptor field an immediate: lo = sbd + A_LO where sbd = (shared-memory base) >> 4 is the only
+// register input besides the TMEM base — nothing for the compiler to hoist out of the issue loop and spill
+template <uint32_t A_LO, uint32_t A_HI, uint32_t B_LO, uint32_t B_HI, uint32_t IDESC, uint32_t DCOL>
+__device__ __forceinline__ void mma_imm(uint32_t tmem_base, uint32_t sbd, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      ".reg .b32 al, ah, bl, bh, dd, id;\n\t"
+      ".reg .b64 da, db;\n\t"
+      "add.u32 al, %1, %3;\n\t"
+      "mov.u32 ah, %4;\n\t"
+      "add.u32 bl, %1, %5;\n\t"
+      "mov.u32 bh, %6;\n\t"
+      "add.u32 dd, %0, %8;\n\t"
+      "mov.u32 id, %7;\n\t"
+      "mov.b64 da, {al, ah};\n\t"
+      "mov.b64 db, {bl, bh};\n\t"
+      "setp.ne.b32 p, %2, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [dd], da, db, id, p;\n\t"
+      "}\n" ::"r"(tmem_base),
+      "r"(sbd), "r"(accumulate), "n"(A_LO), "n"(A_HI), "n"(B_LO), "n"(B_HI), "n"(IDESC), "n"(DCOL)
+      : "memory");
+}
 __device__ __forceinline__ void mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
       "{\n\t"

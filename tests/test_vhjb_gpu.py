@@ -175,7 +175,8 @@ def test_controller_params_update_matches_oracle_and_trains():
     for w, g in zip(W32, grads):   # first Adam step moves each weight by -lr * sign(g) (up to eps)
         new = params.flat[off:off + w.size].cpu().numpy().reshape(w.shape); off += w.size
         wn, _, _ = V.adam_step(w.astype(np.float64), 0, 0, g, 1)
-        big = np.abs(g) > 1e-6 * np.abs(g).max()
+        # (elements whose gradient is below the 1e-4 gradient tolerance have an undetermined sign: not compared)
+        big = np.abs(g) > TOL * np.abs(g).max()
         np.testing.assert_allclose(new[big], wn[big], rtol=0, atol=2e-6)
     # single-state interface
     x = dyn.get_initial_state()
