@@ -3,6 +3,7 @@
 # Each ncu pass runs only after the same command has exited 0 without ncu.  Outputs land in gpurun_out/;
 # profiles/summarize_ncu.py turns them into the committed summaries.
 set -u
+export HJB_BENCH_NO_CLOCK_LOOP=1   # the 1 s clock-sampling loop would put hundreds of launches under ncu
 CMD="python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-vhjb ${BENCH_ARGS:-}"
 TAG=${TAG:-rollout}
 KERNEL=${KERNEL:-rollout_kernel}
