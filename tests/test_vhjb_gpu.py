@@ -210,3 +210,91 @@ def test_full_size_batch_is_consistent_with_its_chunks():
     hjb, term, _ = orc.losses(xs[sl], dones[sl], costs[sl])
     d = dones[sl].astype(np.float64)
     assert abs(float(sums[0]) / ((1 - d).sum() + p.eps) - float(hjb)) <= TOL * float(hjb)
+
+
+# ---- the two kernels behind the same C ABI: tcgen05 (default for relu nets) and CUDA-core fp32 (HJB_VHJB_IMPL=simt) ----
+def _with_impl(impl, fn):
+    import os
+    old = os.environ.get("HJB_VHJB_IMPL")
+    try:
+        if impl is None:
+            os.environ.pop("HJB_VHJB_IMPL", None)
+        else:
+            os.environ["HJB_VHJB_IMPL"] = impl
+        return fn()
+    finally:
+        if old is None:
+            os.environ.pop("HJB_VHJB_IMPL", None)
+        else:
+            os.environ["HJB_VHJB_IMPL"] = old
+
+
+@pytest.mark.parametrize("name", ["linear", "quad10d"])
+def test_tensor_core_and_cuda_core_kernels_agree(name):
+    """Same inputs through vhjb_tc.cuh (fp16x3 on tcgen05) and vhjb_simt.cuh (fp32 FMAs): per-state outputs, loss sums
+    and gradient agree within the parity tolerance (they are two independent implementations of SURVEY.md 8a-V1..V6)."""
+    B = 12000 + 37
+    torch, k, p, orc, params, xs, dones, costs = _setup(name, B, seed=21, wseed=4)
+    xd, dd, cd = _dev(torch, xs, dones, costs)
+    k.counts(dd, p.eps)
+
+    def run():
+        out, sums = k.residual(params, xd, dd, cd)
+        res = {key: v.clone() for key, v in out.items()}
+        rs = sums.clone()
+        g = k.loss_grad(params, xd, dd, cd, 0.25)[0].clone()
+        return res, rs, g, k.sums.clone()
+
+    rt, st, gt, s2t = _with_impl(None, run)
+    rc, sc, gc, s2c = _with_impl("simt", run)
+    assert not torch.equal(gt, gc)                       # really two different kernels
+    assert (gt - gc).abs().max() <= TOL * gc.abs().max()
+    assert ((st - sc).abs() <= TOL * sc.abs() + 1e-30).all() and ((s2t - s2c).abs() <= TOL * s2c.abs() + 1e-30).all()
+    for key in ("V", "p", "u", "r"):
+        a, b = rt[key].reshape(B, -1).double(), rc[key].reshape(B, -1).double()
+        scale = torch.maximum(b.abs(), b.abs().mean(dim=0, keepdim=True) + 1e-30)
+        err = ((a - b).abs() / scale).max(dim=1).values
+        assert float((err > TOL).double().mean()) <= 2e-3 and float(err.median()) < 1e-5, key
+
+
+def test_near_goal_states_keep_their_weight():
+    """States a distance 1e-3 from the goal carry adjoint seeds thousands of times the batch-typical ones (1/(l + eps)):
+    the tensor-core kernel's per-state power-of-two scaling keeps them exact — gradient within tolerance, none counted
+    as saturated."""
+    B = 4096
+    torch, k, p, orc, params, xs, dones, costs = _setup("linear", B, seed=8, wseed=1)
+    rng = np.random.default_rng(0)
+    idx = rng.choice(B, size=9, replace=False)
+    xs[idx] = (p.xf + 1e-3 * rng.uniform(-1, 1, size=(9, p.sys.n))).astype(np.float32)
+    dones[idx] = 0
+    xd, dd, cd = _dev(torch, xs, dones, costs)
+    k.counts(dd, p.eps)
+    grad = k.loss_grad(params, xd, dd, cd, 0.37)[0]
+    assert k.saturated() == 0
+    _, _, _, grads, _ = orc.loss_and_grad(xs, dones, costs, 0.37)
+    g = grad.cpu().numpy().astype(np.float64)
+    off = 0
+    for gi in grads:
+        sl = slice(off, off + gi.size); off += gi.size
+        assert np.abs(g[sl] - gi.reshape(-1)).max() <= TOL * np.abs(gi).max()
+
+
+def test_saturation_counter_reports_out_of_range_seeds():
+    """A terminal sample whose stored cost is 0 has the weight 1/(0 + eps) = 1e10: beyond the fp16 range management of
+    the tensor-core kernel, which must COUNT it (hjb_vhjb_saturation) instead of overflowing; the CUDA-core kernel
+    (HJB_VHJB_IMPL=simt) handles the same batch exactly."""
+    B = 2048
+    torch, k, p, orc, params, xs, dones, costs = _setup("quad10d", B, seed=13, wseed=3)
+    dones[:] = 0
+    dones[5] = 1
+    costs[5] = 0.0
+    xd, dd, cd = _dev(torch, xs, dones, costs)
+    k.counts(dd, p.eps)
+    g_tc = _with_impl(None, lambda: k.loss_grad(params, xd, dd, cd, 0.5)[0].clone())
+    assert torch.isfinite(g_tc).all()
+    assert _with_impl(None, k.saturated) >= 1
+    g_cc = _with_impl("simt", lambda: k.loss_grad(params, xd, dd, cd, 0.5)[0].clone())
+    assert _with_impl("simt", k.saturated) == 0
+    _, _, _, grads, _ = orc.loss_and_grad(xs, dones, costs, 0.5)
+    go = np.concatenate([x.reshape(-1) for x in grads])
+    assert np.abs(g_cc.cpu().numpy() - go).max() <= TOL * np.abs(go).max()
