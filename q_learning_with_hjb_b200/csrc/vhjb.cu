@@ -132,7 +132,9 @@ static int run_vhjb(const hjb_system* sys, const hjb_vnet* net, const hjb_task* 
 
   VhjbLaunch l;
   l.grad = want_grad;
-  int64_t grid = a.n_tiles < sm_count() ? a.n_tiles : sm_count();
+  // the residual-only tensor kernel runs two tiles per CTA (vhjb_tc.cuh)
+  const int64_t cta_tiles = (tensor && !want_grad) ? (a.n_tiles + 1) / 2 : a.n_tiles;
+  int64_t grid = cta_tiles < sm_count() ? cta_tiles : sm_count();
   if (grid < 1) grid = 1;
   l.grid = (int)grid;
 
@@ -164,7 +166,10 @@ static int run_vhjb(const hjb_system* sys, const hjb_vnet* net, const hjb_task* 
     cudaStreamSynchronize(st);
     cudaMemcpy(h, dbg_buf, sizeof(h), cudaMemcpyDeviceToHost);
     std::fprintf(stderr, "[hjb tc timing] grad=%d:", (int)want_grad);
-    for (int i = 1; i < 64 && h[i] != 0; ++i) std::fprintf(stderr, " %s%lld", (i & 1) ? "w" : "p", h[i] - h[i - 1]);
+    if (h[63] > h[61])
+      std::fprintf(stderr, " [CTA 0: %lld cycles in %lld ns = %.0f MHz]", h[62] - h[60], h[63] - h[61],
+                   1e3 * (double)(h[62] - h[60]) / (double)(h[63] - h[61]));
+    for (int i = 1; i < 58 && h[i] != 0; ++i) std::fprintf(stderr, " %s%lld", (i & 1) ? "w" : "p", h[i] - h[i - 1]);
     std::fprintf(stderr, "\n");
   }
   const int P = vhjb_param_count(n);

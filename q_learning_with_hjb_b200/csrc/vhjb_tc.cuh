@@ -32,6 +32,7 @@
 #include <utility>
 
 #include "umma.cuh"
+#include "vhjb_epilogue.cuh"
 #include "vhjb_simt.cuh"
 
 namespace hjb {
@@ -74,6 +75,11 @@ struct KMaj { static constexpr uint32_t addr = ADDR, piece = PIECE, lbo = 128u, 
 template <uint32_t ADDR, uint32_t PIECE, uint32_t RB>
 struct MnMaj { static constexpr uint32_t addr = ADDR, piece = PIECE, lbo = RB, sbo = 128u, kadv = 2u * RB; };
 
+__device__ __forceinline__ long long global_ns() {
+  long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred;
   asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
@@ -197,6 +203,7 @@ __global__ void __launch_bounds__(kThreads, 1) vhjb_tc_kernel(const __grid_const
   __syncthreads();
   tc_fence_after();
   const uint32_t tm = *tptr;
+  if (a.dbg != nullptr && blockIdx.x == 0 && tid == 0) { a.dbg[60] = clock64(); a.dbg[61] = global_ns(); }
   const uint32_t sb = smem_u32(smem) >> 4;
   const int64_t n_iter = a.n_tiles > blockIdx.x ? (a.n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
   float* part = a.partial + (int64_t)blockIdx.x * a.pstride;
@@ -349,6 +356,8 @@ __global__ void __launch_bounds__(kThreads, 1) vhjb_tc_kernel(const __grid_const
     float xraw[N], z[N];
     float fdyn[N], Gdyn[N * M];            // f(x), g(x) of the state this thread owns (epilogue warps)
     float lz = 0.f, zz = 0.f, done = 0.f, cost = 1.f;
+    float xnext[N], dnext = 0.f, cnext = 1.f;   // epilogue warps: the next tile's inputs, loads issued one tile ahead
+    bool vnext = false;
     float Vsum = 0.f, Vbar = 0.f, gymax = 0.f, fscale = 0.f;
     float hjb_sum = 0.f, term_sum = 0.f, sat_count = 0.f;
     float inv_norm0 = 0.f, inv_norm1 = 0.f;
@@ -373,7 +382,7 @@ __global__ void __launch_bounds__(kThreads, 1) vhjb_tc_kernel(const __grid_const
     int64_t idx = 0;
     int mark = 0;
     auto tmark = [&](int64_t it) {
-      if (a.dbg != nullptr && blockIdx.x == 0 && it == 2 && tid == 0) a.dbg[mark++] = clock64();
+      if (a.dbg != nullptr && blockIdx.x == 0 && it == 2 && tid == 0 && mark < 58) a.dbg[mark++] = clock64();
     };
 
     const bool load_warp = state_warp && hh == 1;   // warps 4, 5: stage the NEXT tile's input while 0, 1 run the epilogue
@@ -382,7 +391,7 @@ __global__ void __launch_bounds__(kThreads, 1) vhjb_tc_kernel(const __grid_const
       tc_fence_after();
     };
     // states of a tile -> error coordinates z = wrap(x - xf) (vhjb.py:39); registers of the calling thread
-    auto fetch_state = [&](int64_t tile) {
+    auto fetch_raw = [&](int64_t tile) {   // global loads issued early, consumed by to_error() later
       idx = tile * TS + j;
       valid = idx < a.B;
       if (valid) load_row<N>(a.xs, idx, xraw);
@@ -390,9 +399,15 @@ __global__ void __launch_bounds__(kThreads, 1) vhjb_tc_kernel(const __grid_const
 #pragma unroll
         for (int i = 0; i < N; ++i) xraw[i] = a.xf[i];
       }
+    };
+    auto to_error = [&]() {
 #pragma unroll
       for (int i = 0; i < N; ++i) z[i] = xraw[i] - a.xf[i];
       wrap_state<S>(z);
+    };
+    auto fetch_state = [&](int64_t tile) {
+      fetch_raw(tile);
+      to_error();
     };
     // normalised input h0 = (z - mu) / sd (vhjb.py:45), optionally x 2^f_s, -> [s][16] operand buffer
     auto store_h0 = [&](uint32_t buf, float scale) {
@@ -458,10 +473,28 @@ __global__ void __launch_bounds__(kThreads, 1) vhjb_tc_kernel(const __grid_const
     for (int64_t it = 0; it < n_iter; ++it) {
       const int64_t tile = blockIdx.x + it * (int64_t)gridDim.x;
       const bool more = it + 1 < n_iter;
-      if (epi_warp) {   // everything of the epilogue that depends on x alone: issued here, in flight under steps 1..5
-        fetch_state(tile);
-        done = valid ? __ldg(a.dones + idx) : 0.f;
-        cost = valid ? __ldg(a.costs + idx) : 1.f;
+      if (load_warp && more) fetch_raw(tile + gridDim.x);       // consumed in step 6
+      tmark(it);
+      // P1: h1 = sigma(a1) -> F0
+      wait_mma();
+      tmark(it);
+      act_pass(cA1, kF0, std::false_type{});
+      tmark(it);
+      pass_done();                                              // -> G1
+      if (epi_warp) {   // under G1: everything of the epilogue that depends on x alone (loads were issued a tile ahead)
+        if (it == 0) {
+          fetch_raw(tile);
+          done = valid ? __ldg(a.dones + idx) : 0.f;
+          cost = valid ? __ldg(a.costs + idx) : 1.f;
+        } else {
+          idx = tile * TS + j;
+          valid = vnext;
+          done = dnext;
+          cost = cnext;
+#pragma unroll
+          for (int i = 0; i < N; ++i) xraw[i] = xnext[i];
+        }
+        to_error();
         float zi[N];
         to_internal<S>(a.sys, xraw, zi);
         typename S::Trig tr;
@@ -480,13 +513,6 @@ __global__ void __launch_bounds__(kThreads, 1) vhjb_tc_kernel(const __grid_const
           }
         }
       }
-      tmark(it);
-      // P1: h1 = sigma(a1) -> F0
-      wait_mma();
-      tmark(it);
-      act_pass(cA1, kF0, std::false_type{});
-      tmark(it);
-      pass_done();                                              // -> G1
       if constexpr (GRAD) {   // under G1: every earlier MMA is complete (G0 committed after them), step 6 is the next writer
         if (it > 0 && (it + blockIdx.x) % kFlushTiles == 0) {   // staggered over CTAs: L2 sees a trickle, not 15 MB bursts
           drain_accumulators(drained);
@@ -534,6 +560,17 @@ __global__ void __launch_bounds__(kThreads, 1) vhjb_tc_kernel(const __grid_const
       // P5: g1 = b1 sigma'(a1) -> F1
       wait_mma();
       tmark(it);
+      if (epi_warp && more) {   // issue the next tile's loads now; they are consumed under its G1
+        const int64_t nidx = (tile + gridDim.x) * TS + j;
+        vnext = nidx < a.B;
+        if (vnext) load_row<N>(a.xs, nidx, xnext);
+        else {
+#pragma unroll
+          for (int i = 0; i < N; ++i) xnext[i] = a.xf[i];
+        }
+        dnext = vnext ? __ldg(a.dones + nidx) : 0.f;
+        cnext = vnext ? __ldg(a.costs + nidx) : 1.f;
+      }
       feature_pass(cWk, cA1, kF1, masked);
       tmark(it);
       pass_done();                                              // -> G5
@@ -544,106 +581,11 @@ __global__ void __launch_bounds__(kThreads, 1) vhjb_tc_kernel(const __grid_const
         uint32_t gv[16];
         tmem_ld16(tl + cG0, gv);
         tc_wait_ld();
-        float p[N];
-        float V = Vsum;
+        float g0v[N], pbar[N];
 #pragma unroll
-        for (int i = 0; i < N; ++i) p[i] = fmaf(__uint_as_float(gv[i]) * iws, a.inv_std[i], 2.f * a.eps_s * z[i]);
-        V = fmaf(a.eps_s, zz, V);
-        const float* f = fdyn;
-        const float* G = Gdyn;
-        float c[M], u[M], du[M];
-        bool inside[M];
-#pragma unroll
-        for (int k = 0; k < M; ++k) {
-          float s = 0.f;
-#pragma unroll
-          for (int i = 0; i < N; ++i) s = fmaf(p[i], G[i * M + k], s);
-          c[k] = s;
-        }
-#pragma unroll
-        for (int k = 0; k < M; ++k) {
-          if constexpr (UFORM == HJB_U_CLIPPED) {
-            float ur = a.uf[k];
-#pragma unroll
-            for (int jj = 0; jj < M; ++jj) ur = fmaf(-0.5f * a.Rinv[k * M + jj], c[jj], ur);
-            inside[k] = (ur > a.sys.umin[k]) && (ur < a.sys.umax[k]);
-            u[k] = clampf(ur, a.sys.umin[k], a.sys.umax[k]);
-          } else {
-            inside[k] = false;
-            u[k] = -sign0(c[k]);
-          }
-          du[k] = u[k] - a.uf[k];
-        }
-        float xdot[N], vdot = 0.f;
-#pragma unroll
-        for (int i = 0; i < N; ++i) {
-          float s = f[i];
-#pragma unroll
-          for (int k = 0; k < M; ++k) s = fmaf(G[i * M + k], u[k], s);
-          xdot[i] = s;
-          vdot = fmaf(p[i], s, vdot);
-        }
-        float r, pbar[N];
-#pragma unroll
-        for (int i = 0; i < N; ++i) pbar[i] = 0.f;
-        Vbar = 0.f;
-        if constexpr (RFORM == HJB_RES_NORMALIZED) {
-          float l = lz;
-#pragma unroll
-          for (int k = 0; k < M; ++k) {
-            float row = 0.f;
-#pragma unroll
-            for (int jj = 0; jj < M; ++jj) row = fmaf(a.R[k * M + jj], du[jj], row);
-            l = fmaf(du[k], row, l);
-          }
-          const float den = l + a.eps;
-          const float iden = 1.0f / den;
-          r = fmaf(vdot, iden, 1.f);
-          const float tq = V / (cost + a.eps) - 1.f;
-          if (valid) {
-            hjb_sum += fabsf(r) * (1.f - done);
-            term_sum += fabsf(tq) * done;
-          }
-          if constexpr (GRAD) {
-            const float rbar = valid ? (1.f - done) * inv_norm0 * sign0(r) : 0.f;
-            const float vbar = rbar * iden;
-            const float lbar = -rbar * vdot * iden * iden;
-            float t[M];
-#pragma unroll
-            for (int k = 0; k < M; ++k) {
-              float ub = vbar * c[k];
-#pragma unroll
-              for (int jj = 0; jj < M; ++jj) ub = fmaf(lbar * a.Rsym[k * M + jj], du[jj], ub);
-              t[k] = inside[k] ? ub : 0.f;
-            }
-#pragma unroll
-            for (int i = 0; i < N; ++i) pbar[i] = vbar * xdot[i];
-#pragma unroll
-            for (int jj = 0; jj < M; ++jj) {
-              float s = 0.f;
-#pragma unroll
-              for (int k = 0; k < M; ++k) s = fmaf(t[k], a.Rinv[k * M + jj], s);
-              s *= -0.5f;
-#pragma unroll
-              for (int i = 0; i < N; ++i) pbar[i] = fmaf(G[i * M + jj], s, pbar[i]);
-            }
-            Vbar = valid ? a.reg * done * inv_norm1 * sign0(tq) / (cost + a.eps) : 0.f;
-          }
-        } else {
-          r = vdot + cost;
-          if (valid) hjb_sum += fabsf(r);
-          if constexpr (GRAD) {
-            const float rbar = valid ? inv_norm0 * sign0(r) : 0.f;
-#pragma unroll
-            for (int i = 0; i < N; ++i) pbar[i] = rbar * xdot[i];
-          }
-        }
-        if (valid) {
-          if (a.V) a.V[idx] = V;
-          if (a.r) a.r[idx] = r;
-          if (a.p) store_row<N>(a.p, idx, p);
-          if (a.u) store_row<M>(a.u, idx, u);
-        }
+        for (int i = 0; i < N; ++i) g0v[i] = __uint_as_float(gv[i]) * iws;
+        state_epilogue<S, UFORM, RFORM, GRAD>(a, g0v, Vsum, z, zz, lz, fdyn, Gdyn, done, cost, valid, idx, inv_norm0, inv_norm1,
+                                              hjb_sum, term_sum, pbar, Vbar);
         if constexpr (GRAD) {
           float gb[16];
 #pragma unroll
@@ -696,7 +638,7 @@ __global__ void __launch_bounds__(kThreads, 1) vhjb_tc_kernel(const __grid_const
       }
       // warps 4, 5 (idle during the epilogue): the next tile's input -> H0 (G0 of this tile read it long ago)
       if (load_warp && more) {
-        fetch_state(tile + gridDim.x);
+        to_error();
         store_h0(kH0, 1.f);
       }
       tmark(it);
@@ -792,7 +734,350 @@ __global__ void __launch_bounds__(kThreads, 1) vhjb_tc_kernel(const __grid_const
   }
   tc_fence_before();
   __syncthreads();
+  if (a.dbg != nullptr && blockIdx.x == 0 && tid == 0) { a.dbg[62] = clock64(); a.dbg[63] = global_ns(); }
   if (warp == kComputeWarps) tmem_dealloc(tm, 512);
+}
+
+// =====================================================================================================================
+// Residual-only kernel (rows V1-V5): no weight-gradient operands have to stay alive, so ONE activation buffer per tile
+// is enough (each pass starts after the GEMM that read the buffer has completed) and two tiles fit in shared memory.
+// Two groups of 8 warps each own a tile; after its pass a group synchronises on a named barrier and one elected lane of
+// its first warp issues the group's next GEMM, so the tensor pipe works on one group's GEMM while the other group runs
+// its element-wise pass (ping-pong).  The groups' accumulators are disjoint TMEM columns.  TMEM: 256
+// columns per group (a1 | a2 | y | work; g0 reuses the work columns).
+// =====================================================================================================================
+constexpr int kResGroups = 2;
+constexpr int kResThreads = 32 * kComputeWarps * kResGroups;   // 16 warps: 4 per scheduler, 128 registers each
+constexpr uint32_t kRG = kF0;                                            // first byte after the resident weights
+constexpr uint32_t kRG_F = 0, kRG_Y = kRG_F + 2 * kFPiece, kRG_H = kRG_Y + 2 * kYPiece, kResGroupBytes = kRG_H + 2 * kHPiece;
+constexpr uint32_t kResMisc = kRG + kResGroups * kResGroupBytes;         // per group: float sV[64]; then barriers, tmem ptr
+constexpr uint32_t kResSmemBytes = kResMisc + 1024;
+static_assert(kResSmemBytes <= 232448, "shared memory budget (227 KB)");
+constexpr uint32_t rA1 = 0, rA2 = 64, rY = 128, rWk = 192, kResTmemCols = 256;
+
+template <int G, int FMT>
+struct ResOps {
+  static constexpr uint32_t base = kRG + G * kResGroupBytes, col = G * kResTmemCols;
+  using F_mn = MnMaj<base + kRG_F, kFPiece, kRbF>;
+  using Y_k = KMaj<base + kRG_Y, kYPiece, kRbY>;
+  using H_k = KMaj<base + kRG_H, kHPiece, kRbH>;
+  using W2_mn = MnMaj<kW2, kW2Piece, kRbW2>; using W2_k = KMaj<kW2, kW2Piece, kRbW2>;
+  using W3_mn = MnMaj<kW3, kW3Piece, kRbW3>; using W3_k = KMaj<kW3, kW3Piece, kRbW3>;
+  using W1_mn = MnMaj<kW1, kW1Piece, kRbW1>; using W1_k = KMaj<kW1, kW1Piece, kRbW1>;
+  static constexpr uint32_t idN64_mn_mn = idesc_f16(128, TS, FMT, FMT, 1, 1), idN64_mn_k = idesc_f16(128, TS, FMT, FMT, 1, 0),
+                            idN64_k_k = idesc_f16(128, TS, FMT, FMT, 0, 0), idN64_k_mn = idesc_f16(128, TS, FMT, FMT, 0, 1),
+                            idY_mn_mn = idesc_f16(128, VH3, FMT, FMT, 1, 1), idN16_mn_k = idesc_f16(128, 16, FMT, FMT, 1, 0);
+  // the six GEMMs of a tile, in order
+  static __device__ __forceinline__ void issue(int step, uint32_t tm, uint32_t sb) {
+    switch (step) {
+      case 0: gemm3<1, W1_mn, H_k, idN64_mn_k, col + rA1>(tm, sb, 0u); break;    // a1^T = W1^T h0^T
+      case 1: gemm3<8, W2_mn, F_mn, idN64_mn_mn, col + rA2>(tm, sb, 0u); break;  // a2^T = W2^T h1^T
+      case 2: gemm3<8, F_mn, W3_mn, idY_mn_mn, col + rY>(tm, sb, 0u); break;     // y = h2 W3 (lanes = states)
+      case 3: gemm3<4, W3_k, Y_k, idN64_k_k, col + rWk>(tm, sb, 0u); break;      // b2^T = W3 gy^T
+      case 4: gemm3<8, W2_k, F_mn, idN64_k_mn, col + rWk>(tm, sb, 0u); break;    // b1^T = W2 g2^T
+      default: gemm3<8, F_mn, W1_k, idN16_mn_k, col + rWk>(tm, sb, 0u); break;   // g0 = g1 W1^T (lanes = states)
+    }
+  }
+};
+
+template <class S, int ACT, int UFORM, int RFORM, int FMT>
+__global__ void __launch_bounds__(kResThreads, 1) vhjb_tc_residual_kernel(const __grid_constant__ VhjbArgs a) {
+  static_assert(ACT == HJB_ACT_RELU, "tensor-core path: relu value nets");
+  constexpr int N = S::N;
+  static_assert(N <= 16, "state dimension padded to one K = 16 step");
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kResMisc + 512);   // [g]: pass, [2 + g]: mma
+  uint32_t* tptr = reinterpret_cast<uint32_t*>(smem + kResMisc + 560);
+  float* sLoss = reinterpret_cast<float*>(smem + kResMisc + 576);        // [g][warp 0/1][2]
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  {  // weights -> shared memory (split, core-matrix layout), once per CTA
+    const float* W1 = a.params;
+    const float* W2 = W1 + N * VH1;
+    const float* W3 = W2 + VH1 * VH2;
+    for (int c = tid; c < VH1 * (VH2 / 8); c += kResThreads) {
+      const int k = c / (VH2 / 8), jb = c % (VH2 / 8);
+      const float4 v0 = __ldg(reinterpret_cast<const float4*>(W2 + k * VH2 + 8 * jb));
+      const float4 v1 = __ldg(reinterpret_cast<const float4*>(W2 + k * VH2 + 8 * jb) + 1);
+      const float o[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+      store8<FMT>(smem, kW2, kW2Piece, kRbW2, k, 8 * jb, o);
+    }
+    for (int c = tid; c < VH2 * (VH3 / 8); c += kResThreads) {
+      const int k = c / (VH3 / 8), cb = c % (VH3 / 8);
+      const float4 v0 = __ldg(reinterpret_cast<const float4*>(W3 + k * VH3 + 8 * cb));
+      const float4 v1 = __ldg(reinterpret_cast<const float4*>(W3 + k * VH3 + 8 * cb) + 1);
+      const float o[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+      store8<FMT>(smem, kW3, kW3Piece, kRbW3, k, 8 * cb, o);
+    }
+    for (int c = tid; c < 16 * (VH1 / 8); c += kResThreads) {
+      const int i = c / (VH1 / 8), jb = c % (VH1 / 8);
+      float o[8];
+#pragma unroll
+      for (int t = 0; t < 8; ++t) o[t] = i < N ? __ldg(W1 + i * VH1 + 8 * jb + t) : 0.f;
+      store8<FMT>(smem, kW1, kW1Piece, kRbW1, i, 8 * jb, o);
+    }
+  }
+  if (tid == 0) {
+    for (int g = 0; g < kResGroups; ++g) {
+      mbar_init(bars + 2 + g, 1);
+    }
+    mbar_fence_init();
+  }
+  if (warp == 0) tmem_alloc(tptr, 512);
+  fence_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tm = *tptr;
+  if (a.dbg != nullptr && blockIdx.x == 0 && tid == 0) { a.dbg[60] = clock64(); a.dbg[61] = global_ns(); }
+  const uint32_t sb = smem_u32(smem) >> 4;
+  // group g of CTA b owns the tiles 2 b + g, 2 b + g + 2 gridDim.x, ...
+  auto tiles_of = [&](int g) -> int64_t {
+    const int64_t first = 2 * (int64_t)blockIdx.x + g, stride = 2 * (int64_t)gridDim.x;
+    return a.n_tiles > first ? (a.n_tiles - first + stride - 1) / stride : 0;
+  };
+
+  {
+    const int g = warp / kComputeWarps, wg = warp % kComputeWarps;
+    const int q = wg & 3, hh = wg >> 2;
+    const int j = 32 * q + lane, sc0 = 32 * hh;
+    const uint32_t tl = tm + ((uint32_t)(32 * q) << 16) + (uint32_t)g * kResTmemCols;
+    const uint32_t gb = kRG + (uint32_t)g * kResGroupBytes;
+    const uint32_t bF = gb + kRG_F, bY = gb + kRG_Y, bH = gb + kRG_H;
+    float* sV = reinterpret_cast<float*>(smem + kResMisc) + g * TS;
+    uint64_t* bar_mma = bars + 2 + g;
+    const bool state_warp = q < 2, epi_warp = state_warp && hh == 0, load_warp = state_warp && hh == 1;
+    const int64_t n_iter = tiles_of(g);
+    const int64_t first = 2 * (int64_t)blockIdx.x + g, stride = 2 * (int64_t)gridDim.x;
+    uint32_t ph = 0;
+    int step = 0;                               // next GEMM of this group: 0..5, cyclic
+    auto pass_done = [&]() {                    // group barrier, then one lane of the group's first warp issues
+      fence_async_smem();
+      tc_fence_before();
+      if (g == 0) asm volatile("bar.sync 3, 256;" ::: "memory");
+      else asm volatile("bar.sync 4, 256;" ::: "memory");
+      if (wg == 0) {
+        tc_fence_after();
+        if (elect_one()) {
+          if (g == 0) ResOps<0, FMT>::issue(step, tm, sb);
+          else ResOps<1, FMT>::issue(step, tm, sb);
+          mma_commit(bar_mma);
+        }
+        __syncwarp();
+      }
+      step = step == 5 ? 0 : step + 1;
+    };
+    auto wait_mma = [&]() {
+      mbar_wait(bar_mma, ph);
+      ph ^= 1u;
+      tc_fence_after();
+    };
+    auto act_pass = [&](uint32_t cStash) {
+      uint32_t st[32];
+      tmem_ld32(tl + cStash + sc0, st);
+      tc_wait_ld();
+#pragma unroll
+      for (int gq = 0; gq < 4; ++gq) {
+        float o[8];
+#pragma unroll
+        for (int t = 0; t < 8; ++t) o[t] = act_f<ACT>(__uint_as_float(st[8 * gq + t]));
+        store8<FMT>(smem, bF, kFPiece, kRbF, j, sc0 + 8 * gq, o);
+      }
+    };
+    auto masked_pass = [&](uint32_t cStash) {
+      uint32_t d[32], st[32];
+      tmem_ld32(tl + rWk + sc0, d);
+      tmem_ld32(tl + cStash + sc0, st);
+      tc_wait_ld();
+#pragma unroll
+      for (int gq = 0; gq < 4; ++gq) {
+        float o[8];
+#pragma unroll
+        for (int t = 0; t < 8; ++t) o[t] = __uint_as_float(st[8 * gq + t]) > 0.f ? __uint_as_float(d[8 * gq + t]) : 0.f;
+        store8<FMT>(smem, bF, kFPiece, kRbF, j, sc0 + 8 * gq, o);
+      }
+    };
+    float xraw[N], z[N], fdyn[N], Gdyn[N * S::M];
+    float xnext[N];                         // epilogue warps: next tile's raw states (issued one tile ahead)
+    bool vnext = false;
+    float dnext = 0.f, cnext = 1.f;
+    float lz = 0.f, zz = 0.f, done = 0.f, cost = 1.f, Vsum = 0.f;
+    float hjb_sum = 0.f, term_sum = 0.f;
+    bool valid = false;
+    int64_t idx = 0;
+    int mark = 0;
+    auto tmark = [&](int64_t it) {
+      if (a.dbg != nullptr && blockIdx.x == 0 && (it == 2 || it == 3) && tid == 0 && mark < 58) a.dbg[mark++] = clock64();
+    };
+    // global loads of a tile's states are ISSUED one tile ahead (fetch_raw) and consumed later (to_error)
+    auto fetch_raw = [&](int64_t tile) {
+      idx = tile * TS + j;
+      valid = idx < a.B;
+      if (valid) load_row<N>(a.xs, idx, xraw);
+      else {
+#pragma unroll
+        for (int i = 0; i < N; ++i) xraw[i] = a.xf[i];
+      }
+    };
+    auto to_error = [&]() {
+#pragma unroll
+      for (int i = 0; i < N; ++i) z[i] = xraw[i] - a.xf[i];
+      wrap_state<S>(z);
+    };
+    auto store_h0 = [&]() {
+      float h[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) h[i] = 0.f;
+#pragma unroll
+      for (int i = 0; i < N; ++i) h[i] = (z[i] - a.mean[i]) * a.inv_std[i];
+      store8<FMT>(smem, bH, kHPiece, kRbH, j, 0, h);
+      store8<FMT>(smem, bH, kHPiece, kRbH, j, 8, h + 8);
+    };
+
+    if (n_iter > 0) {
+      if (load_warp) {
+        fetch_raw(first);
+        to_error();
+        store_h0();
+      }
+      pass_done();                                              // -> G0 of the first tile
+    }
+    for (int64_t it = 0; it < n_iter; ++it) {
+      const int64_t tile = first + it * stride;
+      const bool more = it + 1 < n_iter;
+      if (load_warp && more) fetch_raw(tile + stride);          // consumed in step 6
+      wait_mma();
+      tmark(it);
+      act_pass(rA1);                                            // P1: h1 = sigma(a1)
+      tmark(it);
+      pass_done();                                              // -> G1
+      if (epi_warp) {   // what the epilogue needs from x alone (under G1; loads were issued a tile ahead)
+        if (it == 0) {
+          fetch_raw(tile);
+          done = valid ? __ldg(a.dones + idx) : 0.f;
+          cost = valid ? __ldg(a.costs + idx) : 1.f;
+        } else {
+          idx = tile * TS + j;
+          valid = vnext;
+          done = dnext;
+          cost = cnext;
+#pragma unroll
+          for (int i = 0; i < N; ++i) xraw[i] = xnext[i];
+        }
+        to_error();
+        float zi[N];
+        to_internal<S>(a.sys, xraw, zi);
+        typename S::Trig tr;
+        S::trig(a.sys, zi, tr);
+        S::fg(a.sys, zi, tr, fdyn, Gdyn);
+        zz = 0.f;
+        lz = 0.f;
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+          zz = fmaf(z[i], z[i], zz);
+          if constexpr (RFORM == HJB_RES_NORMALIZED) {
+            float row = 0.f;
+#pragma unroll
+            for (int jj = 0; jj < N; ++jj) row = fmaf(a.Q[i * N + jj], z[jj], row);
+            lz = fmaf(z[i], row, lz);
+          }
+        }
+      }
+      wait_mma();
+      tmark(it);
+      act_pass(rA2);                                            // P2: h2 = sigma(a2)  (G1 has read h1: same buffer)
+      tmark(it);
+      pass_done();                                              // -> G2
+      wait_mma();
+      tmark(it);
+      if (state_warp) {                                         // P3: V = |y|^2, gy = 2 y -> Y[s][c]
+        uint32_t yv[32];
+        tmem_ld32(tl + rY + sc0, yv);
+        tc_wait_ld();
+        float v = 0.f;
+#pragma unroll
+        for (int gq = 0; gq < 4; ++gq) {
+          float o[8];
+#pragma unroll
+          for (int t = 0; t < 8; ++t) {
+            const float y = __uint_as_float(yv[8 * gq + t]);
+            v = fmaf(y, y, v);
+            o[t] = 2.f * y;
+          }
+          store8<FMT>(smem, bY, kYPiece, kRbY, j, sc0 + 8 * gq, o);
+        }
+        if (hh == 1) sV[j] = v;
+        if (g == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
+        else asm volatile("bar.sync 2, 128;" ::: "memory");
+        if (hh == 0) Vsum = v + sV[j];
+      }
+      tmark(it);
+      pass_done();                                              // -> G3
+      wait_mma();
+      tmark(it);
+      masked_pass(rA2);                                         // P4: g2 = b2 sigma'(a2)
+      tmark(it);
+      pass_done();                                              // -> G4
+      wait_mma();
+      tmark(it);
+      if (epi_warp && more) {                                   // issue the next tile's loads: consumed at its top
+        const int64_t nidx = (tile + stride) * TS + j;
+        vnext = nidx < a.B;
+        if (vnext) load_row<N>(a.xs, nidx, xnext);
+        else {
+#pragma unroll
+          for (int i = 0; i < N; ++i) xnext[i] = a.xf[i];
+        }
+        dnext = vnext ? __ldg(a.dones + nidx) : 0.f;
+        cnext = vnext ? __ldg(a.costs + nidx) : 1.f;
+      }
+      masked_pass(rA1);                                         // P5: g1 = b1 sigma'(a1)
+      tmark(it);
+      pass_done();                                              // -> G5
+      wait_mma();
+      tmark(it);
+      if (epi_warp) {                                           // P6: control, residual, outputs
+        uint32_t gv[16];
+        tmem_ld16(tl + rWk, gv);
+        tc_wait_ld();
+        float g0v[N], pbar[N], Vbar;
+#pragma unroll
+        for (int i = 0; i < N; ++i) g0v[i] = __uint_as_float(gv[i]);
+        state_epilogue<S, UFORM, RFORM, false>(a, g0v, Vsum, z, zz, lz, fdyn, Gdyn, done, cost, valid, idx, 0.f, 0.f, hjb_sum,
+                                               term_sum, pbar, Vbar);
+      }
+      tmark(it);
+      if (more) {
+        if (load_warp) {                                        // next tile's input while warps 0, 1 run the epilogue
+          to_error();
+          store_h0();
+        }
+        pass_done();                                            // -> G0 of the next tile
+      }
+    }
+    // ---- loss sums of this CTA (both groups) ----
+    if (epi_warp) {
+#pragma unroll
+      for (int sft = 16; sft > 0; sft >>= 1) {
+        hjb_sum += __shfl_xor_sync(0xffffffffu, hjb_sum, sft);
+        term_sum += __shfl_xor_sync(0xffffffffu, term_sum, sft);
+      }
+      if (lane == 0) {
+        sLoss[(g * 2 + q) * 2] = hjb_sum;
+        sLoss[(g * 2 + q) * 2 + 1] = term_sum;
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (tid == 0) {
+    float* part = a.partial + (int64_t)blockIdx.x * a.pstride;
+    part[vhjb_param_count(N)] = (sLoss[0] + sLoss[2]) + (sLoss[4] + sLoss[6]);
+    part[vhjb_param_count(N) + 1] = (sLoss[1] + sLoss[3]) + (sLoss[5] + sLoss[7]);
+    part[vhjb_param_count(N) + 2] = 0.f;
+  }
+  if (a.dbg != nullptr && blockIdx.x == 0 && tid == 0) { a.dbg[62] = clock64(); a.dbg[63] = global_ns(); }
+  if (warp == 0) tmem_dealloc(tm, 512);
 }
 
 template <class S, int ACT, int UFORM, int RFORM>
@@ -804,10 +1089,10 @@ inline cudaError_t launch_vhjb_tc_variant(const VhjbArgs& a, const VhjbLaunch& l
     if (e != cudaSuccess) return e;
     k<<<l.grid, kThreads, kSmemBytes, st>>>(a);
   } else {
-    auto k = vhjb_tc_kernel<S, ACT, UFORM, RFORM, false, kF16>;
-    e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
+    auto k = vhjb_tc_residual_kernel<S, ACT, UFORM, RFORM, kF16>;
+    e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kResSmemBytes);
     if (e != cudaSuccess) return e;
-    k<<<l.grid, kThreads, kSmemBytes, st>>>(a);
+    k<<<l.grid, kResThreads, kResSmemBytes, st>>>(a);
   }
   return cudaGetLastError();
 }
