@@ -573,4 +573,9 @@ def main():
 
 
 if __name__ == "__main__":
+    # The contract is ONE JSON line on stdout.  Libraries write banners to file descriptor 1 (NCCL prints its version
+    # there): keep a private copy of the real stdout for Python's print and point fd 1 at stderr for everything else.
+    _real = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(_real, "w", buffering=1)
     main()
