@@ -44,8 +44,8 @@ constexpr int kComputeWarps = 8;
 constexpr int kThreads = 32 * (kComputeWarps + 1);
 // The TMEM accumulators of the weight gradients are drained into the per-CTA partial (fp32, round-to-nearest) every
 // kFlushTiles tiles: tcgen05.mma accumulates with truncation, and the bias of a longer chain was measured
-// (7.7e-5 of the gradient over 110 tiles = 3960 accumulating MMAs; 288 keep it near 5e-6).
-constexpr int kFlushTiles = 8;
+// (7.7e-5 of the gradient over 110 tiles = 3960 accumulating MMAs; 576 keep it near 1e-5).
+constexpr int kFlushTiles = 16;
 
 // ---- shared-memory map (bytes); every 16-bit matrix is stored as [hi piece | lo piece] ----
 constexpr uint32_t kW2 = 0, kW2Piece = VH1 * VH2 * 2;
@@ -212,7 +212,7 @@ __global__ void __launch_bounds__(kThreads, 1) vhjb_tc_kernel(const __grid_const
     // ================================ MMA issuer ================================
     constexpr uint32_t idN64_mn_mn = idesc_f16(128, TS, FMT, FMT, 1, 1), idN64_mn_k = idesc_f16(128, TS, FMT, FMT, 1, 0),
                        idN64_k_k = idesc_f16(128, TS, FMT, FMT, 0, 0), idN64_k_mn = idesc_f16(128, TS, FMT, FMT, 0, 1),
-                       idY_mn_mn = idesc_f16(128, VH3, FMT, FMT, 1, 1), idN16_mn_k = idesc_f16(128, 16, FMT, FMT, 1, 0),
+                       idY_mn_mn = idesc_f16(64, VH3, FMT, FMT, 1, 1), idN16_mn_k = idesc_f16(64, 16, FMT, FMT, 1, 0),   // M = 64: per-state GEMMs
                        idN16_k_mn = idesc_f16(128, 16, FMT, FMT, 0, 1), idN128_k_k = idesc_f16(128, VH2, FMT, FMT, 0, 0),
                        idW3g_k_mn = idesc_f16(128, VH3, FMT, FMT, 0, 1);
     using W2_mn = MnMaj<kW2, kW2Piece, kRbW2>; using W2_k = KMaj<kW2, kW2Piece, kRbW2>;
@@ -285,7 +285,8 @@ __global__ void __launch_bounds__(kThreads, 1) vhjb_tc_kernel(const __grid_const
         // G10b: W2bar += h1^T a2bar         (h1 recomputed under G10a)
         HJB_TC_GROUP_B(gemm3<4, F0_k, F1_k, idN128_k_k, cW2g>(tm, sb, 1u));
         // G11: W1bar^T += a1bar^T h0 ; then the next tile's first GEMM (its H0 was written during step 6)
-        HJB_TC_GROUP(gemm3<4, F2_k, G0_mn, idN16_k_mn, cW1g>(tm, sb, 1u); if (more) { HJB_G0; } else { mma_commit(bar_mma); });
+        // (the next tile's first GEMM goes ahead of the W1bar GEMM: the passes wait for it)
+        HJB_TC_GROUP(if (more) { HJB_G0; } gemm3<4, F2_k, G0_mn, idN16_k_mn, cW1g>(tm, sb, 1u); if (!more) { mma_commit(bar_mma); });
       }
     }
 #undef HJB_G0
@@ -297,8 +298,11 @@ __global__ void __launch_bounds__(kThreads, 1) vhjb_tc_kernel(const __grid_const
     const int j = 32 * q + lane;                 // feature == TMEM lane
     const int sc0 = 32 * hh;                     // first state column of this thread
     const uint32_t tl = tm + ((uint32_t)(32 * q) << 16);
-    const bool state_warp = q < 2;               // lanes 0..63 hold state rows of the per-state GEMMs
-    const bool epi_warp = state_warp && hh == 0; // owns state j for the epilogue
+    // Per-state GEMMs are M = 64 MMAs (32.6 cycles at N = 64 against 48.6 for M = 128): accumulator row s lives in TMEM
+    // lane (s % 16) + 32 (s / 16), i.e. lanes 0..15 of EVERY warp quarter hold the states 16 q .. 16 q + 15.
+    const int sj = 16 * q + (lane & 15);         // the state this thread owns in the per-state passes
+    const bool sact = lane < 16;                 // (lanes 16..31 of a quarter hold no state)
+    const bool epi_warp = hh == 0;               // warps 0..3: per-state epilogue of their 16 states
     uint32_t ph = 0;
     auto pass_done = [&]() {
       fence_async_smem();
@@ -385,15 +389,15 @@ __global__ void __launch_bounds__(kThreads, 1) vhjb_tc_kernel(const __grid_const
       if (a.dbg != nullptr && blockIdx.x == 0 && it == 2 && tid == 0 && mark < 58) a.dbg[mark++] = clock64();
     };
 
-    const bool load_warp = state_warp && hh == 1;   // warps 4, 5: stage the NEXT tile's input while 0, 1 run the epilogue
+    const bool load_warp = hh == 1;                 // warps 4..7: stage the NEXT tile's input while 0..3 run the epilogue
     auto wait_bar = [&](uint64_t* bar, uint32_t parity) {
       mbar_wait(bar, parity);
       tc_fence_after();
     };
     // states of a tile -> error coordinates z = wrap(x - xf) (vhjb.py:39); registers of the calling thread
     auto fetch_raw = [&](int64_t tile) {   // global loads issued early, consumed by to_error() later
-      idx = tile * TS + j;
-      valid = idx < a.B;
+      idx = tile * TS + sj;
+      valid = sact && idx < a.B;
       if (valid) load_row<N>(a.xs, idx, xraw);
       else {
 #pragma unroll
@@ -416,8 +420,10 @@ __global__ void __launch_bounds__(kThreads, 1) vhjb_tc_kernel(const __grid_const
       for (int i = 0; i < 16; ++i) h[i] = 0.f;
 #pragma unroll
       for (int i = 0; i < N; ++i) h[i] = (z[i] - a.mean[i]) * a.inv_std[i] * scale;
-      store8<FMT>(smem, buf, kHPiece, kRbH, j, 0, h);
-      store8<FMT>(smem, buf, kHPiece, kRbH, j, 8, h + 8);
+      if (sact) {
+        store8<FMT>(smem, buf, kHPiece, kRbH, sj, 0, h);
+        store8<FMT>(smem, buf, kHPiece, kRbH, sj, 8, h + 8);
+      }
     };
 
     // TMEM accumulators (x 2^E) -> per-CTA partial in global memory; every thread owns fixed elements
@@ -487,7 +493,7 @@ __global__ void __launch_bounds__(kThreads, 1) vhjb_tc_kernel(const __grid_const
           done = valid ? __ldg(a.dones + idx) : 0.f;
           cost = valid ? __ldg(a.costs + idx) : 1.f;
         } else {
-          idx = tile * TS + j;
+          idx = tile * TS + sj;
           valid = vnext;
           done = dnext;
           cost = cnext;
@@ -528,7 +534,7 @@ __global__ void __launch_bounds__(kThreads, 1) vhjb_tc_kernel(const __grid_const
       // P3 (state warps): V = |y|^2 (+ eps_s |z|^2 later), gy = 2 y -> Y0[s][c]
       wait_mma();
       tmark(it);
-      if (state_warp) {
+      {
         uint32_t yv[32];
         tmem_ld32(tl + cY + sc0, yv);
         tc_wait_ld();
@@ -543,11 +549,11 @@ __global__ void __launch_bounds__(kThreads, 1) vhjb_tc_kernel(const __grid_const
             o[t] = 2.f * y;
             ym = fmaxf(ym, fabsf(o[t]));
           }
-          store8<FMT>(smem, kY0, kYPiece, kRbY, j, sc0 + 8 * g, o);
+          if (sact) store8<FMT>(smem, kY0, kYPiece, kRbY, sj, sc0 + 8 * g, o);
         }
-        if (hh == 1) { sV[j] = v; sYm[j] = ym; }
-        asm volatile("bar.sync 1, 128;" ::: "memory");          // warps 0, 1, 4, 5
-        if (hh == 0) { Vsum = v + sV[j]; gymax = fmaxf(ym, sYm[j]); }
+        if (hh == 1 && sact) { sV[sj] = v; sYm[sj] = ym; }
+        asm volatile("bar.sync 1, 256;" ::: "memory");          // column halves of every quarter meet
+        if (hh == 0) { Vsum = v + sV[sj]; gymax = fmaxf(ym, sYm[sj]); }
       }
       tmark(it);
       pass_done();                                              // -> G3
@@ -561,8 +567,8 @@ __global__ void __launch_bounds__(kThreads, 1) vhjb_tc_kernel(const __grid_const
       wait_mma();
       tmark(it);
       if (epi_warp && more) {   // issue the next tile's loads now; they are consumed under its G1
-        const int64_t nidx = (tile + gridDim.x) * TS + j;
-        vnext = nidx < a.B;
+        const int64_t nidx = (tile + gridDim.x) * TS + sj;
+        vnext = sact && nidx < a.B;
         if (vnext) load_row<N>(a.xs, nidx, xnext);
         else {
 #pragma unroll
@@ -602,20 +608,22 @@ __global__ void __launch_bounds__(kThreads, 1) vhjb_tc_kernel(const __grid_const
             const int ks = eb - 126, ts = ks - expE;
             const int as = max(-24, min(8, ts));
             const int fe = min(6, ts - as);                                  // >= 0; 0 for all but near-goal states
-            if (ts - as > 6) sat_count += 1.f;                               // seed beyond 2^(14+E): under-weighted
+            if (sact && ts - as > 6) sat_count += 1.f;                               // seed beyond 2^(14+E): under-weighted
             lam = __uint_as_float((uint32_t)(as - ks + 127) << 23);          // 2^(a_s - k_s), exponent in [19, 252]
-            fs = exp2f((float)fe);
+            fs = __uint_as_float((uint32_t)(fe + 127) << 23);                // 2^fe, fe in [0, 6]
           }
 #pragma unroll
           for (int i = 0; i < N; ++i) gb[i] *= lam;
-          store8<FMT>(smem, kG0, kHPiece, kRbH, j, 0, gb);
-          store8<FMT>(smem, kG0, kHPiece, kRbH, j, 8, gb + 8);
-          sVb[j] = Vbar * lam;
-          sF[j] = fs;
-          if (fs != 1.f && fs != 0.f) {   // rare: rescale this state's column of g1 (F1), g2 (F0) and row of gy (Y0)
+          if (sact) {
+            store8<FMT>(smem, kG0, kHPiece, kRbH, sj, 0, gb);
+            store8<FMT>(smem, kG0, kHPiece, kRbH, sj, 8, gb + 8);
+            sVb[sj] = Vbar * lam;
+            sF[sj] = fs;
+          }
+          if (sact && fs != 1.f && fs != 0.f) {   // rare: rescale this state's column of g1 (F1), g2 (F0) and row of gy (Y0)
             const __half m = __float2half_rn(fs);
             for (int r = 0; r < 128; ++r) {
-              const uint32_t off = (uint32_t)(r >> 3) * kRbF + ((uint32_t)(j >> 3) << 7) + ((uint32_t)(r & 7) << 4) + ((uint32_t)(j & 7) << 1);
+              const uint32_t off = (uint32_t)(r >> 3) * kRbF + ((uint32_t)(sj >> 3) << 7) + ((uint32_t)(r & 7) << 4) + ((uint32_t)(sj & 7) << 1);
 #pragma unroll
               for (int pc = 0; pc < 2; ++pc) {
                 __half* e1 = reinterpret_cast<__half*>(smem + kF1 + off + pc * kFPiece);
@@ -625,7 +633,7 @@ __global__ void __launch_bounds__(kThreads, 1) vhjb_tc_kernel(const __grid_const
               }
             }
             for (int c = 0; c < VH3; ++c) {
-              const uint32_t off = kY0 + (uint32_t)(j >> 3) * kRbY + ((uint32_t)(c >> 3) << 7) + ((uint32_t)(j & 7) << 4) + ((uint32_t)(c & 7) << 1);
+              const uint32_t off = kY0 + (uint32_t)(sj >> 3) * kRbY + ((uint32_t)(c >> 3) << 7) + ((uint32_t)(sj & 7) << 4) + ((uint32_t)(c & 7) << 1);
 #pragma unroll
               for (int pc = 0; pc < 2; ++pc) {
                 __half* e = reinterpret_cast<__half*>(smem + off + pc * kYPiece);
@@ -664,19 +672,19 @@ __global__ void __launch_bounds__(kThreads, 1) vhjb_tc_kernel(const __grid_const
         // P9a (state warps): ybar = 2 gybar + 2 y Vbar -> Y1 (F2's space: W2bar's GEMM of step 7 precedes G8)
         wait_mma();
         tmark(it);
-        if (state_warp) {
+        {
           uint32_t gv[32], yv[32];
           tmem_ld32(tl + cWk + sc0, gv);
           tmem_ld32(tl + cY + sc0, yv);
           tc_wait_ld();
-          const float vb = sVb[j];
+          const float vb = sVb[sj];
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
             float o[8];
 #pragma unroll
             for (int t = 0; t < 8; ++t)
               o[t] = (2.f * iws) * fmaf(__uint_as_float(yv[8 * g + t]), vb, __uint_as_float(gv[8 * g + t]));
-            store8<FMT>(smem, kF2, kYPiece, kRbY, j, sc0 + 8 * g, o);
+            if (sact) store8<FMT>(smem, kF2, kYPiece, kRbY, sj, sc0 + 8 * g, o);
           }
         }
         tmark(it);
@@ -712,7 +720,8 @@ __global__ void __launch_bounds__(kThreads, 1) vhjb_tc_kernel(const __grid_const
       else
         for (int i = tid; i < vhjb_param_count(N); i += 32 * kComputeWarps) part[i] = 0.f;
     }
-    if (warp < 2) {
+    if (epi_warp) {
+      if (!sact) { hjb_sum = 0.f; term_sum = 0.f; sat_count = 0.f; }
 #pragma unroll
       for (int s = 16; s > 0; s >>= 1) {
         hjb_sum += __shfl_xor_sync(0xffffffffu, hjb_sum, s);
@@ -720,15 +729,15 @@ __global__ void __launch_bounds__(kThreads, 1) vhjb_tc_kernel(const __grid_const
         sat_count += __shfl_xor_sync(0xffffffffu, sat_count, s);
       }
       if (lane == 0) {
-        sV[4 * warp] = hjb_sum;
-        sV[4 * warp + 1] = term_sum;
-        sV[4 * warp + 2] = sat_count;
+        sV[4 * q] = hjb_sum;
+        sV[4 * q + 1] = term_sum;
+        sV[4 * q + 2] = sat_count;
       }
-      asm volatile("bar.sync 2, 64;" ::: "memory");
+      asm volatile("bar.sync 2, 128;" ::: "memory");
       if (tid == 0) {
-        part[vhjb_param_count(N)] = sV[0] + sV[4];
-        part[vhjb_param_count(N) + 1] = sV[1] + sV[5];
-        part[vhjb_param_count(N) + 2] = sV[2] + sV[6];
+        part[vhjb_param_count(N)] = (sV[0] + sV[4]) + (sV[8] + sV[12]);
+        part[vhjb_param_count(N) + 1] = (sV[1] + sV[5]) + (sV[9] + sV[13]);
+        part[vhjb_param_count(N) + 2] = (sV[2] + sV[6]) + (sV[10] + sV[14]);
       }
     }
   }
@@ -766,7 +775,7 @@ struct ResOps {
   using W1_mn = MnMaj<kW1, kW1Piece, kRbW1>; using W1_k = KMaj<kW1, kW1Piece, kRbW1>;
   static constexpr uint32_t idN64_mn_mn = idesc_f16(128, TS, FMT, FMT, 1, 1), idN64_mn_k = idesc_f16(128, TS, FMT, FMT, 1, 0),
                             idN64_k_k = idesc_f16(128, TS, FMT, FMT, 0, 0), idN64_k_mn = idesc_f16(128, TS, FMT, FMT, 0, 1),
-                            idY_mn_mn = idesc_f16(128, VH3, FMT, FMT, 1, 1), idN16_mn_k = idesc_f16(128, 16, FMT, FMT, 1, 0);
+                            idY_mn_mn = idesc_f16(64, VH3, FMT, FMT, 1, 1), idN16_mn_k = idesc_f16(64, 16, FMT, FMT, 1, 0);   // M = 64
   // the six GEMMs of a tile, in order
   static __device__ __forceinline__ void issue(int step, uint32_t tm, uint32_t sb) {
     switch (step) {
@@ -846,7 +855,9 @@ __global__ void __launch_bounds__(kResThreads, 1) vhjb_tc_residual_kernel(const 
     const uint32_t bF = gb + kRG_F, bY = gb + kRG_Y, bH = gb + kRG_H;
     float* sV = reinterpret_cast<float*>(smem + kResMisc) + g * TS;
     uint64_t* bar_mma = bars + 2 + g;
-    const bool state_warp = q < 2, epi_warp = state_warp && hh == 0, load_warp = state_warp && hh == 1;
+    // per-state GEMMs are M = 64 MMAs: state s in TMEM lane (s % 16) + 32 (s / 16) -> lanes 0..15 of every quarter
+    const int sj = 16 * q + (lane & 15);
+    const bool sact = lane < 16, epi_warp = hh == 0, load_warp = hh == 1;
     const int64_t n_iter = tiles_of(g);
     const int64_t first = 2 * (int64_t)blockIdx.x + g, stride = 2 * (int64_t)gridDim.x;
     uint32_t ph = 0;
@@ -911,8 +922,8 @@ __global__ void __launch_bounds__(kResThreads, 1) vhjb_tc_residual_kernel(const 
     };
     // global loads of a tile's states are ISSUED one tile ahead (fetch_raw) and consumed later (to_error)
     auto fetch_raw = [&](int64_t tile) {
-      idx = tile * TS + j;
-      valid = idx < a.B;
+      idx = tile * TS + sj;
+      valid = sact && idx < a.B;
       if (valid) load_row<N>(a.xs, idx, xraw);
       else {
 #pragma unroll
@@ -930,8 +941,10 @@ __global__ void __launch_bounds__(kResThreads, 1) vhjb_tc_residual_kernel(const 
       for (int i = 0; i < 16; ++i) h[i] = 0.f;
 #pragma unroll
       for (int i = 0; i < N; ++i) h[i] = (z[i] - a.mean[i]) * a.inv_std[i];
-      store8<FMT>(smem, bH, kHPiece, kRbH, j, 0, h);
-      store8<FMT>(smem, bH, kHPiece, kRbH, j, 8, h + 8);
+      if (sact) {
+        store8<FMT>(smem, bH, kHPiece, kRbH, sj, 0, h);
+        store8<FMT>(smem, bH, kHPiece, kRbH, sj, 8, h + 8);
+      }
     };
 
     if (n_iter > 0) {
@@ -957,7 +970,7 @@ __global__ void __launch_bounds__(kResThreads, 1) vhjb_tc_residual_kernel(const 
           done = valid ? __ldg(a.dones + idx) : 0.f;
           cost = valid ? __ldg(a.costs + idx) : 1.f;
         } else {
-          idx = tile * TS + j;
+          idx = tile * TS + sj;
           valid = vnext;
           done = dnext;
           cost = cnext;
@@ -990,7 +1003,7 @@ __global__ void __launch_bounds__(kResThreads, 1) vhjb_tc_residual_kernel(const 
       pass_done();                                              // -> G2
       wait_mma();
       tmark(it);
-      if (state_warp) {                                         // P3: V = |y|^2, gy = 2 y -> Y[s][c]
+      {                                                         // P3: V = |y|^2, gy = 2 y -> Y[s][c]
         uint32_t yv[32];
         tmem_ld32(tl + rY + sc0, yv);
         tc_wait_ld();
@@ -1004,12 +1017,12 @@ __global__ void __launch_bounds__(kResThreads, 1) vhjb_tc_residual_kernel(const 
             v = fmaf(y, y, v);
             o[t] = 2.f * y;
           }
-          store8<FMT>(smem, bY, kYPiece, kRbY, j, sc0 + 8 * gq, o);
+          if (sact) store8<FMT>(smem, bY, kYPiece, kRbY, sj, sc0 + 8 * gq, o);
         }
-        if (hh == 1) sV[j] = v;
-        if (g == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
-        else asm volatile("bar.sync 2, 128;" ::: "memory");
-        if (hh == 0) Vsum = v + sV[j];
+        if (hh == 1 && sact) sV[sj] = v;
+        if (g == 0) asm volatile("bar.sync 1, 256;" ::: "memory");
+        else asm volatile("bar.sync 2, 256;" ::: "memory");
+        if (hh == 0) Vsum = v + sV[sj];
       }
       tmark(it);
       pass_done();                                              // -> G3
@@ -1021,8 +1034,8 @@ __global__ void __launch_bounds__(kResThreads, 1) vhjb_tc_residual_kernel(const 
       wait_mma();
       tmark(it);
       if (epi_warp && more) {                                   // issue the next tile's loads: consumed at its top
-        const int64_t nidx = (tile + stride) * TS + j;
-        vnext = nidx < a.B;
+        const int64_t nidx = (tile + stride) * TS + sj;
+        vnext = sact && nidx < a.B;
         if (vnext) load_row<N>(a.xs, nidx, xnext);
         else {
 #pragma unroll
@@ -1057,14 +1070,15 @@ __global__ void __launch_bounds__(kResThreads, 1) vhjb_tc_residual_kernel(const 
     }
     // ---- loss sums of this CTA (both groups) ----
     if (epi_warp) {
+      if (!sact) { hjb_sum = 0.f; term_sum = 0.f; }
 #pragma unroll
       for (int sft = 16; sft > 0; sft >>= 1) {
         hjb_sum += __shfl_xor_sync(0xffffffffu, hjb_sum, sft);
         term_sum += __shfl_xor_sync(0xffffffffu, term_sum, sft);
       }
       if (lane == 0) {
-        sLoss[(g * 2 + q) * 2] = hjb_sum;
-        sLoss[(g * 2 + q) * 2 + 1] = term_sum;
+        sLoss[(g * 4 + q) * 2] = hjb_sum;
+        sLoss[(g * 4 + q) * 2 + 1] = term_sum;
       }
     }
   }
@@ -1072,8 +1086,10 @@ __global__ void __launch_bounds__(kResThreads, 1) vhjb_tc_residual_kernel(const 
   __syncthreads();
   if (tid == 0) {
     float* part = a.partial + (int64_t)blockIdx.x * a.pstride;
-    part[vhjb_param_count(N)] = (sLoss[0] + sLoss[2]) + (sLoss[4] + sLoss[6]);
-    part[vhjb_param_count(N) + 1] = (sLoss[1] + sLoss[3]) + (sLoss[5] + sLoss[7]);
+    float h = 0.f, tt = 0.f;
+    for (int i = 0; i < 8; ++i) { h += sLoss[2 * i]; tt += sLoss[2 * i + 1]; }
+    part[vhjb_param_count(N)] = h;
+    part[vhjb_param_count(N) + 1] = tt;
     part[vhjb_param_count(N) + 2] = 0.f;
   }
   if (a.dbg != nullptr && blockIdx.x == 0 && tid == 0) { a.dbg[62] = clock64(); a.dbg[63] = global_ns(); }

@@ -89,7 +89,7 @@ static std::vector<uint8_t> pack(const std::vector<float>& X, int R, int C, int 
   return img;
 }
 
-struct Case { const char* name; int Mvalid, N, K; int afmt, bfmt; int a_mn, b_mn; };
+struct Case { const char* name; int Mvalid, N, K; int afmt, bfmt; int a_mn, b_mn; int mma_m = 128; };
 
 static bool run_case(const Case& c) {
   const int M = c.Mvalid, N = c.N, K = c.K;
@@ -121,7 +121,7 @@ static bool run_case(const Case& c) {
     bi = pack(T, K, N, c.bfmt, pad);
     p.b_sbo = 128; p.b_lbo = (N / 8) * 128; p.b_kadv = 2 * p.b_lbo;
   }
-  p.idesc = idesc_f16(128, N, c.afmt, c.bfmt, c.a_mn, c.b_mn);
+  p.idesc = idesc_f16(c.mma_m, N, c.afmt, c.bfmt, c.a_mn, c.b_mn);
   p.ksteps = K / 16;
   p.ncols = N;
   p.a_bytes = (int)ai.size(); p.b_bytes = (int)bi.size();
@@ -143,7 +143,9 @@ static bool run_case(const Case& c) {
     for (int n = 0; n < N; ++n) {
       double s = 0;
       for (int k = 0; k < K; ++k) s += (double)A[(size_t)m * K + k] * (double)B[(size_t)n * K + k];
-      double d = fabs(s - (double)out[(size_t)m * N + n]);
+      // accumulator row -> TMEM lane: M = 128: lane = row; M = 64: 16 rows per 32-lane quarter (cute tmem_frg_1sm)
+      const int lane_of_m = c.mma_m == 64 ? (m % 16) + 32 * (m / 16) : m;
+      double d = fabs(s - (double)out[(size_t)lane_of_m * N + n]);
       if (!(d <= maxerr)) maxerr = d;   // NaN-propagating
       if (fabs(s) > maxref) maxref = fabs(s);
     }
@@ -155,7 +157,7 @@ static bool run_case(const Case& c) {
 
 // ---- timing probes -----------------------------------------------------------------------------------------
 // one thread issues `reps` MMAs (M=128, N, K=16) on resident operands; cycles from first issue to commit-arrival
-__global__ void __launch_bounds__(128, 1) mma_rate_probe(int N, int reps, int a_mn, int b_mn, long long* cycles) {
+__global__ void __launch_bounds__(128, 1) mma_rate_probe(int N, int reps, int a_mn, int b_mn, long long* cycles, int mma_m) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ uint64_t bar;
   __shared__ uint32_t tmem_base;
@@ -169,7 +171,7 @@ __global__ void __launch_bounds__(128, 1) mma_rate_probe(int N, int reps, int a_
   tc_fence_after();
   const uint32_t tm = tmem_base;
   if (tid == 0) {
-    const uint32_t idesc = idesc_f16(128, N, kF16, kF16, a_mn, b_mn);
+    const uint32_t idesc = idesc_f16(mma_m, N, kF16, kF16, a_mn, b_mn);
     const uint32_t a_lbo = a_mn ? 2048 : 128, a_sbo = a_mn ? 128 : 2048;
     const uint32_t b_lbo = b_mn ? (N / 8) * 128 : 128, b_sbo = b_mn ? 128 : 2048;
     const uint32_t a_kadv = a_mn ? 2 * a_lbo : 256, b_kadv = b_mn ? 2 * b_lbo : 256;
@@ -236,6 +238,9 @@ int main() {
     {"partial-M 32 valid, A:MN B:K  N=16", 32, 16, 128, kF16, kF16, 1, 0},
     {"partial-M 64 valid, A:K  B:K  N=64", 64, 64, 128, kF16, kF16, 0, 0},
     {"K=16 A:MN B:K N=32 (W1 fwd)", 128, 32, 16, kF16, kF16, 1, 0},
+    {"M=64 MMA, A:MN B:MN N=64 (y = h2 W3)", 64, 64, 128, kF16, kF16, 1, 1, 64},
+    {"M=64 MMA, A:MN B:K  N=16 (g0 = g1 W1^T)", 64, 16, 128, kF16, kF16, 1, 0, 64},
+    {"M=64 MMA, A:K  B:K  N=64", 64, 64, 64, kF16, kF16, 0, 0, 64},
     {"K=32 A:K  B:MN N=16 (W1 grad)", 128, 16, 32, kBF16, kBF16, 0, 1},
   };
   int fails = 0;
@@ -250,7 +255,7 @@ int main() {
         if (N == 256 && bmn) continue;
         long long best = 1ll << 60;
         for (int it = 0; it < 3; ++it) {
-          mma_rate_probe<<<1, 128, 132 * 1024>>>(N, 512, amn, bmn, dc);
+          mma_rate_probe<<<1, 128, 132 * 1024>>>(N, 512, amn, bmn, dc, 128);
           CK(cudaDeviceSynchronize());
           long long c; CK(cudaMemcpy(&c, dc, 8, cudaMemcpyDeviceToHost));
           if (c < best) best = c;
