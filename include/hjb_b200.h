@@ -233,6 +233,19 @@ int hjb_vhjb_loss_grad(const hjb_system* sys, const hjb_vnet* net, const hjb_tas
  */
 int hjb_vhjb_saturation(const void* workspace, int32_t n, float* count, void* stream);
 
+/*
+ * One step of the learned-policy rollout for N trajectories at once (VHJBController.rollout_trajectory,
+ * controller/vhjb.py:171-193; the first widening row of SURVEY.md 8f).  `u` [N, m] is the value-net policy's control at
+ * `x` [N, n] (hjb_vhjb_residual's u output).  For every trajectory with alive != 0: if wrap(x - xf) left the box
+ * [obs_lo, obs_hi] (:176-177) or `terminal` is set (:188-191) it ends with the sample (x, dx^T P dx, done = 1)
+ * (P row-major n x n: the Riccati terminal cost, :156-160, :167-169); otherwise the sample is (x, l(x, u) dt, 0)
+ * (:162-165, :184) and x <- Dynamics.simulate(x, u).  total_cost accumulates the sample costs; rec_* (nullable, one
+ * time slice) receive the sample, rec_done = -1 where the trajectory had already ended.  xf, obs_lo, obs_hi, P: host.
+ */
+int hjb_policy_step(const hjb_system* sys, const hjb_task* task, const float* xf, const float* obs_lo, const float* obs_hi,
+                    const float* P, int32_t terminal, float* x, const float* u, float* alive, float* total_cost, float* rec_x,
+                    float* rec_cost, float* rec_done, int64_t N, void* stream);
+
 /* optax.adam update (controller/vhjb.py:120, 286-287; defaults b1 = 0.9, b2 = 0.999, eps = 1e-8), in place on the
  * flat buffers; `step` is the 1-based index of this update. */
 int hjb_adam(float* params, float* m, float* v, const float* grad, int64_t len, float lr, float b1, float b2,

@@ -85,8 +85,20 @@ SYMBOLS = {
     "hjb_vhjb_loss_grad": (C.c_int, [C.POINTER(HjbSystem), C.POINTER(HjbVnet), C.POINTER(HjbTask), _P, _P, _P, C.c_int64,
                                      _P, C.c_float, _P, _P, _P, _P]),
     "hjb_vhjb_saturation": (C.c_int, [_P, C.c_int32, _P, _P]),
+    "hjb_policy_step": (C.c_int, [C.POINTER(HjbSystem), C.POINTER(HjbTask), C.POINTER(C.c_float), C.POINTER(C.c_float),
+                                  C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_int32, _P, _P, _P, _P, _P, _P, _P,
+                                  C.c_int64, _P]),
     "hjb_adam": (C.c_int, [_P, _P, _P, _P, C.c_int64, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int32, _P]),
 }
+
+
+def c_floats(values, count: int):
+    """A ctypes float[count] filled from ``values`` (host-side arguments of the C ABI)."""
+    import numpy as np
+    a = np.zeros(count, dtype=np.float32)
+    v = np.asarray(values, dtype=np.float32).reshape(-1)
+    a[: v.size] = v[:count]
+    return (C.c_float * count)(*a.tolist())
 
 
 def lib_path() -> str:

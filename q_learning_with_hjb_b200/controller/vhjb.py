@@ -285,6 +285,42 @@ class VHJBController(Controller):
             trajectory.append((x, self.termination_cost(x), 1.0))
         return trajectory
 
+    def rollout_trajectories(self, x0s, max_steps: Optional[int] = None):
+        """``rollout_trajectory`` for N initial states at once, every step on device: per step
+        ONE fused value-net launch for all trajectories (``hjb_vhjb_residual`` -> u) and ONE bookkeeping launch
+        (``hjb_policy_step``: out-of-box termination, sample cost, Euler step; vhjb.py:171-193).
+
+        Returns device tensors ``xs [T+1, N, n]``, ``costs [T+1, N]``, ``dones [T+1, N]`` (-1 where the trajectory had
+        already ended: no sample) and ``total_cost [N]`` (= ``get_trajectory_cost`` of each trajectory)."""
+        torch = self.torch
+        T = int(self.maximum_timestep if max_steps is None else max_steps)
+        n = self.state_dim
+        x = L.dev_f32(x0s, (-1, n)).clone()
+        N = x.shape[0]
+        alive = torch.ones(N, device="cuda", dtype=torch.float32)
+        total = torch.zeros(N, device="cuda", dtype=torch.float32)
+        rec_x = torch.empty((T + 1, N, n), device="cuda", dtype=torch.float32)
+        rec_c = torch.zeros((T + 1, N), device="cuda", dtype=torch.float32)
+        rec_d = torch.full((T + 1, N), -1.0, device="cuda", dtype=torch.float32)
+        u_dummy = torch.zeros((N, self.control_dim), device="cuda", dtype=torch.float32)
+        xf = L.c_floats(self.xf, n)
+        lo = L.c_floats(self.obs_min, n)
+        hi = L.c_floats(self.obs_max, n)
+        P = L.c_floats(np.asarray(self.P, dtype=np.float64).reshape(-1), n * n)
+        for i in range(T + 1):
+            terminal = i == T
+            if terminal:
+                u = u_dummy                                           # vhjb.py:188-191: close what is still running
+            else:
+                out, _ = self._residual(self.model_params, x, want=("u",))
+                u = out["u"]
+            L.check(L.lib().hjb_policy_step(self.kernels.sys_spec, self.kernels.task, xf, lo, hi, P, int(terminal),
+                                            L.ptr(x), L.ptr(u), L.ptr(alive), L.ptr(total), L.ptr(rec_x[i]), L.ptr(rec_c[i]),
+                                            L.ptr(rec_d[i]), N, L.stream_ptr()), "hjb_policy_step")
+            if i % 32 == 31 and not bool(alive.any()):                # every trajectory has left the box
+                break
+        return rec_x, rec_c, rec_d, total
+
     def get_trajectory_cost(self, trajectory):
         return sum(cost for _, cost, _ in trajectory)
 
@@ -345,12 +381,19 @@ class VHJBController(Controller):
         for epoch in range(self.epochs):
             costs_list, lengths = [], 0
             self.train_mode = False
-            for _ in range(self.num_of_trajectories_per_epoch):
-                traj = self.rollout_trajectory()
-                costs_list.append(self.get_trajectory_cost(traj))
-                lengths += len(traj)
-                for x, c, d in traj:
-                    self.replay_buffer.append(x, c, d)
+            if self.num_of_trajectories_per_epoch > 0:
+                # the epoch's trajectories in one batched device rollout; initial states are drawn in the reference's
+                # order (one get_initial_state() per trajectory, no other np.random draw in between: vhjb.py:173)
+                x0s = np.stack([self.dynamics.get_initial_state() for _ in range(self.num_of_trajectories_per_epoch)])
+                rx, rc, rd, total = self.rollout_trajectories(x0s)
+                rx, rc, rd = rx.cpu().numpy(), rc.cpu().numpy(), rd.cpu().numpy()
+                costs_list = [float(v) for v in total.cpu().numpy()]
+                for e in range(self.num_of_trajectories_per_epoch):   # replay buffer filled trajectory by trajectory
+                    for t in range(rd.shape[0]):
+                        if rd[t, e] < 0:
+                            break
+                        self.replay_buffer.append(rx[t, e].astype(np.float64), float(rc[t, e]), float(rd[t, e]))
+                        lengths += 1
             self.train_mode = True
             totals = hjbs = terms = 0.0
             n_batches = 0

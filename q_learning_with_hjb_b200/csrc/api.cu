@@ -282,6 +282,27 @@ int hjb_states_wrap(const hjb_system* sys, float* x, int64_t B, void* stream) {
   return to_status(step_wrap(sys->kind, sys->n, x, B, (cudaStream_t)stream));
 }
 
+int hjb_policy_step(const hjb_system* sys, const hjb_task* task, const float* xf, const float* obs_lo, const float* obs_hi,
+                    const float* P, int32_t terminal, float* x, const float* u, float* alive, float* total_cost, float* rec_x,
+                    float* rec_cost, float* rec_done, int64_t N, void* stream) {
+  if (!sys || !task || !xf || !obs_lo || !obs_hi || !P || N < 0) return HJB_ERR_BAD_ARG;
+  if (!dims_ok(sys)) return HJB_ERR_UNSUPPORTED;
+  if (N == 0) return HJB_OK;
+  if (!x || !u || !alive || !total_cost) return HJB_ERR_BAD_ARG;
+  PolicyStepArgs a;
+  std::memset(&a, 0, sizeof(a));
+  make_dev_sys(sys, a.sys);
+  const int n = sys->n, m = sys->m;
+  for (int i = 0; i < n; ++i) { a.xf[i] = xf[i]; a.lo[i] = obs_lo[i]; a.hi[i] = obs_hi[i]; }
+  for (int i = 0; i < n * n; ++i) { a.Q[i] = task->Q[i]; a.P[i] = P[i]; }
+  for (int i = 0; i < m * m; ++i) a.R[i] = task->R[i];
+  for (int i = 0; i < m; ++i) a.uf[i] = task->uf[i];
+  a.terminal = terminal;
+  a.x = x; a.u = u; a.alive = alive; a.total_cost = total_cost;
+  a.rec_x = rec_x; a.rec_cost = rec_cost; a.rec_done = rec_done; a.N = N;
+  return to_status(step_policy(sys->kind, a, (cudaStream_t)stream));
+}
+
 int hjb_fma_peak_probe(float* sink, int64_t sink_len, int32_t iters, double* flops, void* stream) {
   if (!sink || sink_len <= 0 || iters <= 0) return HJB_ERR_BAD_ARG;
   return to_status(fma_probe(sink, sink_len, iters, flops, (cudaStream_t)stream));

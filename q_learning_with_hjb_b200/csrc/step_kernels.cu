@@ -148,6 +148,93 @@ static cudaError_t step_control_fb(int sys_kind, const CtlArgs& a, bool fast, cu
 }
 
 // ---------------------------------------------------------------------------------------------
+// Learned-policy rollout, one step of every trajectory (VHJBController.rollout_trajectory, controller/vhjb.py:171-193):
+//   dx = wrap(x - xf); outside the observation box (:176-177) or `terminal` (:188-191): the trajectory ends with the
+//   sample (x, dx^T P dx, done = 1) (:167-169, :178-181); otherwise the sample is (x, l(x, u) dt, done = 0) with
+//   l = dx^T Q dx + (u - uf)^T R (u - uf) (:162-165, :184) and x <- simulate(x, u) (dynamics_basic.py:107-122).
+// u is the policy's control at x (hjb_vhjb_residual); trajectories that already ended produce no sample.
+template <class S>
+__global__ void __launch_bounds__(256) policy_step_kernel(const __grid_constant__ PolicyStepArgs a) {
+  constexpr int N = S::N, M = S::M;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= a.N) return;
+  if (a.alive[i] == 0.f) {
+    if (a.rec_done) a.rec_done[i] = -1.f;
+    return;
+  }
+  float xr[N], z[N];
+  load_row<N>(a.x, i, xr);
+#pragma unroll
+  for (int k = 0; k < N; ++k) z[k] = xr[k] - a.xf[k];
+  wrap_state<S>(z);
+  bool outside = a.terminal != 0;
+#pragma unroll
+  for (int k = 0; k < N; ++k) outside = outside || (z[k] > a.hi[k]) || (z[k] < a.lo[k]);
+  float cost = 0.f;
+  if (outside) {
+#pragma unroll
+    for (int r = 0; r < N; ++r) {
+      float row = 0.f;
+#pragma unroll
+      for (int c = 0; c < N; ++c) row = fmaf(a.P[r * N + c], z[c], row);
+      cost = fmaf(z[r], row, cost);
+    }
+    a.alive[i] = 0.f;
+  } else {
+    float u[M], du[M];
+    load_row<M>(a.u, i, u);
+#pragma unroll
+    for (int r = 0; r < N; ++r) {
+      float row = 0.f;
+#pragma unroll
+      for (int c = 0; c < N; ++c) row = fmaf(a.Q[r * N + c], z[c], row);
+      cost = fmaf(z[r], row, cost);
+    }
+#pragma unroll
+    for (int k = 0; k < M; ++k) du[k] = u[k] - a.uf[k];
+#pragma unroll
+    for (int r = 0; r < M; ++r) {
+      float row = 0.f;
+#pragma unroll
+      for (int c = 0; c < M; ++c) row = fmaf(a.R[r * M + c], du[c], row);
+      cost = fmaf(du[r], row, cost);
+    }
+    cost *= a.sys.dt;
+    float x[N];
+    to_internal<S>(a.sys, xr, x);
+    typename S::Trig tr;
+    S::trig(a.sys, x, tr);
+    clip_u<S>(a.sys, u);
+    integrate<S, HJB_INT_EULER>(a.sys, x, tr, u);
+    float xo[N];
+    to_external<S>(a.sys, x, xo);
+    store_row<N>(a.x, i, xo);
+  }
+  a.total_cost[i] += cost;
+  if (a.rec_x) store_row<N>(a.rec_x, i, xr);
+  if (a.rec_cost) a.rec_cost[i] = cost;
+  if (a.rec_done) a.rec_done[i] = outside ? 1.f : 0.f;
+}
+
+template <class S>
+static cudaError_t launch_policy(const PolicyStepArgs& a, cudaStream_t st) {
+  policy_step_kernel<S><<<(unsigned)((a.N + 255) / 256), 256, 0, st>>>(a);
+  return cudaGetLastError();
+}
+
+cudaError_t step_policy(int kind, const PolicyStepArgs& a, cudaStream_t st) {
+  switch (kind) {
+    case HJB_SYS_LINEAR:
+      if (a.sys.n == 2 && a.sys.m == 1) return launch_policy<LinearSys<2, 1, false>>(a, st);
+      return cudaErrorNotSupported;
+    case HJB_SYS_CARTPOLE: return launch_policy<CartpoleSys<false>>(a, st);
+    case HJB_SYS_QUAD2D: return launch_policy<Quad2DSys<false>>(a, st);
+    case HJB_SYS_QUAD10D: return launch_policy<Quad10DSys<false>>(a, st);
+    default: return cudaErrorNotSupported;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 struct WrapArgs {
   float* x;
   int64_t B;

@@ -298,3 +298,71 @@ def test_saturation_counter_reports_out_of_range_seeds():
     _, _, _, grads, _ = orc.loss_and_grad(xs, dones, costs, 0.5)
     go = np.concatenate([x.reshape(-1) for x in grads])
     assert np.abs(g_cc.cpu().numpy() - go).max() <= TOL * np.abs(go).max()
+
+
+# ---- learned-policy rollouts, all trajectories at once on device ----
+def _cartpole_controller(max_step):
+    import os
+    from q_learning_with_hjb_b200.configs import gin_compat as gin
+    from q_learning_with_hjb_b200.configs.controller.vhjb_controller_config import VHJBControllerConfig
+    from q_learning_with_hjb_b200.controller.vhjb import VHJBController
+    from tests.helpers import PKG, make_dynamics
+    dyn = make_dynamics("cartpole")
+    gin.parse_config_file(os.path.join(PKG, "configs", "controller", "cartpole_vhjb_controller.gin"))
+    cfg = VHJBControllerConfig()
+    cfg.epochs, cfg.num_of_trajectories_per_epoch, cfg.maximum_step = 1, 4, max_step
+    return dyn, VHJBController(dyn, cfg)
+
+
+def test_batched_policy_rollout_matches_the_per_trajectory_loop():
+    """rollout_trajectories (one residual launch + one hjb_policy_step launch per step for ALL trajectories) produces
+    the samples of rollout_trajectory (the reference's per-trajectory loop, vhjb.py:171-193) for the same initial states:
+    same lengths and done flags, states / costs within 1e-5."""
+    _cuda()
+    T = 40
+    dyn, ctl = _cartpole_controller(T)
+    N = 7
+    x0s = np.stack([dyn.get_initial_state() for _ in range(N)])
+    x0s[3, 0] = 4.75                                   # leaves the observation box (|p| <= 4.8) within a few steps
+    x0s[3, 2] = 3.0
+    x0s[5, 0] = 5.5                                    # starts outside: a single terminal sample
+    rx, rc, rd, total = ctl.rollout_trajectories(x0s)
+    rx, rc, rd, total = rx.cpu().numpy(), rc.cpu().numpy(), rd.cpu().numpy(), total.cpu().numpy()
+    it = iter(x0s)
+    dyn.get_initial_state = lambda: next(it).copy()
+    for e in range(N):
+        traj = ctl.rollout_trajectory()
+        L = len(traj)
+        assert (rd[:L, e] >= 0).all() and (rd[L:, e] < 0).all(), (e, L)
+        xs = np.stack([t[0] for t in traj]); cs = np.array([t[1] for t in traj]); ds = np.array([t[2] for t in traj])
+        np.testing.assert_array_equal(rd[:L, e], ds)
+        scale = np.abs(xs).max(axis=0) + 1e-6
+        assert (np.abs(rx[:L, e] - xs) / scale).max() < 1e-5
+        np.testing.assert_allclose(rc[:L, e], cs, rtol=2e-5, atol=1e-6)
+        assert abs(total[e] - ctl.get_trajectory_cost(traj)) <= 2e-5 * abs(ctl.get_trajectory_cost(traj)) + 1e-6
+    assert rd[0, 5] == 1 and rd[1, 5] < 0              # out of the box at the first check
+    assert 1 < int((rd[:, 3] >= 0).sum()) < T + 1      # left the box on the way
+
+
+def test_batched_policy_rollout_matches_oracle_steps():
+    """The first steps of the batched learned-policy rollout against the oracles: u from the torch-fp64 value-net oracle,
+    x' from the rollout oracle (the reference's Dynamics.simulate), sample cost l(x, u) dt."""
+    _cuda()
+    from oracle import rollout_oracle as O
+    T = 6
+    dyn, ctl = _cartpole_controller(T)
+    p = problem("cartpole")
+    W = [kk.cpu().numpy().astype(np.float64) for kk in ctl.model_params.kernels()]
+    orc = V.VhjbOracle(p, W)
+    osys = O.std_system("cartpole")
+    x0s = np.stack([dyn.get_initial_state() for _ in range(5)])
+    rx, rc, rd, _ = ctl.rollout_trajectories(x0s)
+    rx, rc = rx.cpu().numpy().astype(np.float64), rc.cpu().numpy().astype(np.float64)
+    x = x0s.astype(np.float32).astype(np.float64)
+    for t in range(T):
+        assert np.abs(rx[t] - x).max() < 2e-5 * (t + 1)
+        u = orc.pieces(rx[t])["u"].detach().numpy()              # policy at the device trajectory's own state
+        z = osys.wrap(rx[t] - p.xf)
+        l = np.einsum("bi,ij,bj->b", z, p.Q, z) + np.einsum("bi,ij,bj->b", u - p.uf, p.R, u - p.uf)
+        np.testing.assert_allclose(rc[t], l * osys.dt, rtol=1e-4, atol=1e-7)
+        x = osys.step(rx[t], u)
