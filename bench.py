@@ -90,6 +90,16 @@ def cpu_rollout_throughput(w, integ, cores, envs_per_core, T):
 # ---------------------------------------------------------------------------------------------------------------
 # clocks
 # ---------------------------------------------------------------------------------------------------------------
+def ncu_traffic(tag):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu capture (profiles/traffic.json, written by
+    profiles/summarize_ncu.py); None when that configuration has not been profiled."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(tag)
+    except (OSError, ValueError):
+        return None
+    return t["dram_bytes_per_launch"] if t else None
+
+
 class ClockSampler:
     QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
@@ -281,7 +291,11 @@ def run_rollout(args, w, integ):
             rec_bytes = (n + m) * 4.0 / args.record_stride
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
         roof = {"bound": "fp32", "achieved": achieved, "peak": fma_peak_tflops, "unit": "TFLOP/s",
-                "frac": achieved / fma_peak_tflops, "traffic": None,
+                "frac": achieved / fma_peak_tflops,
+                # dram__bytes_read + write of one launch, from the committed ncu capture of this same configuration
+                "traffic": (ncu_traffic(f"r01_rollout_quad2d_{integ}") if (args.workload == DEFAULT_WORKLOAD and args.envs == 0
+                                                                          and args.horizon == 0 and args.record_stride == 0)
+                            else None),
                 "peak_source": "measured: hjb_fma_peak_probe FFMA-only kernel in this run (FP32 CUDA-core peak is not "
                                "in MEASURED_PEAKS.json)",
                 "peak_nominal": nominal, "frac_of_nominal": achieved / nominal,
@@ -470,7 +484,7 @@ def measure_vhjb(w, steps, warmup, rank, world, local, want_cpu):
         executed_res = 3 * (B * steps / (res_ms * 1e-3)) * 98304 / 1e12
         peak = peaks.get("bf16_tflops", 1590.0)
         d["roofline"] = {"bound": "tensor", "achieved": executed, "unit": "TFLOP/s", "peak": peak, "frac": executed / peak,
-                         "traffic": None,
+                         "traffic": ncu_traffic("r01_vhjb_quad10d_tc") if (w["problem"] == "quad10d" and B == 1 << 20) else None,
                          "peak_source": ("MEASURED_PEAKS.json bf16_tflops (burst; kind::f16 fp16/bf16 share the rate)"
                                          if "bf16_tflops" in peaks else "fallback 1590 TFLOP/s (B200_PROFILING.md)"),
                          "peak_sustained": peaks.get("bf16_tflops_sustained"),

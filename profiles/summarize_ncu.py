@@ -60,7 +60,32 @@ def full(tag):
     return "\n".join(out)
 
 
+def traffic(tag):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the profiled launch, in bytes (None if absent)."""
+    rep = os.path.join(OUT, f"{tag}_full.ncu-rep")
+    txt = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(txt)))
+    hdr, units, vals = rows[0], rows[1], rows[2]
+    mult = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    tot = 0.0
+    for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+        if k not in hdr:
+            return None
+        i = hdr.index(k)
+        tot += float(vals[i].replace(",", "")) * mult.get(units[i], 1)
+    return {"dram_bytes_per_launch": tot, "kernel": vals[hdr.index("Kernel Name")][:80],
+            "source": f"profiles/{tag}.md (ncu --set full, one launch)"}
+
+
 def main():
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    table = json.load(open(tpath)) if os.path.exists(tpath) else {}
+    for tag in sys.argv[1:]:
+        t = traffic(tag)
+        if t:
+            table[tag] = t
+    with open(tpath, "w") as fh:
+        json.dump(table, fh, indent=1, sort_keys=True)
     for tag in sys.argv[1:]:
         plain = open(os.path.join(OUT, f"{tag}_plain.log")).read().strip().splitlines()[-1]
         try:
