@@ -431,7 +431,7 @@ def measure_vhjb(w, steps, warmup, rank, world, local, want_cpu):
     def grad_kernel_only():
         k.loss_grad(params, dev[0], dev[1], dev[2], 1e-5)
 
-    tensor_path = p.act == "relu" and os.environ.get("HJB_VHJB_IMPL", "") != "simt"
+    tensor_path = os.environ.get("HJB_VHJB_IMPL", "") != "simt"
     for _ in range(max(warmup, 3)):
         train(); residual_only()
     # clocks: the K timed steps last a few tens of ms, too short for nvidia-smi's sampling; the same train step is

@@ -13,10 +13,11 @@ namespace hjb {
 
 constexpr int kMaxCtas = 160;  // >= SM count (148 on B200)
 
-// Kernel selection: the tcgen05 kernel (vhjb_tc.cuh) wherever it is compiled (relu value nets), the CUDA-core
-// kernel (vhjb_simt.cuh) otherwise.  HJB_VHJB_IMPL=simt forces the CUDA-core kernel (A/B measurements, parity).
+// Kernel selection: the tcgen05 kernel (vhjb_tc.cuh) for every compiled combination (relu / tanh / sin value nets);
+// the CUDA-core kernel (vhjb_simt.cuh) is the fp32 reference implementation on the device.  HJB_VHJB_IMPL=simt forces the CUDA-core kernel (A/B measurements, parity).
 static bool use_tensor_path(const hjb_vnet* net, int64_t B) {
-  if (net->act != HJB_ACT_RELU || B <= 0) return false;
+  if (B <= 0) return false;
+  (void)net;
   const char* e = std::getenv("HJB_VHJB_IMPL");
   return !(e && std::strcmp(e, "simt") == 0);
 }

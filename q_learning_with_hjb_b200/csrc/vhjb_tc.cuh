@@ -140,10 +140,44 @@ __device__ __forceinline__ void store8(uint8_t* smem, uint32_t buf, uint32_t pie
   *reinterpret_cast<uint4*>(smem + off + piece) = lo;
 }
 
+// Activations on the tensor path.  The pre-activation columns of TMEM (a1, a2) hold a STASH from which sigma, sigma'
+// and sigma'' are re-derived by every later pass: the pre-activation itself for relu and sin (sin / cos are one MUFU
+// each: sin.approx / cos.approx, absolute error 2^-21 for |a| up to a few pi — below the 2^-22 relative split error of
+// the operands for |a| < 8), and t = tanh(a) for tanh (tanhf evaluated once per element; sigma' = 1 - t^2,
+// sigma'' = -2 t (1 - t^2) are FMAs).
+template <int ACT>
+__device__ __forceinline__ float tc_stash(float a) {
+  if constexpr (ACT == HJB_ACT_TANH) return tanhf(a);
+  else return a;
+}
+template <int ACT>
+__device__ __forceinline__ float tc_sig(float st) {
+  if constexpr (ACT == HJB_ACT_RELU) return fmaxf(st, 0.f);
+  else if constexpr (ACT == HJB_ACT_TANH) return st;
+  else return __sinf(st);
+}
+template <int ACT>
+__device__ __forceinline__ float tc_d1(float st) {
+  if constexpr (ACT == HJB_ACT_RELU) return st > 0.f ? 1.f : 0.f;
+  else if constexpr (ACT == HJB_ACT_TANH) return fmaf(-st, st, 1.f);
+  else return __cosf(st);
+}
+template <int ACT>
+__device__ __forceinline__ float tc_d2(float st) {
+  if constexpr (ACT == HJB_ACT_RELU) return 0.f;
+  else if constexpr (ACT == HJB_ACT_TANH) return -2.f * st * fmaf(-st, st, 1.f);
+  else return -__sinf(st);
+}
+
 template <class S, int ACT, int UFORM, int RFORM, bool GRAD, int FMT>
 __global__ void __launch_bounds__(kThreads, 1) vhjb_tc_kernel(const __grid_constant__ VhjbArgs a) {
-  static_assert(ACT == HJB_ACT_RELU, "tensor-core path: relu value nets (sigma'' = 0)");
   constexpr int N = S::N, M = S::M;
+  // Smooth activations (tanh, sin) carry the sigma'' terms of SURVEY.md 8a-V6: a2bar += g2bar b2 sigma''(a2) and
+  // a1bar += g1bar b1 sigma''(a1).  b2 is accumulated straight into the y columns (y is consumed by pass 3, before
+  // G3 is issued; pass 9a re-reads y from the gy operand in shared memory) and replaced there by the product
+  // g2bar b2 sigma''(a2) in pass 8; the b1 chain lives in 32 registers per thread (pass 5 -> 7 -> 11).
+  constexpr bool kSmooth = ACT != HJB_ACT_RELU;
+  constexpr uint32_t cB2 = kSmooth ? cY : cWk;
   static_assert(N <= 16, "state dimension padded to one K = 16 step");
   constexpr float iws = Fm<FMT>::iws;
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -258,7 +292,7 @@ __global__ void __launch_bounds__(kThreads, 1) vhjb_tc_kernel(const __grid_const
       // G2: y = h2 W3                      (lanes = states)
       HJB_TC_GROUP(gemm3<8, F1_mn, W3_mn, idY_mn_mn, cY>(tm, sb, 0u); mma_commit(bar_mma));
       // G3: b2^T = W3 gy^T
-      HJB_TC_GROUP(gemm3<4, W3_k, Y0_k, idN64_k_k, cWk>(tm, sb, 0u); mma_commit(bar_mma));
+      HJB_TC_GROUP(gemm3<4, W3_k, Y0_k, idN64_k_k, cB2>(tm, sb, 0u); mma_commit(bar_mma));
       // G4: b1^T = W2 g2^T
       HJB_TC_GROUP(gemm3<8, W2_k, F0_mn, idN64_k_mn, cWk>(tm, sb, 0u); mma_commit(bar_mma));
       // G5: g0 = g1 W1^T                   (lanes = states, 16 columns)
@@ -335,15 +369,21 @@ __global__ void __launch_bounds__(kThreads, 1) vhjb_tc_kernel(const __grid_const
         store8<FMT>(smem, buf, kFPiece, kRbF, j, sc0 + 8 * g, o);
       }
     };
-    auto act_pass = [&](uint32_t cStash, uint32_t buf, auto scaled) {   // h = sigma(a) [* 2^f_s]
+    // h = sigma(a) [* 2^f_s]; `first`: the columns hold the raw pre-activation (tanh: replaced by the stash here)
+    auto act_pass = [&](uint32_t cStash, uint32_t buf, auto scaled, auto first) {
       uint32_t st[32];
       tmem_ld32(tl + cStash + sc0, st);
       tc_wait_ld();
+      if constexpr (decltype(first)::value && ACT == HJB_ACT_TANH) {
+#pragma unroll
+        for (int t = 0; t < 32; ++t) st[t] = __float_as_uint(tc_stash<ACT>(__uint_as_float(st[t]) * iws));
+        tmem_st32(tl + cStash + sc0, st);
+      }
 #pragma unroll
       for (int g = 0; g < 4; ++g) {
         float o[8];
 #pragma unroll
-        for (int t = 0; t < 8; ++t) o[t] = act_f<ACT>(__uint_as_float(st[8 * g + t]) * iws);
+        for (int t = 0; t < 8; ++t) o[t] = tc_sig<ACT>(__uint_as_float(st[8 * g + t]) * iws);
         if constexpr (decltype(scaled)::value) {
           const float4 f0 = *reinterpret_cast<const float4*>(sF + sc0 + 8 * g), f1 = *reinterpret_cast<const float4*>(sF + sc0 + 8 * g + 4);
           o[0] *= f0.x; o[1] *= f0.y; o[2] *= f0.z; o[3] *= f0.w;
@@ -351,10 +391,52 @@ __global__ void __launch_bounds__(kThreads, 1) vhjb_tc_kernel(const __grid_const
         }
         store8<FMT>(smem, buf, kFPiece, kRbF, j, sc0 + 8 * g, o);
       }
+      if constexpr (decltype(first)::value && ACT == HJB_ACT_TANH) tc_wait_st();
     };
     auto masked = [](float d, float st) {
       if constexpr (ACT == HJB_ACT_RELU) return st > 0.f ? d * iws : 0.f;
-      else return d * (iws * act_d1<ACT>(st * iws));
+      else return d * (iws * tc_d1<ACT>(st));
+    };
+    // smooth activations: the b1 chain (b1 sigma''(a1), then g1bar b1 sigma''(a1)) of this thread's 32 states
+    float chain1[kSmooth ? 32 : 1];
+    // feature pass with the column index handed to fn (for chain1)
+    auto feature_pass_k = [&](uint32_t cD, uint32_t cStash, uint32_t buf, auto fn) {
+      uint32_t d[32], st[32];
+      tmem_ld32(tl + cD + sc0, d);
+      tmem_ld32(tl + cStash + sc0, st);
+      tc_wait_ld();
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        float o[8];
+#pragma unroll
+        for (int t = 0; t < 8; ++t) o[t] = fn(__uint_as_float(d[8 * g + t]), __uint_as_float(st[8 * g + t]), 8 * g + t);
+        store8<FMT>(smem, buf, kFPiece, kRbF, j, sc0 + 8 * g, o);
+      }
+    };
+    // feature pass with a third TMEM operand x (the b2 chain in the y columns), 16 columns at a time;
+    // out = fn(d, stash, x) (x is replaced by the new chain value when WB)
+    auto feature_pass_x = [&](uint32_t cD, uint32_t cStash, uint32_t cX, uint32_t buf, auto wb, auto fn) {
+#pragma unroll
+      for (int hf = 0; hf < 2; ++hf) {
+        uint32_t d[16], st[16], x[16];
+        tmem_ld16(tl + cD + sc0 + 16 * hf, d);
+        tmem_ld16(tl + cStash + sc0 + 16 * hf, st);
+        tmem_ld16(tl + cX + sc0 + 16 * hf, x);
+        tc_wait_ld();
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+          float o[8];
+#pragma unroll
+          for (int t = 0; t < 8; ++t) {
+            float xv = __uint_as_float(x[8 * g + t]);
+            o[t] = fn(__uint_as_float(d[8 * g + t]), __uint_as_float(st[8 * g + t]), xv);
+            x[8 * g + t] = __float_as_uint(xv);
+          }
+          store8<FMT>(smem, buf, kFPiece, kRbF, j, sc0 + 16 * hf + 8 * g, o);
+        }
+        if constexpr (decltype(wb)::value) tmem_st16(tl + cX + sc0 + 16 * hf, x);
+      }
+      if constexpr (decltype(wb)::value) tc_wait_st();
     };
 
     float xraw[N], z[N];
@@ -484,7 +566,7 @@ __global__ void __launch_bounds__(kThreads, 1) vhjb_tc_kernel(const __grid_const
       // P1: h1 = sigma(a1) -> F0
       wait_mma();
       tmark(it);
-      act_pass(cA1, kF0, std::false_type{});
+      act_pass(cA1, kF0, std::false_type{}, std::true_type{});
       tmark(it);
       pass_done();                                              // -> G1
       if (epi_warp) {   // under G1: everything of the epilogue that depends on x alone (loads were issued a tile ahead)
@@ -528,7 +610,7 @@ __global__ void __launch_bounds__(kThreads, 1) vhjb_tc_kernel(const __grid_const
       // P2: h2 = sigma(a2) -> F1
       wait_mma();
       tmark(it);
-      act_pass(cA2, kF1, std::false_type{});
+      act_pass(cA2, kF1, std::false_type{}, std::true_type{});
       tmark(it);
       pass_done();                                              // -> G2
       // P3 (state warps): V = |y|^2 (+ eps_s |z|^2 later), gy = 2 y -> Y0[s][c]
@@ -560,7 +642,7 @@ __global__ void __launch_bounds__(kThreads, 1) vhjb_tc_kernel(const __grid_const
       // P4: g2 = b2 sigma'(a2) -> F0
       wait_mma();
       tmark(it);
-      feature_pass(cWk, cA2, kF0, masked);
+      feature_pass(cB2, cA2, kF0, masked);
       tmark(it);
       pass_done();                                              // -> G4
       // P5: g1 = b1 sigma'(a1) -> F1
@@ -577,7 +659,12 @@ __global__ void __launch_bounds__(kThreads, 1) vhjb_tc_kernel(const __grid_const
         dnext = vnext ? __ldg(a.dones + nidx) : 0.f;
         cnext = vnext ? __ldg(a.costs + nidx) : 1.f;
       }
-      feature_pass(cWk, cA1, kF1, masked);
+      if constexpr (kSmooth)
+        feature_pass_k(cWk, cA1, kF1, [&](float d, float st, int k) {
+          chain1[k] = d * (iws * tc_d2<ACT>(st));
+          return masked(d, st);
+        });
+      else feature_pass(cWk, cA1, kF1, masked);
       tmark(it);
       pass_done();                                              // -> G5
       // P6 (epilogue warps): control, Hamiltonian residual, adjoint seeds (vhjb.py:204-253)
@@ -656,7 +743,12 @@ __global__ void __launch_bounds__(kThreads, 1) vhjb_tc_kernel(const __grid_const
         // P7: b1bar = g1bar sigma'(a1) -> F2 ; then h0 2^f_s -> G0 buffer (for step 11) once W1bar's GEMM has read g0bar
         wait_mma();
         tmark(it);
-        feature_pass(cWk, cA1, kF2, masked);
+        if constexpr (kSmooth)
+          feature_pass_k(cWk, cA1, kF2, [&](float d, float st, int k) {
+            chain1[k] *= d * iws;                               // g1bar b1 sigma''(a1)
+            return masked(d, st);
+          });
+        else feature_pass(cWk, cA1, kF2, masked);
         if (epi_warp) {
           wait_bar(bar_wg6, tpar);
           store_h0(kG0, fscale);
@@ -666,7 +758,12 @@ __global__ void __launch_bounds__(kThreads, 1) vhjb_tc_kernel(const __grid_const
         // P8: b2bar = g2bar sigma'(a2) -> F1   (W1bar's GEMM, the last reader of g1 in F1, precedes G7 in issue order)
         wait_mma();
         tmark(it);
-        feature_pass(cWk, cA2, kF1, masked);
+        if constexpr (kSmooth)
+          feature_pass_x(cWk, cA2, cB2, kF1, std::true_type{}, [&](float d, float st, float& x) {
+            x *= d * (iws * tc_d2<ACT>(st));                    // b2 -> g2bar b2 sigma''(a2)
+            return masked(d, st);
+          });
+        else feature_pass(cWk, cA2, kF1, masked);
         tmark(it);
         pass_done();                                            // -> G8
         // P9a (state warps): ybar = 2 gybar + 2 y Vbar -> Y1 (F2's space: W2bar's GEMM of step 7 precedes G8)
@@ -675,9 +772,27 @@ __global__ void __launch_bounds__(kThreads, 1) vhjb_tc_kernel(const __grid_const
         {
           uint32_t gv[32], yv[32];
           tmem_ld32(tl + cWk + sc0, gv);
-          tmem_ld32(tl + cY + sc0, yv);
+          float vb = sVb[sj];
+          if constexpr (kSmooth) {   // y = gy / 2 from the operand buffer (the y columns carry the b2 chain by now)
+            const float fs = sF[sj];
+            vb *= (fs != 0.f ? 0.5f / fs : 0.5f);               // a rescaled row (rare path of pass 6) holds 2^f_s gy
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              const uint32_t off = kY0 + (uint32_t)(sj >> 3) * kRbY + ((uint32_t)((sc0 + 8 * g) >> 3) << 7) + ((uint32_t)(sj & 7) << 4);
+              const uint4 hi = *reinterpret_cast<const uint4*>(smem + off), lo = *reinterpret_cast<const uint4*>(smem + off + kYPiece);
+              const uint32_t hw[4] = {hi.x, hi.y, hi.z, hi.w}, lw[4] = {lo.x, lo.y, lo.z, lo.w};
+#pragma unroll
+              for (int t = 0; t < 4; ++t) {
+                const float2 hf2 = __half22float2(*reinterpret_cast<const __half2*>(&hw[t]));
+                const float2 lf2 = __half22float2(*reinterpret_cast<const __half2*>(&lw[t]));
+                yv[8 * g + 2 * t] = __float_as_uint(hf2.x + lf2.x);
+                yv[8 * g + 2 * t + 1] = __float_as_uint(hf2.y + lf2.y);
+              }
+            }
+          } else {
+            tmem_ld32(tl + cY + sc0, yv);
+          }
           tc_wait_ld();
-          const float vb = sVb[sj];
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
             float o[8];
@@ -690,22 +805,26 @@ __global__ void __launch_bounds__(kThreads, 1) vhjb_tc_kernel(const __grid_const
         tmark(it);
         pass_done();                                            // -> G9a
         // P9b (under G9a): h2 2^f_s = sigma(a2) 2^f_s -> F0   (g2's last reader, step 7, is complete)
-        act_pass(cA2, kF0, std::true_type{});
+        act_pass(cA2, kF0, std::true_type{}, std::false_type{});
         pass_done_b();                                          // -> G9b
         // P10a: a2bar = a2bar_pre sigma'(a2) -> F1             (b2bar's last reader, step 8, precedes G9a)
         wait_mma();
         tmark(it);
-        feature_pass(cWk, cA2, kF1, masked);
+        if constexpr (kSmooth)
+          feature_pass_x(cWk, cA2, cB2, kF1, std::false_type{}, [&](float d, float st, float& x) { return masked(d, st) + x; });
+        else feature_pass(cWk, cA2, kF1, masked);
         tmark(it);
         pass_done();                                            // -> G10a
         // P10b (under G10a): h1 2^f_s -> F0 once W3bar's GEMM of step 9 has read h2 (and ybar in F2)
         wait_bar(bar_wg9, tpar);
-        act_pass(cA1, kF0, std::true_type{});
+        act_pass(cA1, kF0, std::true_type{}, std::false_type{});
         pass_done_b();                                          // -> G10b
         // P11: a1bar = a1bar_pre sigma'(a1) -> F2
         wait_mma();
         tmark(it);
-        feature_pass(cWk, cA1, kF2, masked);
+        if constexpr (kSmooth)
+          feature_pass_k(cWk, cA1, kF2, [&](float d, float st, int k) { return masked(d, st) + chain1[k]; });
+        else feature_pass(cWk, cA1, kF2, masked);
         tmark(it);
         pass_done();                                            // -> G11 (+ G0 of the next tile)
       }
@@ -791,7 +910,6 @@ struct ResOps {
 
 template <class S, int ACT, int UFORM, int RFORM, int FMT>
 __global__ void __launch_bounds__(kResThreads, 1) vhjb_tc_residual_kernel(const __grid_constant__ VhjbArgs a) {
-  static_assert(ACT == HJB_ACT_RELU, "tensor-core path: relu value nets");
   constexpr int N = S::N;
   static_assert(N <= 16, "state dimension padded to one K = 16 step");
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -883,17 +1001,23 @@ __global__ void __launch_bounds__(kResThreads, 1) vhjb_tc_residual_kernel(const 
       ph ^= 1u;
       tc_fence_after();
     };
-    auto act_pass = [&](uint32_t cStash) {
+    auto act_pass = [&](uint32_t cStash) {      // h = sigma(a); tanh: the columns keep t = tanh(a) for sigma'
       uint32_t st[32];
       tmem_ld32(tl + cStash + sc0, st);
       tc_wait_ld();
+      if constexpr (ACT == HJB_ACT_TANH) {
+#pragma unroll
+        for (int t = 0; t < 32; ++t) st[t] = __float_as_uint(tc_stash<ACT>(__uint_as_float(st[t])));
+        tmem_st32(tl + cStash + sc0, st);
+      }
 #pragma unroll
       for (int gq = 0; gq < 4; ++gq) {
         float o[8];
 #pragma unroll
-        for (int t = 0; t < 8; ++t) o[t] = act_f<ACT>(__uint_as_float(st[8 * gq + t]));
+        for (int t = 0; t < 8; ++t) o[t] = tc_sig<ACT>(__uint_as_float(st[8 * gq + t]));
         store8<FMT>(smem, bF, kFPiece, kRbF, j, sc0 + 8 * gq, o);
       }
+      if constexpr (ACT == HJB_ACT_TANH) tc_wait_st();
     };
     auto masked_pass = [&](uint32_t cStash) {
       uint32_t d[32], st[32];
@@ -904,7 +1028,10 @@ __global__ void __launch_bounds__(kResThreads, 1) vhjb_tc_residual_kernel(const 
       for (int gq = 0; gq < 4; ++gq) {
         float o[8];
 #pragma unroll
-        for (int t = 0; t < 8; ++t) o[t] = __uint_as_float(st[8 * gq + t]) > 0.f ? __uint_as_float(d[8 * gq + t]) : 0.f;
+        for (int t = 0; t < 8; ++t) {
+          if constexpr (ACT == HJB_ACT_RELU) o[t] = __uint_as_float(st[8 * gq + t]) > 0.f ? __uint_as_float(d[8 * gq + t]) : 0.f;
+          else o[t] = __uint_as_float(d[8 * gq + t]) * tc_d1<ACT>(__uint_as_float(st[8 * gq + t]));
+        }
         store8<FMT>(smem, bF, kFPiece, kRbF, j, sc0 + 8 * gq, o);
       }
     };
@@ -1115,7 +1242,7 @@ inline cudaError_t launch_vhjb_tc_variant(const VhjbArgs& a, const VhjbLaunch& l
 
 }  // namespace tc
 
-// tensor-core launchers (relu nets); cudaErrorNotSupported when the variant is not compiled
+// tensor-core launchers; cudaErrorNotSupported when the variant is not compiled
 cudaError_t vhjb_tc_launch_linear21(const VhjbArgs& a, const VhjbLaunch& l, int act, int uform, int rform, cudaStream_t st);
 cudaError_t vhjb_tc_launch_cartpole(const VhjbArgs& a, const VhjbLaunch& l, int act, int uform, int rform, cudaStream_t st);
 cudaError_t vhjb_tc_launch_quad2d(const VhjbArgs& a, const VhjbLaunch& l, int act, int uform, int rform, cudaStream_t st);

@@ -12,8 +12,9 @@ def problem(name: str) -> V.VhjbProblem:
     if name == "cartpole":      # cartpole.gin + cartpole_vhjb_controller.gin
         s = O.std_system("cartpole")
         return V.VhjbProblem(s, np.eye(4), np.eye(1), np.array([0, 3.1415926, 0, 0]), np.zeros(1), np.zeros(4), np.ones(4))
-    if name == "cartpole_tanh":  # cartpole_balancing.ipynb cell 6 (tanh net)
-        p = problem("cartpole"); p.act = "tanh"; return p
+    for suffix in ("_tanh", "_sin"):   # same task, smooth value net (cartpole_balancing.ipynb cell 6 uses tanh)
+        if name.endswith(suffix):
+            p = problem(name[:-len(suffix)]); p.act = suffix[1:]; return p
     if name == "quad2d":        # quadrotors2D.gin + quadrotors2DHovering_vhjb_controller.gin
         s = O.std_system("quad2d")
         return V.VhjbProblem(s, np.eye(6), np.eye(2), np.zeros(6), np.array([4.905, 4.905]), np.zeros(6), np.ones(6))
@@ -29,15 +30,22 @@ def problem(name: str) -> V.VhjbProblem:
     raise ValueError(name)
 
 
-OBS = {"linear": [2, 3], "cartpole": [4.8, 0.418, 4, 4], "cartpole_tanh": [4.8, 0.418, 4, 4],
+OBS = {"linear": [2, 3], "cartpole": [4.8, 0.418, 4, 4],
        "quad2d": [2, 2, 1.5, 5, 5, 2], "quad10d": [2, 2, 2, .5, .5, 4, 4, 4, 2, 2], "di_mintime": [1, 1]}
+
+
+def base_name(name: str) -> str:
+    for suffix in ("_tanh", "_sin"):
+        if name.endswith(suffix):
+            return name[:-len(suffix)]
+    return name
 
 
 def sample_batch(name: str, B: int, seed: int = 0):
     """States U(obs_min, obs_max) about xf, dones ~ Bernoulli(0.1), costs ~ U(0.1, 10)."""
     p = problem(name)
     rng = np.random.default_rng(seed)
-    xs = rng.uniform(-1, 1, size=(B, p.sys.n)) * np.asarray(OBS[name]) + p.xf
+    xs = rng.uniform(-1, 1, size=(B, p.sys.n)) * np.asarray(OBS[base_name(name)]) + p.xf
     if p.residual_form == "min_time":
         dones = np.zeros(B)
         costs = ((xs ** 2).sum(1) > 1e-4).astype(np.float64)     # running cost l_i (nb cell 7:4)
@@ -66,8 +74,8 @@ def make_kernels(name: str):
     from q_learning_with_hjb_b200.controller.vhjb import VhjbKernels
     from tests.helpers import make_dynamics
     p = problem(name)
-    kind = {"linear": "linear", "cartpole": "cartpole", "cartpole_tanh": "cartpole", "quad2d": "quad2d",
-            "quad10d": "quad10d", "di_mintime": "linear"}[name]
+    kind = {"linear": "linear", "cartpole": "cartpole", "quad2d": "quad2d", "quad10d": "quad10d",
+            "di_mintime": "linear"}[base_name(name)]
     dyn = make_dynamics(kind)
     if name == "di_mintime":
         dyn.dt = 0.01

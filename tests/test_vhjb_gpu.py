@@ -36,7 +36,7 @@ def _setup(name, B, seed=0, wseed=0):
     return torch, k, p, orc, params, xs, dones, costs
 
 
-NAMES = ["linear", "cartpole", "cartpole_tanh", "quad2d", "quad10d", "di_mintime"]
+NAMES = ["linear", "cartpole", "cartpole_tanh", "quad2d", "quad10d", "di_mintime", "linear_sin", "quad2d_tanh", "quad10d_sin"]
 
 
 @pytest.mark.parametrize("name", NAMES)
@@ -212,7 +212,7 @@ def test_full_size_batch_is_consistent_with_its_chunks():
     assert abs(float(sums[0]) / ((1 - d).sum() + p.eps) - float(hjb)) <= TOL * float(hjb)
 
 
-# ---- the two kernels behind the same C ABI: tcgen05 (default for relu nets) and CUDA-core fp32 (HJB_VHJB_IMPL=simt) ----
+# ---- the two kernels behind the same C ABI: tcgen05 (default) and CUDA-core fp32 (HJB_VHJB_IMPL=simt) ----
 def _with_impl(impl, fn):
     import os
     old = os.environ.get("HJB_VHJB_IMPL")
@@ -229,7 +229,7 @@ def _with_impl(impl, fn):
             os.environ["HJB_VHJB_IMPL"] = old
 
 
-@pytest.mark.parametrize("name", ["linear", "quad10d"])
+@pytest.mark.parametrize("name", ["linear", "quad10d", "cartpole_tanh", "di_mintime", "quad2d_sin"])
 def test_tensor_core_and_cuda_core_kernels_agree(name):
     """Same inputs through vhjb_tc.cuh (fp16x3 on tcgen05) and vhjb_simt.cuh (fp32 FMAs): per-state outputs, loss sums
     and gradient agree within the parity tolerance (they are two independent implementations of SURVEY.md 8a-V1..V6)."""
