@@ -393,7 +393,6 @@ def measure_vhjb(w, steps, warmup, rank, world, local, want_cpu):
     xs, dones, costs = sample_batch(w["problem"], B, seed=1234 + rank)
     host = [torch.as_tensor(a).pin_memory() for a in (xs, dones, costs)]
     dev = [h.cuda() for h in host]
-    stage = [torch.empty_like(d) for d in dev]
     out_host = torch.empty(4, dtype=torch.float32).pin_memory()
 
     def barrier():
@@ -421,9 +420,8 @@ def measure_vhjb(w, steps, warmup, rank, world, local, want_cpu):
         k.residual(params, dev[0], dev[1], dev[2], want=())
 
     def e2e():
-        for s, h in zip(stage, host):
-            s.copy_(h, non_blocking=True)
-        sums, norm = k.train_step(params, opt, stage[0], stage[1], stage[2], 1e-5, 1e-3)
+        # public host-batch call: H2D of the pinned batch pipelined under the kernel (VhjbKernels.train_step_host)
+        sums, norm = k.train_step_host(params, opt, host[0], host[1], host[2], 1e-5, 1e-3)
         out_host[:2].copy_(sums, non_blocking=True)
         out_host[2:].copy_(norm, non_blocking=True)
         torch.cuda.current_stream().synchronize()

@@ -225,6 +225,16 @@ int hjb_vhjb_loss_grad(const hjb_system* sys, const hjb_vnet* net, const hjb_tas
                        float* sums, void* workspace, void* stream);
 
 /*
+ * Same, for a batch that arrives in pieces (host batches streamed over PCIe chunk by chunk, VhjbKernels.train_step_host):
+ * grad, sums and the saturation count are ADDED to what the buffers hold.  The first piece goes through
+ * hjb_vhjb_loss_grad, the following ones through this entry point, all with the norm of the WHOLE batch; the result is
+ * the full-batch gradient of controller/vhjb.py:282-285, summed piece by piece in launch order (deterministic).
+ */
+int hjb_vhjb_loss_grad_accumulate(const hjb_system* sys, const hjb_vnet* net, const hjb_task* task, const float* xs,
+                                  const float* dones, const float* costs, int64_t B, const float* norm, float reg,
+                                  float* grad, float* sums, void* workspace, void* stream);
+
+/*
  * Range check of the last hjb_vhjb_loss_grad on this workspace (device float `count`, stream-ordered).  The
  * tensor-core gradient pass carries per-state adjoints in fp16 with per-state power-of-two scaling (vhjb_tc.cuh);
  * a state whose adjoint seed exceeds 2^26 times the batch-typical weight (only |x - xf| and |u - uf| ~ 1e-4 and

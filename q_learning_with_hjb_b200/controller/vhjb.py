@@ -150,12 +150,14 @@ class VhjbKernels:
                                           L.ptr(self.sums), L.ptr(self.workspace), L.stream_ptr()), "hjb_vhjb_residual")
         return out, self.sums
 
-    def loss_grad(self, params_flat, xs, dones, costs, reg: float):
-        """grad (normalised by self.norm) and the un-normalised loss sums of this shard."""
+    def loss_grad(self, params_flat, xs, dones, costs, reg: float, accumulate: bool = False):
+        """grad (normalised by self.norm) and the un-normalised loss sums of this shard; ``accumulate`` adds this
+        piece of a batch to what grad / sums already hold (hjb_vhjb_loss_grad_accumulate)."""
         self._bind(params_flat)
-        L.check(L.lib().hjb_vhjb_loss_grad(self.sys_spec, self.net, self.task, L.ptr(xs), L.ptr(dones), L.ptr(costs),
-                                           xs.shape[0], L.ptr(self.norm), float(reg), L.ptr(self.grad), L.ptr(self.sums),
-                                           L.ptr(self.workspace), L.stream_ptr()), "hjb_vhjb_loss_grad")
+        fn = L.lib().hjb_vhjb_loss_grad_accumulate if accumulate else L.lib().hjb_vhjb_loss_grad
+        L.check(fn(self.sys_spec, self.net, self.task, L.ptr(xs), L.ptr(dones), L.ptr(costs), xs.shape[0],
+                   L.ptr(self.norm), float(reg), L.ptr(self.grad), L.ptr(self.sums), L.ptr(self.workspace),
+                   L.stream_ptr()), "hjb_vhjb_loss_grad")
         return self.grad, self.sums
 
     def saturated(self) -> int:
@@ -182,6 +184,64 @@ class VhjbKernels:
         else:
             parallel.global_counts(self.norm, self.eps, group)
         self.loss_grad(params_flat, xs, dones, costs, reg)
+        parallel.sum_across_ranks(self.grad_and_sums, group)
+        opt.count += 1
+        self.adam(params_flat, opt.mu, opt.nu, self.grad, opt.count, lr)
+        return self.sums, self.norm
+
+
+    # ---- the same step for a batch that lives in HOST memory (what params_update receives from the replay buffer) ----
+    def _host_staging(self, B: int):
+        st = getattr(self, "_stage", None)
+        if st is None or st["B"] < B:
+            t = self.torch
+            f32 = dict(device="cuda", dtype=t.float32)
+            st = {"B": B, "xs": t.empty((B, self.n), **f32), "dones": t.empty(B, **f32), "costs": t.empty(B, **f32),
+                  "copy": getattr(self, "_stage", {}).get("copy") or t.cuda.Stream()}
+            self._stage = st
+        return st
+
+    def train_step_host(self, params_flat, opt: AdamState, xs_h, dones_h, costs_h, reg: float, lr: float, group=None,
+                        chunks: int = 8):
+        """``train_step`` on host tensors ([B, n], [B], [B] float32 CPU, ideally pinned).  The done flags go up first
+        (the normalisers of vhjb.py:241, 253 are sums over the WHOLE batch and must be known before any gradient
+        piece); the states and costs follow in ``chunks`` pieces on a copy stream while the fused loss+gradient kernel
+        works through the pieces already on the device (the first with hjb_vhjb_loss_grad, the rest accumulating).
+        Returns the device tensors (sums, norm) like ``train_step``; stream-ordered, no host synchronisation."""
+        from q_learning_with_hjb_b200 import parallel
+        t = self.torch
+        B = int(xs_h.shape[0])
+        st = self._host_staging(B)
+        xs, dones, costs = st["xs"][:B], st["dones"][:B], st["costs"][:B]
+        cur, cp = t.cuda.current_stream(), st["copy"]
+        chunks = max(1, min(int(chunks), B // 32768))
+        step = -(-B // chunks)
+        step = -(-step // 128) * 128                        # whole tiles (and 16-byte aligned rows) per piece
+        ev0 = t.cuda.Event()
+        ev0.record(cur)
+        ups = []
+        with t.cuda.stream(cp):
+            cp.wait_event(ev0)                              # the previous step's kernels have read the staging buffers
+            dones.copy_(dones_h, non_blocking=True)
+            evd = t.cuda.Event()
+            evd.record(cp)
+            for lo in range(0, B, step):
+                sl = slice(lo, min(B, lo + step))
+                xs[sl].copy_(xs_h[sl], non_blocking=True)
+                costs[sl].copy_(costs_h[sl], non_blocking=True)
+                ev = t.cuda.Event()
+                ev.record(cp)
+                ups.append((sl, ev))
+        cur.wait_event(evd)
+        self.counts(dones, 0.0)
+        if self.residual_form == "min_time":
+            parallel.global_counts(self.norm, 0.0, group)
+            self.norm[1] = 1.0
+        else:
+            parallel.global_counts(self.norm, self.eps, group)
+        for i, (sl, ev) in enumerate(ups):
+            cur.wait_event(ev)
+            self.loss_grad(params_flat, xs[sl], dones[sl], costs[sl], reg, accumulate=i > 0)
         parallel.sum_across_ranks(self.grad_and_sums, group)
         opt.count += 1
         self.adam(params_flat, opt.mu, opt.nu, self.grad, opt.count, lr)
@@ -366,10 +426,19 @@ class VHJBController(Controller):
     def params_update(self, params, states, optimizer_state, xs, dones, costs, regularization):
         """One fused update (vhjb.py:255-288).  Returns (params, states, optimizer_state, total, hjb, term); the
         three losses are 0-d device tensors (no host synchronisation here)."""
-        xd, _ = self._batch(xs)
-        B = xd.shape[0]
-        sums, norm = self.kernels.train_step(params.flat, optimizer_state, xd, L.dev_f32(dones, (B,)),
-                                             L.dev_f32(costs, (B,)), float(regularization), self.lr)
+        torch = self.torch
+        if isinstance(xs, torch.Tensor) and xs.is_cuda:
+            xd, _ = self._batch(xs)
+            B = xd.shape[0]
+            sums, norm = self.kernels.train_step(params.flat, optimizer_state, xd, L.dev_f32(dones, (B,)),
+                                                 L.dev_f32(costs, (B,)), float(regularization), self.lr)
+        else:   # host batch (the replay buffer's): copies pipelined under the kernel
+            host = lambda a, shape: torch.as_tensor(np.ascontiguousarray(np.asarray(a, dtype=np.float32))).reshape(shape) \
+                if not isinstance(a, torch.Tensor) else a.to(torch.float32).reshape(shape).contiguous()
+            xh = host(xs, (-1, self.state_dim))
+            B = xh.shape[0]
+            sums, norm = self.kernels.train_step_host(params.flat, optimizer_state, xh, host(dones, (B,)), host(costs, (B,)),
+                                                      float(regularization), self.lr)
         hjb = sums[0] / norm[0]
         term = sums[1] / norm[1]
         return params, states, optimizer_state, hjb + float(regularization) * term, hjb, term

@@ -25,13 +25,14 @@ static bool use_tensor_path(const hjb_vnet* net, int64_t B) {
 static int64_t pstride_of(int n) { return ((int64_t)vhjb_param_count(n) + 2 + 3) / 4 * 4; }
 
 // grad[j] = sum over CTAs (fixed order) of partial[cta][j]; j in [first, first + count)
+// (accumulate: out[j] += the sum — a batch processed as several launches, in launch order)
 __global__ void __launch_bounds__(256) vhjb_reduce_kernel(const float* __restrict__ partial, int64_t pstride, int ncta,
-                                                          int first, int count, float* __restrict__ out) {
+                                                          int first, int count, float* __restrict__ out, int accumulate) {
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= count) return;
   float s = 0.f;
   for (int c = 0; c < ncta; ++c) s += partial[(int64_t)c * pstride + first + j];
-  out[j] = s;
+  out[j] = accumulate ? out[j] + s : s;
 }
 
 // ---- sum(1 - done), sum(done): two-stage, fixed order ----
@@ -86,7 +87,7 @@ static int sm_count() {
 
 static int run_vhjb(const hjb_system* sys, const hjb_vnet* net, const hjb_task* task, const float* xs, const float* dones,
                     const float* costs, int64_t B, const float* norm, float reg, float* V, float* p, float* u, float* r,
-                    float* grad, float* sums, void* workspace, bool want_grad, cudaStream_t st) {
+                    float* grad, float* sums, void* workspace, bool want_grad, bool accumulate, cudaStream_t st) {
   if (!sys || !net || !task || B < 0) return HJB_ERR_BAD_ARG;
   if (net->n != sys->n || net->features[0] != VH1 || net->features[1] != VH2 || net->features[2] != VH3)
     return HJB_ERR_UNSUPPORTED;
@@ -175,17 +176,17 @@ static int run_vhjb(const hjb_system* sys, const hjb_vnet* net, const hjb_task* 
   }
   const int P = vhjb_param_count(n);
   if (want_grad) {
-    vhjb_reduce_kernel<<<(P + 255) / 256, 256, 0, st>>>(a.partial, a.pstride, l.grid, 0, P, grad);
+    vhjb_reduce_kernel<<<(P + 255) / 256, 256, 0, st>>>(a.partial, a.pstride, l.grid, 0, P, grad, (int)accumulate);
     e = cudaGetLastError();
     if (e != cudaSuccess) return (int)e;
   }
   if (sums) {
-    vhjb_reduce_kernel<<<1, 256, 0, st>>>(a.partial, a.pstride, l.grid, P, 2, sums);
+    vhjb_reduce_kernel<<<1, 256, 0, st>>>(a.partial, a.pstride, l.grid, P, 2, sums, (int)accumulate);
     e = cudaGetLastError();
     if (e != cudaSuccess) return (int)e;
   }
   if (want_grad) {  // saturation count of the fp16 range management (vhjb_tc.cuh) -> workspace tail
-    vhjb_reduce_kernel<<<1, 256, 0, st>>>(a.partial, a.pstride, l.grid, P + 2, 1, a.partial + (int64_t)kMaxCtas * a.pstride);
+    vhjb_reduce_kernel<<<1, 256, 0, st>>>(a.partial, a.pstride, l.grid, P + 2, 1, a.partial + (int64_t)kMaxCtas * a.pstride, (int)accumulate);
     e = cudaGetLastError();
     if (e != cudaSuccess) return (int)e;
   }
@@ -226,7 +227,7 @@ int hjb_vhjb_count(const float* dones, int64_t B, float eps, float* norm, void* 
 int hjb_vhjb_residual(const hjb_system* sys, const hjb_vnet* net, const hjb_task* task, const float* xs, const float* dones,
                       const float* costs, int64_t B, float* V, float* p, float* u, float* r, float* sums, void* workspace,
                       void* stream) {
-  return run_vhjb(sys, net, task, xs, dones, costs, B, nullptr, 0.f, V, p, u, r, nullptr, sums, workspace, false,
+  return run_vhjb(sys, net, task, xs, dones, costs, B, nullptr, 0.f, V, p, u, r, nullptr, sums, workspace, false, false,
                   (cudaStream_t)stream);
 }
 
@@ -234,7 +235,14 @@ int hjb_vhjb_loss_grad(const hjb_system* sys, const hjb_vnet* net, const hjb_tas
                        const float* costs, int64_t B, const float* norm, float reg, float* grad, float* sums, void* workspace,
                        void* stream) {
   return run_vhjb(sys, net, task, xs, dones, costs, B, norm, reg, nullptr, nullptr, nullptr, nullptr, grad, sums, workspace,
-                  true, (cudaStream_t)stream);
+                  true, false, (cudaStream_t)stream);
+}
+
+int hjb_vhjb_loss_grad_accumulate(const hjb_system* sys, const hjb_vnet* net, const hjb_task* task, const float* xs,
+                                  const float* dones, const float* costs, int64_t B, const float* norm, float reg,
+                                  float* grad, float* sums, void* workspace, void* stream) {
+  return run_vhjb(sys, net, task, xs, dones, costs, B, norm, reg, nullptr, nullptr, nullptr, nullptr, grad, sums, workspace,
+                  true, true, (cudaStream_t)stream);
 }
 
 int hjb_adam(float* params, float* m, float* v, const float* grad, int64_t len, float lr, float b1, float b2, float eps,

@@ -141,21 +141,76 @@ class BatchedRollout:
     def d2h_bytes(self) -> int:
         return self.N * self.n * 4 + (self.N * 4 if self.cost is not None else 0)
 
-    def run_host(self, x0_host, copy_in: bool = True):
+    def _launch_range(self, x0_dev, lo: int, hi: int):
+        """Envs [lo, hi) of a final-state(+cost) plan on the current stream (the outputs are env-major: a range of
+        environments is a contiguous slice of every buffer)."""
+        import ctypes as C
+
+        sl = slice(lo, hi)
+        L.check(L.lib().hjb_rollout(self.sys_spec, self.ctl_spec,
+                                    self.cost_spec if self.cost_spec is not None else C.POINTER(L.HjbCost)(),
+                                    self.opts, L.ptr(x0_dev[sl]), hi - lo, self.T, None, None,
+                                    L.ptr(self.x_final[sl]), L.ptr(self.cost[sl]) if self.cost is not None else None,
+                                    L.ptr(self.steps[sl]) if self.steps is not None else None, L.stream_ptr()),
+                "hjb_rollout")
+
+    def _pipeline(self):
+        if getattr(self, "_pipe", None) is None:
+            t = self.torch
+            self._pipe = {"h2d": t.cuda.Stream(), "d2h": t.cuda.Stream(), "run": [t.cuda.Stream(), t.cuda.Stream()]}
+        return self._pipe
+
+    def run_host(self, x0_host, copy_in: bool = True, chunks: int = 8):
         """x0 on the host -> (x_final, cost) on the host.  Copies x0 into pinned staging unless it already IS
-        the staging buffer (``copy_in=False`` after writing into ``self.pinned_x0()``), then H2D, one launch,
-        D2H of the final states and per-environment costs, and a stream synchronise."""
+        the staging buffer (``copy_in=False`` after writing into ``self.pinned_x0()``), then H2D, launch, D2H of
+        the final states and per-environment costs, and a synchronise.
+
+        Final-state plans (record_stride = 0) are software-pipelined over ``chunks`` ranges of environments: the
+        H2D copy of range c + 1 and the D2H copy of range c - 1 run on their own streams under the kernel of range
+        c (PCIe is full duplex), and consecutive ranges alternate between two launch streams so that the tail wave
+        of one overlaps the head of the next.  Recorded trajectories are time-major, so those plans run as one
+        launch."""
         t = self.torch
         pin = self._staging()
         if copy_in:
             pin["x0"].copy_(t.as_tensor(np.asarray(x0_host, dtype=np.float32)) if not isinstance(x0_host, t.Tensor)
                             else x0_host)
-        self._x0_dev.copy_(pin["x0"], non_blocking=True)
-        res = self.launch(self._x0_dev)
-        pin["x_final"].copy_(res.x_final, non_blocking=True)
-        if res.cost is not None:
-            pin["cost"].copy_(res.cost, non_blocking=True)
-        t.cuda.current_stream().synchronize()
+        chunks = max(1, min(int(chunks), self.N // 65536)) if self.xs is None else 1
+        if chunks <= 1:
+            self._x0_dev.copy_(pin["x0"], non_blocking=True)
+            res = self.launch(self._x0_dev)
+            pin["x_final"].copy_(res.x_final, non_blocking=True)
+            if res.cost is not None:
+                pin["cost"].copy_(res.cost, non_blocking=True)
+            t.cuda.current_stream().synchronize()
+            return pin["x_final"], pin["cost"]
+        pipe = self._pipeline()
+        cur = t.cuda.current_stream()
+        start = t.cuda.Event()
+        start.record(cur)
+        for s in (pipe["h2d"], pipe["d2h"], *pipe["run"]):
+            s.wait_event(start)                              # earlier work on the caller's stream comes first
+        step = -(-self.N // chunks)
+        step = -(-step // 256) * 256                         # whole CTAs per range
+        for c, lo in enumerate(range(0, self.N, step)):
+            hi = min(self.N, lo + step)
+            sl = slice(lo, hi)
+            run = pipe["run"][c & 1]
+            with t.cuda.stream(pipe["h2d"]):
+                self._x0_dev[sl].copy_(pin["x0"][sl], non_blocking=True)
+                up = t.cuda.Event()
+                up.record(pipe["h2d"])
+            with t.cuda.stream(run):
+                run.wait_event(up)
+                self._launch_range(self._x0_dev, lo, hi)
+                done = t.cuda.Event()
+                done.record(run)
+            with t.cuda.stream(pipe["d2h"]):
+                pipe["d2h"].wait_event(done)
+                pin["x_final"][sl].copy_(self.x_final[sl], non_blocking=True)
+                if self.cost is not None:
+                    pin["cost"][sl].copy_(self.cost[sl], non_blocking=True)
+        pipe["d2h"].synchronize()                            # the last D2H copy follows every launch and every H2D copy
         return pin["x_final"], pin["cost"]
 
     def pinned_x0(self):

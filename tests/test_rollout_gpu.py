@@ -395,3 +395,24 @@ def test_full_size_cartpole_c1_matches_oracle():
         res = dyn.rollout(ctl, x0, 500, integrator=integ, record_stride=1)
         xs, us, _, _ = O.rollout(osys, octl, x0.astype(np.float64), 500, integ, record_stride=1)
         assert rel_err(res.xs, xs, (1,)) < 1e-5
+
+
+def test_pipelined_host_rollout_equals_one_launch():
+    """BatchedRollout.run_host streams the environments through in ranges (H2D / kernel / D2H overlapped on separate
+    streams); every environment is independent, so the result is BIT-identical to one launch over the whole batch."""
+    torch = _cuda()
+    from q_learning_with_hjb_b200.rollout import BatchedRollout, RunningCost
+    dyn = make_dynamics("quad2d")
+    ctl = make_controller("quad2d_hover", dyn)
+    N = 5 * 65536 + 777                                 # ragged last range
+    cost = RunningCost(np.eye(6), np.eye(2), np.zeros(6), np.asarray(ctl.uf))
+    plan = BatchedRollout(dyn, ctl, N, 50, cost=cost)
+    x0 = _x0("quad2d", N)
+    ref = plan.launch(torch.as_tensor(x0).cuda())
+    xf_ref, c_ref = ref.x_final.cpu().clone(), ref.cost.cpu().clone()
+    plan.x_final.zero_(); plan.cost.zero_()
+    for chunks in (1, 3, 8):
+        xf, c = plan.run_host(x0, chunks=chunks)
+        assert torch.equal(xf, xf_ref) and torch.equal(c, c_ref), chunks
+        plan.x_final.zero_(); plan.cost.zero_()
+        plan._staging()["x_final"].zero_()

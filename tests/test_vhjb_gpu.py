@@ -366,3 +366,31 @@ def test_batched_policy_rollout_matches_oracle_steps():
         l = np.einsum("bi,ij,bj->b", z, p.Q, z) + np.einsum("bi,ij,bj->b", u - p.uf, p.R, u - p.uf)
         np.testing.assert_allclose(rc[t], l * osys.dt, rtol=1e-4, atol=1e-7)
         x = osys.step(rx[t], u)
+
+
+@pytest.mark.parametrize("name", ["quad10d", "di_mintime"])
+def test_host_batch_train_step_matches_device_batch(name):
+    """VhjbKernels.train_step_host (pinned host batch, copies pipelined under the kernel, gradient accumulated piece by
+    piece with the whole batch's normalisers) against train_step on the same batch already on the device: identical for
+    one piece, and equal up to fp32 summation order for several."""
+    from q_learning_with_hjb_b200.controller.vhjb import AdamState
+    B = 4 * 32768 + 4321
+    torch, k, p, orc, params, xs, dones, costs = _setup(name, B, seed=11, wseed=5)
+    xd, dd, cd = _dev(torch, xs, dones, costs)
+    host = [torch.as_tensor(np.ascontiguousarray(a, dtype=np.float32)).pin_memory() for a in (xs, dones, costs)]
+
+    def run(fn):
+        w = params.clone()
+        opt = AdamState(0, torch.zeros_like(w), torch.zeros_like(w))
+        sums, norm = fn(w, opt)
+        return w, k.grad.clone(), sums.clone(), norm.clone()
+
+    w0, g0, s0, n0 = run(lambda w, opt: k.train_step(w, opt, xd, dd, cd, 0.3, 1e-3))
+    w1, g1, s1, n1 = run(lambda w, opt: k.train_step_host(w, opt, host[0], host[1], host[2], 0.3, 1e-3, chunks=1))
+    assert torch.equal(g0, g1) and torch.equal(w0, w1) and torch.equal(s0, s1) and torch.equal(n0, n1)
+    for chunks in (2, 4):
+        w2, g2, s2, n2 = run(lambda w, opt: k.train_step_host(w, opt, host[0], host[1], host[2], 0.3, 1e-3, chunks=chunks))
+        assert torch.equal(n0, n2)
+        assert (g2 - g0).abs().max() <= 2e-5 * g0.abs().max()
+        assert ((s2 - s0).abs() <= 1e-5 * s0.abs() + 1e-30).all()
+    assert not torch.equal(w0, params)                  # the step really updated the weights
