@@ -256,6 +256,26 @@ int hjb_policy_step(const hjb_system* sys, const hjb_task* task, const float* xf
                     const float* P, int32_t terminal, float* x, const float* u, float* alive, float* total_cost, float* rec_x,
                     float* rec_cost, float* rec_done, int64_t N, void* stream);
 
+/*
+ * Device-resident replay buffer (second half of SURVEY.md 8f row 1).  The reference keeps (state, cost, done) samples in
+ * a deque(maxlen) behind a torch Dataset / shuffling DataLoader (controller/vhjb.py:62-73, :153-154) and extends it
+ * trajectory by trajectory (:299-305).  Here the samples are a ring of `capacity` rows in HBM (buf_x [capacity, n],
+ * buf_cost, buf_done [capacity]; caller-owned, like the ring's head / size bookkeeping).
+ *
+ * hjb_replay_append: the records of a batched rollout (hjb_policy_step's rec_* slices stacked over time: rec_x
+ * [T1, N, n], rec_cost / rec_done [T1, N], rec_done < 0 = no sample) go into the ring in deque order — trajectory by
+ * trajectory, time order within a trajectory: sample (t, e) has sequence number offsets[e] + t (offsets: device,
+ * exclusive prefix sum of the per-trajectory sample counts) and lands in row (tail + seq) mod capacity; samples with
+ * seq < skip (= max(0, total - capacity): they would be pushed out again by this same extend) are dropped.
+ * hjb_replay_gather: minibatch rows xs [B, n], costs [B], dones [B] <- ring rows index[0..B) (device int64: the
+ * caller's shuffled permutation, DataLoader(shuffle=True, drop_last=True)).
+ */
+int hjb_replay_append(const float* rec_x, const float* rec_cost, const float* rec_done, const int64_t* offsets, int64_t T1,
+                      int64_t N, int32_t n, int64_t skip, int64_t tail, int64_t capacity, float* buf_x, float* buf_cost,
+                      float* buf_done, void* stream);
+int hjb_replay_gather(const float* buf_x, const float* buf_cost, const float* buf_done, const int64_t* index, int64_t B,
+                      int32_t n, float* xs, float* costs, float* dones, void* stream);
+
 /* optax.adam update (controller/vhjb.py:120, 286-287; defaults b1 = 0.9, b2 = 0.999, eps = 1e-8), in place on the
  * flat buffers; `step` is the 1-based index of this update. */
 int hjb_adam(float* params, float* m, float* v, const float* grad, int64_t len, float lr, float b1, float b2,

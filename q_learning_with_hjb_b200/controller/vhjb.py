@@ -202,7 +202,7 @@ class VhjbKernels:
         return st
 
     def train_step_host(self, params_flat, opt: AdamState, xs_h, dones_h, costs_h, reg: float, lr: float, group=None,
-                        chunks: int = 8):
+                        chunks: int = 4):
         """``train_step`` on host tensors ([B, n], [B], [B] float32 CPU, ideally pinned).  The done flags go up first
         (the normalisers of vhjb.py:241, 253 are sums over the WHOLE batch and must be known before any gradient
         piece); the states and costs follow in ``chunks`` pieces on a copy stream while the fused loss+gradient kernel
@@ -301,11 +301,12 @@ class VHJBController(Controller):
                     for _ in range(count)]
         interior = sample(config.interior_states_mean, config.interior_states_std, config.num_of_interior_data)
         boundary = sample(config.boundary_states_mean, config.boundary_states_std, config.num_of_boundary_data)
-        self.replay_buffer = ReplayBuffer(self.state_dim, config.maximum_buffer_size)
-        for x in interior:
-            self.replay_buffer.append(x, 0.0, 0.0)
-        for x in boundary:
-            self.replay_buffer.append(x, min(self.termination_cost(x), config.boundary_cost_clip), 1.0)
+        self.replay_buffer = DeviceReplayBuffer(self.state_dim, config.maximum_buffer_size)
+        seed_x = interior + boundary
+        seed_c = [0.0] * len(interior) + [min(self.termination_cost(x), config.boundary_cost_clip) for x in boundary]
+        seed_d = [0.0] * len(interior) + [1.0] * len(boundary)
+        if seed_x:
+            self.replay_buffer.extend(np.stack(seed_x), np.asarray(seed_c), np.asarray(seed_d))
 
     # ---- host-side setup ---------------------------------------------------------------------------------
     def system_additional_init(self) -> None:
@@ -455,14 +456,9 @@ class VHJBController(Controller):
                 # order (one get_initial_state() per trajectory, no other np.random draw in between: vhjb.py:173)
                 x0s = np.stack([self.dynamics.get_initial_state() for _ in range(self.num_of_trajectories_per_epoch)])
                 rx, rc, rd, total = self.rollout_trajectories(x0s)
-                rx, rc, rd = rx.cpu().numpy(), rc.cpu().numpy(), rd.cpu().numpy()
+                # the records go into the device ring in the reference's order (trajectory by trajectory, :305)
+                lengths = self.replay_buffer.extend_rollout(rx, rc, rd)
                 costs_list = [float(v) for v in total.cpu().numpy()]
-                for e in range(self.num_of_trajectories_per_epoch):   # replay buffer filled trajectory by trajectory
-                    for t in range(rd.shape[0]):
-                        if rd[t, e] < 0:
-                            break
-                        self.replay_buffer.append(rx[t, e].astype(np.float64), float(rc[t, e]), float(rd[t, e]))
-                        lengths += 1
             self.train_mode = True
             totals = hjbs = terms = 0.0
             n_batches = 0
@@ -491,9 +487,85 @@ class VHJBController(Controller):
         return avg_cost, std_cost, avg_len, avg_total, avg_hjb, avg_term
 
 
+class DeviceReplayBuffer:
+    """(state, cost, done) samples as a ring in HBM with the reference's semantics — ``deque(maxlen)`` extended
+    trajectory by trajectory, read through ``DataLoader(shuffle=True, drop_last=True)`` (vhjb.py:62-73, :153-154,
+    :299-305).  Rollout records are appended by one ``hjb_replay_append`` launch, minibatches are gathered by one
+    ``hjb_replay_gather`` launch from a device permutation: an epoch of ``VHJBController.train`` touches the host only
+    for its statistics.  ``row k`` of the deque is ring row ``(head + k) % capacity``."""
+
+    def __init__(self, state_dim: int, max_size: int):
+        torch = L.require_cuda()
+        self.torch = torch
+        self.n, self.capacity = int(state_dim), int(max_size)
+        assert self.capacity > 0
+        f32 = dict(device="cuda", dtype=torch.float32)
+        self.xs = torch.zeros((self.capacity, self.n), **f32)
+        self.costs = torch.zeros(self.capacity, **f32)
+        self.dones = torch.zeros(self.capacity, **f32)
+        self.size, self.head = 0, 0
+
+    def __len__(self):
+        return self.size
+
+    def _append_records(self, rec_x, rec_c, rec_d, offsets, total: int):
+        T1, N = rec_d.shape
+        tail = (self.head + self.size) % self.capacity
+        L.check(L.lib().hjb_replay_append(L.ptr(rec_x), L.ptr(rec_c), L.ptr(rec_d), L.ptr(offsets), T1, N, self.n,
+                                          max(0, total - self.capacity), tail, self.capacity, L.ptr(self.xs),
+                                          L.ptr(self.costs), L.ptr(self.dones), L.stream_ptr()), "hjb_replay_append")
+        new_size = min(self.capacity, self.size + total)
+        self.head = (tail + total - new_size) % self.capacity
+        self.size = new_size
+
+    def extend(self, xs, costs, dones):
+        """Append k samples in order (host or device arrays [k, n], [k], [k])."""
+        torch = self.torch
+        x = L.dev_f32(xs, (-1, self.n)).contiguous()
+        k = x.shape[0]
+        if k == 0:
+            return
+        c, d = L.dev_f32(costs, (k,)).contiguous(), L.dev_f32(dones, (k,)).contiguous()
+        assert bool((d >= 0).all()), "done flags are 0 / 1"
+        self._append_records(x.view(k, 1, self.n), c.view(k, 1), d.view(k, 1), torch.zeros(1, device="cuda", dtype=torch.int64), k)
+
+    def append(self, x, cost, done):
+        self.extend(np.asarray(x, dtype=np.float32).reshape(1, self.n), np.float32([cost]), np.float32([done]))
+
+    def extend_rollout(self, rec_x, rec_c, rec_d) -> int:
+        """Append the samples of ``VHJBController.rollout_trajectories`` (device records [T+1, N, n], [T+1, N], [T+1, N];
+        done < 0 = no sample) trajectory by trajectory.  Returns the number of samples (one host read)."""
+        torch = self.torch
+        lengths = (rec_d >= 0).sum(dim=0)
+        offsets = (torch.cumsum(lengths, 0) - lengths).contiguous()
+        total = int(lengths.sum().item())
+        if total:
+            self._append_records(rec_x.contiguous(), rec_c.contiguous(), rec_d.contiguous(), offsets, total)
+        return total
+
+    def batches(self, batch_size: int):
+        """One shuffled pass of full minibatches, as device tensors (xs, costs, dones)."""
+        torch = self.torch
+        perm = (torch.randperm(self.size, device="cuda") + self.head) % self.capacity
+        for b in range(self.size // batch_size):
+            idx = perm[b * batch_size:(b + 1) * batch_size]
+            xs = torch.empty((batch_size, self.n), device="cuda", dtype=torch.float32)
+            costs = torch.empty(batch_size, device="cuda", dtype=torch.float32)
+            dones = torch.empty(batch_size, device="cuda", dtype=torch.float32)
+            L.check(L.lib().hjb_replay_gather(L.ptr(self.xs), L.ptr(self.costs), L.ptr(self.dones), L.ptr(idx), batch_size,
+                                              self.n, L.ptr(xs), L.ptr(costs), L.ptr(dones), L.stream_ptr()), "hjb_replay_gather")
+            yield xs, costs, dones
+
+    def contents(self):
+        """The deque's rows in order, on the host (tests, checkpoints)."""
+        torch = self.torch
+        order = (torch.arange(self.size, device="cuda") + self.head) % self.capacity
+        return self.xs[order].cpu().numpy(), self.costs[order].cpu().numpy(), self.dones[order].cpu().numpy()
+
+
 class ReplayBuffer:
-    """Ring buffer of (state, cost, done) with the reference's sampling semantics (deque(maxlen) + DataLoader with
-    shuffle=True, drop_last=True; vhjb.py:62-73, :154)."""
+    """Host version of the same ring (NumPy); the reference semantics in plain Python for tests and CPU-side tooling
+    (deque(maxlen) + DataLoader with shuffle=True, drop_last=True; vhjb.py:62-73, :154)."""
 
     def __init__(self, state_dim: int, max_size: int):
         self.max_size = int(max_size)

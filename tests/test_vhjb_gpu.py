@@ -394,3 +394,54 @@ def test_host_batch_train_step_matches_device_batch(name):
         assert (g2 - g0).abs().max() <= 2e-5 * g0.abs().max()
         assert ((s2 - s0).abs() <= 1e-5 * s0.abs() + 1e-30).all()
     assert not torch.equal(w0, params)                  # the step really updated the weights
+
+
+def test_device_replay_buffer_has_deque_semantics():
+    """DeviceReplayBuffer (ring in HBM, hjb_replay_append / hjb_replay_gather) against collections.deque(maxlen): plain
+    extends, rollout records appended trajectory by trajectory, wrap-around, and an extend larger than the capacity."""
+    from collections import deque
+    torch = _cuda()
+    from q_learning_with_hjb_b200.controller.vhjb import DeviceReplayBuffer
+    rng = np.random.default_rng(0)
+    n, cap = 3, 37
+    buf, ref = DeviceReplayBuffer(n, cap), deque(maxlen=cap)
+
+    def check():
+        xs, cs, ds = buf.contents()
+        assert len(buf) == len(ref)
+        np.testing.assert_array_equal(xs, np.array([r[0] for r in ref], dtype=np.float32).reshape(-1, n))
+        np.testing.assert_array_equal(cs, np.array([r[1] for r in ref], dtype=np.float32))
+        np.testing.assert_array_equal(ds, np.array([r[2] for r in ref], dtype=np.float32))
+
+    def plain(k):
+        xs = rng.normal(size=(k, n)).astype(np.float32); cs = rng.uniform(size=k).astype(np.float32)
+        ds = (rng.uniform(size=k) < 0.3).astype(np.float32)
+        buf.extend(xs, cs, ds)
+        ref.extend((xs[i], cs[i], ds[i]) for i in range(k))
+
+    def rollout(T1, N):
+        rx = rng.normal(size=(T1, N, n)).astype(np.float32); rc = rng.uniform(size=(T1, N)).astype(np.float32)
+        lens = rng.integers(1, T1 + 1, size=N)
+        rd = np.full((T1, N), -1.0, dtype=np.float32)
+        for e in range(N):
+            rd[:lens[e], e] = 0.0
+            rd[lens[e] - 1, e] = 1.0
+        got = buf.extend_rollout(torch.as_tensor(rx).cuda(), torch.as_tensor(rc).cuda(), torch.as_tensor(rd).cuda())
+        assert got == int(lens.sum())
+        for e in range(N):                                # the reference's order: trajectory by trajectory (vhjb.py:305)
+            ref.extend((rx[t, e], rc[t, e], rd[t, e]) for t in range(lens[e]))
+
+    plain(10); check()
+    buf.append(np.ones(n), 2.0, 1.0); ref.append((np.ones(n, np.float32), np.float32(2.0), np.float32(1.0))); check()
+    rollout(6, 4); check()                                # still below the capacity
+    rollout(9, 5); check()                                # wraps around
+    plain(5); check()
+    rollout(30, 4); check()                               # may exceed the capacity in one extend
+    plain(100); check()                                   # certainly does
+    # one shuffled pass: full minibatches, every row drawn at most once, all rows come from the buffer
+    rows = {tuple(np.concatenate([x, [c, d]]).tolist()) for x, c, d in zip(*buf.contents())}
+    seen = []
+    for xs, cs, ds in buf.batches(8):
+        assert xs.shape == (8, n) and cs.shape == (8,) and ds.shape == (8,)
+        seen += [tuple(np.concatenate([x, [c, d]]).tolist()) for x, c, d in zip(xs.cpu().numpy(), cs.cpu().numpy(), ds.cpu().numpy())]
+    assert len(seen) == (cap // 8) * 8 and len(set(seen)) == len(seen) and set(seen) <= rows

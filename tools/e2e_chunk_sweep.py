@@ -1,0 +1,37 @@
+"""Developer tool: end-to-end time of VhjbKernels.train_step_host and BatchedRollout.run_host against the number of
+pipeline pieces (run on a GPU box)."""
+import os, sys, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch
+from oracle import vhjb_oracle as V
+from tests.helpers_vhjb import flat_params, make_kernels, sample_batch
+from q_learning_with_hjb_b200.controller.vhjb import AdamState
+
+
+def timed(fn, iters=20):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(iters):
+        fn()
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / iters
+
+
+B = 1 << 20
+k, p = make_kernels("quad10d")
+params = torch.as_tensor(flat_params(V.init_weights(p.sys.n, seed=0))).cuda()
+opt = AdamState(0, torch.zeros_like(params), torch.zeros_like(params))
+xs, dones, costs = sample_batch("quad10d", B, seed=1)
+host = [torch.as_tensor(a).pin_memory() for a in (xs, dones, costs)]
+dev = [h.cuda() for h in host]
+print("device batch train_step: %.3f ms" % timed(lambda: k.train_step(params, opt, *dev, 1e-5, 1e-3)))
+for c in (1, 2, 3, 4, 6, 8, 12, 16, 32):
+    def f():
+        k.train_step_host(params, opt, host[0], host[1], host[2], 1e-5, 1e-3, chunks=c)
+        torch.cuda.current_stream().synchronize()
+    print("train_step_host chunks=%2d: %.3f ms" % (c, timed(f)))
