@@ -215,8 +215,10 @@ class VhjbKernels:
         xs, dones, costs = st["xs"][:B], st["dones"][:B], st["costs"][:B]
         cur, cp = t.cuda.current_stream(), st["copy"]
         chunks = max(1, min(int(chunks), B // 32768))
+        # pieces of whole waves of tiles (one 64-state tile per SM and wave): no CTA idles at the end of a piece
+        wave = 64 * t.cuda.get_device_properties(t.cuda.current_device()).multi_processor_count
         step = -(-B // chunks)
-        step = -(-step // 128) * 128                        # whole tiles (and 16-byte aligned rows) per piece
+        step = -(-step // wave) * wave
         ev0 = t.cuda.Event()
         ev0.record(cur)
         ups = []
