@@ -434,12 +434,17 @@ def measure_vhjb(w, steps, warmup, rank, world, local, want_cpu):
         train(); residual_only()
     # clocks: the K timed steps last a few tens of ms, too short for nvidia-smi's sampling; the same train step is
     # therefore also run for ~1 s with the sampler on (untimed), and the timed steps follow immediately
+    # The number of load-loop steps is agreed between the ranks BEFORE the loop (every train step holds two
+    # all-reduces: a per-rank time-based loop would issue different numbers of collectives and deadlock).
+    est_ms = timed(train, 3) / 3.0                                                             # max over ranks
+    n_load = 0 if os.environ.get("HJB_BENCH_NO_CLOCK_LOOP") else int(min(2000, max(20, 1000.0 / max(est_ms, 1e-3))))
     clocks = ClockSampler(local); clocks.start()
     wall0 = time.time()
-    while time.time() - wall0 < (0.0 if os.environ.get("HJB_BENCH_NO_CLOCK_LOOP") else 1.0):   # (skipped under ncu)
-        for _ in range(20):
-            train()
-        torch.cuda.synchronize()
+    for i in range(n_load):                                                                    # (skipped under ncu)
+        train()
+        if i % 20 == 19:
+            torch.cuda.synchronize()
+    torch.cuda.synchronize()
     train_ms = timed(train, steps)
     clk = clocks.stop(wall0, time.time())
     res_ms = timed(residual_only, steps)
@@ -575,7 +580,12 @@ def main():
     ap.add_argument("--accurate-trig", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-vhjb", action="store_true", help="skip the secondary vhjb measurement of the default line")
+    ap.add_argument("--watchdog", type=int, default=900,
+                    help="seconds after which a hung run dumps every thread's stack to stderr and exits (0 = off)")
     args = ap.parse_args()
+    if args.watchdog > 0:   # a deadlocked collective must not hang the box until the driver's own limit
+        import faulthandler
+        faulthandler.dump_traceback_later(args.watchdog, exit=True)
     if args.workload in ROLLOUTS:
         run_rollout(args, ROLLOUTS[args.workload], args.integrator)
     elif args.workload in VHJB:
