@@ -487,7 +487,8 @@ def measure_vhjb(w, steps, warmup, rank, world, local, want_cpu):
         executed_res = 3 * (B * steps / (res_ms * 1e-3)) * 98304 / 1e12
         peak = peaks.get("bf16_tflops", 1590.0)
         d["roofline"] = {"bound": "tensor", "achieved": executed, "unit": "TFLOP/s", "peak": peak, "frac": executed / peak,
-                         "traffic": ncu_traffic("r01_vhjb_quad10d_tc") if (w["problem"] == "quad10d" and B == 1 << 20) else None,
+                         "traffic": (ncu_traffic({"quad10d": "r01_vhjb_quad10d_tc", "di_mintime": "r01_vhjb_di_tc_sin"}.get(w["problem"], ""))
+                                     if B == 1 << 20 else None),
                          "peak_source": ("MEASURED_PEAKS.json bf16_tflops (burst; kind::f16 fp16/bf16 share the rate)"
                                          if "bf16_tflops" in peaks else "fallback 1590 TFLOP/s (B200_PROFILING.md)"),
                          "peak_sustained": peaks.get("bf16_tflops_sustained"),
