@@ -300,6 +300,9 @@ def run_rollout(args, w, integ):
                                "in MEASURED_PEAKS.json)",
                 "peak_nominal": nominal, "frac_of_nominal": achieved / nominal,
                 "flops_per_env_step": fpe, "flop_model": "SURVEY.md 8d v1",
+                # FLOP model v1 leaves the cost accumulation out ("add 2n + 2m when the cost output is requested"); this
+                # run does accumulate the cost, so the fraction with those flops counted is given beside the headline one
+                "frac_with_cost_flops": achieved * (fpe + 2 * n + 2 * m) / fpe / fma_peak_tflops,
                 # algorithmic HBM bytes: x0 read + x_final/cost write per env, plus the recorded trajectory
                 "hbm": {"achieved_gbs": (per_gpu * rec_bytes + envs * (2 * n + 1) * 4 / (kernel_ms * 1e-3)) / 1e9,
                         "peak_gbs": hbm_peak, "peak_source": "MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback"}}
@@ -558,13 +561,18 @@ def measure_fma_peak():
     from q_learning_with_hjb_b200 import _lib as L
     sink = torch.empty(148 * 8 * 256 * 2, device="cuda", dtype=torch.float32)
     flops = C.c_double(0)
-    for _ in range(2):
+    # a PEAK: the best of several probe launches after a warm-up long enough for the clocks to ramp (a single cold
+    # launch was seen to read 61 instead of 71 TFLOP/s, which flatters every fraction reported against it)
+    for _ in range(6):
         L.check(L.lib().hjb_fma_peak_probe(L.ptr(sink), sink.numel(), 20000, C.byref(flops), L.stream_ptr()))
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    L.check(L.lib().hjb_fma_peak_probe(L.ptr(sink), sink.numel(), 20000, C.byref(flops), L.stream_ptr()))
-    e1.record(); torch.cuda.synchronize()
-    return flops.value / (e0.elapsed_time(e1) * 1e-3) / 1e12
+    best = 0.0
+    for _ in range(5):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        L.check(L.lib().hjb_fma_peak_probe(L.ptr(sink), sink.numel(), 20000, C.byref(flops), L.stream_ptr()))
+        e1.record(); torch.cuda.synchronize()
+        best = max(best, flops.value / (e0.elapsed_time(e1) * 1e-3) / 1e12)
+    return best
 
 
 def main():

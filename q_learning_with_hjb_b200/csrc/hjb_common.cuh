@@ -93,14 +93,22 @@ __device__ __forceinline__ float cos_(float a) {
   if constexpr (FAST) return __cosf(a);
   else return cosf(a);
 }
+// one MUFU.RCP: the operands of the fast paths (the determinant of a 2x2 mass matrix, M11, cos of a tilt angle inside
+// (-pi/2, pi/2)) are normal numbers far from the ends of the exponent range, so the denormal / overflow fix-up sequence
+// that __fdividef adds (compare, select, two multiplies) has nothing to do
+__device__ __forceinline__ float rcp_approx(float a) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(a));
+  return r;
+}
 template <bool FAST>
 __device__ __forceinline__ float tan_(float a) {
-  if constexpr (FAST) return __fdividef(__sinf(a), __cosf(a));
+  if constexpr (FAST) return __sinf(a) * rcp_approx(__cosf(a));
   else return tanf(a);
 }
 template <bool FAST>
 __device__ __forceinline__ float rcp_(float a) {
-  if constexpr (FAST) return __fdividef(1.0f, a);
+  if constexpr (FAST) return rcp_approx(a);
   else return 1.0f / a;
 }
 __device__ __forceinline__ float clampf(float v, float lo, float hi) { return fminf(fmaxf(v, lo), hi); }

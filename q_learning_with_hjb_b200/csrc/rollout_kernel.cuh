@@ -5,6 +5,8 @@
 // Trajectories are written time-major ([t][env][i]) so that a warp's stores of one step are contiguous;
 // stores are vectorised (16 B for n = 4, 8 B for even n) and streaming (st.global.cs).
 #pragma once
+#include <type_traits>
+
 #include "systems.cuh"
 
 namespace hjb {
@@ -43,7 +45,9 @@ __device__ __forceinline__ void error_coords(const float* z, const float* xf, co
 }
 
 // l(x, u) = dx^T Q dx + (u - uf)^T R (u - uf)
-template <class S, int COST>
+// CWRAP: some angle of the cost's goal differs from the internal offset (a wrap per step); the loop-invariant test is made
+// once per launch, outside the step loop
+template <class S, int COST, bool CWRAP>
 __device__ __forceinline__ float running_cost(const DevCost& pc, const float* z, const float* u, float l) {
   if constexpr (COST == COST_DIAG) {
 #pragma unroll
@@ -56,7 +60,7 @@ __device__ __forceinline__ float running_cost(const DevCost& pc, const float* z,
         float d = z[i];
 #pragma unroll
         for (int k = 0; k < S::NANG; ++k)
-          if (S::ang(k) == i && pc.dang[k] != 0.f) d = wrap_pi(z[i] + pc.dang[k]);
+          if (CWRAP && S::ang(k) == i && pc.dang[k] != 0.f) d = wrap_pi(z[i] + pc.dang[k]);
         y = d * pc.sq[i];
       } else {
         y = fmaf(z[i], pc.sq[i], pc.c0[i]);
@@ -70,7 +74,13 @@ __device__ __forceinline__ float running_cost(const DevCost& pc, const float* z,
     }
   } else {
     float dx[S::N], du[S::M];
-    error_coords<S>(z, pc.xf, pc.dang, dx);
+    if constexpr (CWRAP) error_coords<S>(z, pc.xf, pc.dang, dx);
+    else {
+#pragma unroll
+      for (int i = 0; i < S::N; ++i) dx[i] = z[i] - pc.xf[i];
+#pragma unroll
+      for (int k = 0; k < S::NANG; ++k) dx[S::ang(k)] = z[S::ang(k)];
+    }
 #pragma unroll
     for (int k = 0; k < S::M; ++k) du[k] = u[k] - pc.uf[k];
 #pragma unroll
@@ -160,6 +170,8 @@ __global__ void __launch_bounds__(256) rollout_kernel(const __grid_constant__ Ro
   int64_t rec = 1;      // next trajectory slot
   int32_t phase = 0;    // steps since the last recorded state
 
+  auto run = [&](auto cwrap) {
+  constexpr bool CWRAP = decltype(cwrap)::value;
   for (int32_t t = 0; t < a.T; ++t) {
     if constexpr (BOX) alive = alive && inside_box<S>(a.box, z);
     typename S::Trig tr;
@@ -174,7 +186,7 @@ __global__ void __launch_bounds__(256) rollout_kernel(const __grid_constant__ Ro
 #pragma unroll
       for (int i = 0; i < N; ++i) zn[i] = z[i];
       float l = 0.f;
-      if constexpr (COST != COST_NONE) l = running_cost<S, COST>(a.cost, z, u, 0.f);
+      if constexpr (COST != COST_NONE) l = running_cost<S, COST, CWRAP>(a.cost, z, u, 0.f);
       if constexpr (!C::kClips) clip_u<S>(a.sys, u);
       integrate<S, INTEG>(a.sys, zn, tr, u);
       if (alive) {
@@ -184,7 +196,7 @@ __global__ void __launch_bounds__(256) rollout_kernel(const __grid_constant__ Ro
         ++nsteps;
       }
     } else {
-      if constexpr (COST != COST_NONE) J = running_cost<S, COST>(a.cost, z, u, J);
+      if constexpr (COST != COST_NONE) J = running_cost<S, COST, CWRAP>(a.cost, z, u, J);
       // Dynamics.simulate's own clip (dynamics_basic.py:118); idempotent when the controller already clipped
       if constexpr (!C::kClips) clip_u<S>(a.sys, u);
       integrate<S, INTEG>(a.sys, z, tr, u);
@@ -201,6 +213,14 @@ __global__ void __launch_bounds__(256) rollout_kernel(const __grid_constant__ Ro
       }
     }
   }
+  };
+  bool cost_wraps = false;
+  if constexpr (COST != COST_NONE) {
+#pragma unroll
+    for (int k = 0; k < S::NANG; ++k) cost_wraps = cost_wraps || (a.cost.dang[k] != 0.f);
+  }
+  if (COST != COST_NONE && cost_wraps) run(std::true_type{});
+  else run(std::false_type{});
   if (a.x_final) {
     float x[N];
     to_external<S>(a.sys, z, x);
