@@ -4,6 +4,10 @@
 #include <cmath>
 #include <cstring>
 
+#include <cstdint>
+#include <cstdlib>
+#include <cstring>
+
 #include "rollout_kernel.cuh"
 #include "step_kernels.cuh"
 
@@ -214,6 +218,13 @@ int hjb_rollout(const hjb_system* sys, const hjb_control* ctl, const hjb_cost* c
   a.N = N; a.T = T;
   a.stride = opts->record_stride > 0 ? opts->record_stride : 1;
   a.n_rec = T / a.stride;
+  {  // TMA bulk stores of whole 32-row blocks need 16-byte aligned time slices (HJB_ROLLOUT_STORES=direct: A/B switch)
+    const char* e = std::getenv("HJB_ROLLOUT_STORES");
+    const bool direct = e && std::strcmp(e, "direct") == 0;
+    const bool ok_x = !xs || (((uintptr_t)xs % 16 == 0) && ((N * sys->n) % 4 == 0));
+    const bool ok_u = !us || (((uintptr_t)us % 16 == 0) && ((N * sys->m) % 4 == 0));
+    a.staged = (!direct && ok_x && ok_u) ? 1 : 0;
+  }
 
   RolloutVariant v;
   v.integrator = opts->integrator;

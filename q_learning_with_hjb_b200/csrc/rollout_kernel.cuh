@@ -3,7 +3,8 @@
 // State, RK4 stages and the cost accumulator live in registers; system constants, gains and cost
 // matrices are read from the kernel parameter space (constant bank operands, no register cost).
 // Trajectories are written time-major ([t][env][i]) so that a warp's stores of one step are contiguous;
-// stores are vectorised (16 B for n = 4, 8 B for even n) and streaming (st.global.cs).
+// stores are vectorised (16 B for n = 4, 8 B for even n) and streaming (st.global.cs); rows of awkward width (n = 10, m = 3)
+// are staged per warp in shared memory and written by one TMA bulk store per 32-row block.
 #pragma once
 #include <type_traits>
 
@@ -28,6 +29,7 @@ struct RolloutArgs {
   int32_t T;
   int32_t stride;  // record stride (>= 1 when xs/us requested)
   int32_t n_rec;   // T / stride recorded intervals
+  int32_t staged;  // trajectory rows may go through shared memory + cp.async.bulk (alignment checked by the launcher)
 };
 
 // error coordinate of internal state z w.r.t. a goal whose non-angle part is xf and whose angle part differs
@@ -139,6 +141,41 @@ __device__ __forceinline__ void integrate(const DevSys& ps, float* x, const type
   wrap_state<S>(x);
 }
 
+// ---- trajectory write-back through shared memory + TMA bulk stores ----------------------------------------------
+// A warp's 32 rows of one recorded time slice are contiguous in global memory (time-major layout): 128 W bytes.  Each
+// lane writes its row into the warp's staging buffer and ONE lane issues a single cp.async.bulk (shared -> global) for
+// the whole block, so the memory system sees full lines whatever the row width (per-thread stores of odd widths —
+// n = 10 is 5 x 8 bytes at a 40-byte stride, m = 3 is 3 x 4 bytes at 12 — touch every 32-byte sector several times:
+// measured 35 % of the HBM rate for the 10-D quadcopter).  Two buffers per stream of rows; before a buffer is
+// rewritten the issuing lane waits until at most one bulk group is still reading.
+__device__ __forceinline__ void bulk_store_issue(float* gdst, const float* ssrc, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n\tcp.async.bulk.commit_group;" ::"l"(gdst),
+               "r"((uint32_t)__cvta_generic_to_shared(ssrc)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_store_wait_read_1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
+__device__ __forceinline__ void bulk_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+template <int W>
+__device__ __forceinline__ void staged_store(float* stage, int lane, float* gblock, const float* v) {
+  if (lane == 0) bulk_store_wait_read_1();      // the bulk store that last read this buffer is older than the latest one
+  __syncwarp();
+  float* row = stage + lane * W;
+  if constexpr (W % 4 == 0) {
+#pragma unroll
+    for (int i = 0; i < W / 4; ++i) reinterpret_cast<float4*>(row)[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+  } else if constexpr (W % 2 == 0) {
+#pragma unroll
+    for (int i = 0; i < W / 2; ++i) reinterpret_cast<float2*>(row)[i] = make_float2(v[2 * i], v[2 * i + 1]);
+  } else {
+#pragma unroll
+    for (int i = 0; i < W; ++i) row[i] = v[i];
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  __syncwarp();
+  if (lane == 0) bulk_store_issue(gblock, stage, 32u * W * 4u);
+}
+
 template <class S>
 __device__ __forceinline__ bool inside_box(const DevBox& b, const float* z) {
   float dx[S::N];
@@ -153,6 +190,19 @@ template <class S, class C, int INTEG, bool REC, int COST, bool BOX>
 __global__ void __launch_bounds__(256) rollout_kernel(const __grid_constant__ RolloutArgs a) {
   constexpr int N = S::N, M = S::M;
   const int64_t env = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  // recorded rows go through the warp's staging buffers when the whole warp is in range and every time slice starts
+  // on a 16-byte boundary (a.staged: N W divisible by 4 floats, 16-byte aligned bases); otherwise per-thread stores
+  // Measured on B200 (bench.py --record-stride 1, staged against direct): n = 10 / m = 3 rows 6248 against 2399 GB/s;
+  // n = 6 rows +4 %; n = 4 / m = 1 rows (already 16-byte stores) lose to the two proxy fences per step (3894 against
+  // 6439 GB/s).  So only rows whose width is neither a vector width nor small are staged: the 10-D quadcopter's.
+  constexpr bool kStageX = REC && (N % 4 != 0) && (N > 6);
+  constexpr bool kStageU = REC && (M % 2 != 0) && (M > 1);
+  __shared__ __align__(128) float stage_x[kStageX ? 8 * 2 * 32 * N : 1];
+  __shared__ __align__(128) float stage_u[kStageU ? 8 * 2 * 32 * M : 1];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int64_t env0 = env - lane;
+  bool staged = false;
+  if constexpr (kStageX || kStageU) staged = a.staged != 0 && env0 + 32 <= a.N;
   if (env >= a.N) return;
 
   float z[N];  // internal state
@@ -179,7 +229,10 @@ __global__ void __launch_bounds__(256) rollout_kernel(const __grid_constant__ Ro
     float u[M];
     C::template control<S>(a.sys, a.ctl, z, tr, u);
     if constexpr (REC) {
-      if (phase == 0 && a.us && rec <= a.n_rec) store_row<M>(a.us, (rec - 1) * a.N + env, u);
+      if (phase == 0 && a.us && rec <= a.n_rec) {
+        if (kStageU && staged) staged_store<M>(stage_u + (wib * 2 + (int)(rec & 1)) * 32 * M, lane, a.us + ((rec - 1) * a.N + env0) * M, u);
+        else store_row<M>(a.us, (rec - 1) * a.N + env, u);
+      }
     }
     if constexpr (BOX) {
       float zn[N];
@@ -207,7 +260,8 @@ __global__ void __launch_bounds__(256) rollout_kernel(const __grid_constant__ Ro
         if (a.xs) {
           float x[N];
           to_external<S>(a.sys, z, x);
-          store_row<N>(a.xs, rec * a.N + env, x);
+          if (kStageX && staged) staged_store<N>(stage_x + (wib * 2 + (int)(rec & 1)) * 32 * N, lane, a.xs + (rec * a.N + env0) * N, x);
+          else store_row<N>(a.xs, rec * a.N + env, x);
         }
         ++rec;
       }
@@ -221,6 +275,9 @@ __global__ void __launch_bounds__(256) rollout_kernel(const __grid_constant__ Ro
   }
   if (COST != COST_NONE && cost_wraps) run(std::true_type{});
   else run(std::false_type{});
+  if constexpr (kStageX || kStageU) {
+    if (staged && lane == 0) bulk_store_wait_all();   // the staging buffers must outlive the bulk stores that read them
+  }
   if (a.x_final) {
     float x[N];
     to_external<S>(a.sys, z, x);
