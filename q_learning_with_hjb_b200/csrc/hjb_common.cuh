@@ -73,6 +73,19 @@ __device__ __forceinline__ float wrap_pi(float a) {
   float r = fmaf(-k, kTwoPiHi, a);
   return fmaf(-k, kTwoPiLo, r);
 }
+// The fast-math kernels round a / 2 pi to the nearest integer with the 1.5 * 2^23 trick (two FMA-pipe instructions)
+// instead of floor (FRND runs on the quarter-rate XU pipe next to sin / cos / rcp: with 6 wraps per acrobot step the XU
+// pipe was ~80 % busy).  Same value as wrap_pi except at an exact tie, a = pi (mod 2 pi), which maps to +pi instead of
+// -pi: the same angle.
+template <bool FAST>
+__device__ __forceinline__ float wrap_pi_(float a) {
+  if constexpr (FAST) {
+    const float k = __fadd_rn(__fmaf_rn(a, kInvTwoPi, 12582912.f), -12582912.f);
+    return fmaf(-k, kTwoPiLo, fmaf(-k, kTwoPiHi, a));
+  } else {
+    return wrap_pi(a);
+  }
+}
 
 template <bool FAST>
 __device__ __forceinline__ void sincos_(float a, float& s, float& c) {

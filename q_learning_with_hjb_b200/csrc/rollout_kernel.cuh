@@ -42,7 +42,7 @@ __device__ __forceinline__ void error_coords(const float* z, const float* xf, co
   for (int k = 0; k < S::NANG; ++k) {
     const int i = S::ang(k);
     d[i] = z[i];
-    if (dang[k] != 0.f) d[i] = wrap_pi(z[i] + dang[k]);
+    if (dang[k] != 0.f) d[i] = wrap_pi_<S::kFast>(z[i] + dang[k]);
   }
 }
 
@@ -62,7 +62,7 @@ __device__ __forceinline__ float running_cost(const DevCost& pc, const float* z,
         float d = z[i];
 #pragma unroll
         for (int k = 0; k < S::NANG; ++k)
-          if (CWRAP && S::ang(k) == i && pc.dang[k] != 0.f) d = wrap_pi(z[i] + pc.dang[k]);
+          if (CWRAP && S::ang(k) == i && pc.dang[k] != 0.f) d = wrap_pi_<S::kFast>(z[i] + pc.dang[k]);
         y = d * pc.sq[i];
       } else {
         y = fmaf(z[i], pc.sq[i], pc.c0[i]);

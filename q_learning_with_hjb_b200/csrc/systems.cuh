@@ -25,14 +25,14 @@ namespace hjb {
 template <class S>
 __device__ __forceinline__ void wrap_state(float* z) {
 #pragma unroll
-  for (int k = 0; k < S::NANG; ++k) z[S::ang(k)] = wrap_pi(z[S::ang(k)]);
+  for (int k = 0; k < S::NANG; ++k) z[S::ang(k)] = wrap_pi_<S::kFast>(z[S::ang(k)]);
 }
 template <class S>
 __device__ __forceinline__ void to_internal(const DevSys& p, const float* x, float* z) {
 #pragma unroll
   for (int i = 0; i < S::N; ++i) z[i] = x[i];
 #pragma unroll
-  for (int k = 0; k < S::NANG; ++k) z[S::ang(k)] = wrap_pi(x[S::ang(k)] - p.aoff[k]);
+  for (int k = 0; k < S::NANG; ++k) z[S::ang(k)] = wrap_pi_<S::kFast>(x[S::ang(k)] - p.aoff[k]);
 }
 // x_th = wrap(z_th + aoff); with aoff == 0 the state is returned bit-for-bit
 template <class S>
@@ -41,7 +41,7 @@ __device__ __forceinline__ void to_external(const DevSys& p, const float* z, flo
   for (int i = 0; i < S::N; ++i) x[i] = z[i];
 #pragma unroll
   for (int k = 0; k < S::NANG; ++k)
-    if (p.aoff[k] != 0.f) x[S::ang(k)] = wrap_pi(z[S::ang(k)] + p.aoff[k]);
+    if (p.aoff[k] != 0.f) x[S::ang(k)] = wrap_pi_<S::kFast>(z[S::ang(k)] + p.aoff[k]);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -303,7 +303,7 @@ struct CartpoleESCtl {
     float dx[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) dx[i] = x[i] - pc.xf[i];
-    dx[1] = wrap_pi(dx[1]);                                          // :75
+    dx[1] = wrap_pi_<S::kFast>(dx[1]);                               // :75
     const float de = fmaf(0.5f * x[3], x[3], -t.c) - pc.aux[5];      // :78, :90-95
     const bool near = (fabsf(de) < pc.aux[3]) && (fmaf(dx[1], dx[1], dx[3] * dx[3]) < pc.aux[4]);  // :79
     float ulqr = 0.f;                                                // :80
@@ -328,8 +328,9 @@ struct AcrobotESCtl {
                                                  const typename S::Trig& t, float* u) {
     static_assert(S::KIND == HJB_SYS_ACROBOT, "acrobot energy shaping needs the acrobot");
     float dx[4];
-    dx[0] = wrap_pi(x[0] - pc.xf[0]);                                // :109
-    dx[1] = wrap_pi(x[1] - pc.xf[1]);
+    // (the internal state is wrapped: z in [-pi, pi); a goal angle of 0 — q2 in the reference, :131 — needs no second wrap)
+    dx[0] = wrap_pi_<S::kFast>(x[0] - pc.xf[0]);                     // :109
+    dx[1] = pc.xf[1] != 0.f ? wrap_pi_<S::kFast>(x[1] - pc.xf[1]) : x[1];
     dx[2] = x[2] - pc.xf[2];
     dx[3] = x[3] - pc.xf[3];
     float quad = 0.f;                                                // :114  dx^T P dx
@@ -346,7 +347,7 @@ struct AcrobotESCtl {
     typename S::Terms r;
     S::terms(ps, x, t, r);                                           // :83-86
     const float ubar = (S::energy(ps, x, t, r) - pc.aux[4]) * x[2];  // :88
-    const float a2 = fmaf(pc.aux[2], ubar, -fmaf(pc.aux[0], wrap_pi(x[1]), pc.aux[1] * x[3]));  // :90
+    const float a2 = fmaf(pc.aux[2], ubar, -fmaf(pc.aux[0], x[1], pc.aux[1] * x[3]));  // :90 (wrap(q2) = q2: already wrapped)
     const float i11 = rcp_<S::kFast>(r.m11);
     const float usw = fmaf(fmaf(-r.m12 * r.m12, i11, r.m22), a2, fmaf(-r.m12 * i11, r.h1, r.h2));  // :92
     u[0] = clampf(quad < pc.aux[3] ? ulqr : usw, ps.umin[0], ps.umax[0]);  // :119
