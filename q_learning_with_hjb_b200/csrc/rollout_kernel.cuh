@@ -49,8 +49,12 @@ __device__ __forceinline__ void error_coords(const float* z, const float* xf, co
 // l(x, u) = dx^T Q dx + (u - uf)^T R (u - uf)
 // CWRAP: some angle of the cost's goal differs from the internal offset (a wrap per step); the loop-invariant test is made
 // once per launch, outside the step loop
+// c0r / r0r: the additive constants of the diagonal form, held in registers by the caller (an FFMA takes ONE constant-bank
+// operand; left to itself the compiler re-loads the second one with an LDC inside the step loop — 12 of the 112
+// instructions of a 10-D quadcopter step)
 template <class S, int COST, bool CWRAP>
-__device__ __forceinline__ float running_cost(const DevCost& pc, const float* z, const float* u, float l) {
+__device__ __forceinline__ float running_cost(const DevCost& pc, const float* c0r, const float* r0r, const float* z,
+                                              const float* u, float l) {
   if constexpr (COST == COST_DIAG) {
 #pragma unroll
     for (int i = 0; i < S::N; ++i) {
@@ -65,13 +69,13 @@ __device__ __forceinline__ float running_cost(const DevCost& pc, const float* z,
           if (CWRAP && S::ang(k) == i && pc.dang[k] != 0.f) d = wrap_pi_<S::kFast>(z[i] + pc.dang[k]);
         y = d * pc.sq[i];
       } else {
-        y = fmaf(z[i], pc.sq[i], pc.c0[i]);
+        y = fmaf(z[i], pc.sq[i], c0r[i]);
       }
       l = fmaf(y, y, l);
     }
 #pragma unroll
     for (int k = 0; k < S::M; ++k) {
-      const float y = fmaf(u[k], pc.sr[k], pc.r0[k]);
+      const float y = fmaf(u[k], pc.sr[k], r0r[k]);
       l = fmaf(y, y, l);
     }
   } else {
@@ -220,6 +224,17 @@ __global__ void __launch_bounds__(256) rollout_kernel(const __grid_constant__ Ro
   int64_t rec = 1;      // next trajectory slot
   int32_t phase = 0;    // steps since the last recorded state
 
+  // (+ a zero that only the launch knows: a plain copy of a kernel parameter is re-loaded by ptxas wherever it is used)
+  float c0r[N], r0r[M];
+  // Measured: worth it for the 13 terms of the 10-D quadcopter (112 -> 103 instructions per step, 2.91e11 -> 3.10e11
+  // env-steps/s); for the narrower systems the compiler keeps the constants in registers by itself and the detour costs
+  // ~3 % (C4), so those read the parameters directly.
+  constexpr bool kRegConsts = COST == COST_DIAG && (N + M) > 8;
+  const float opaque0 = kRegConsts && a.T < 0 ? 1.f : 0.f;
+#pragma unroll
+  for (int i = 0; i < N; ++i) c0r[i] = COST == COST_DIAG ? (kRegConsts ? a.cost.c0[i] + opaque0 : a.cost.c0[i]) : 0.f;
+#pragma unroll
+  for (int k = 0; k < M; ++k) r0r[k] = COST == COST_DIAG ? (kRegConsts ? a.cost.r0[k] + opaque0 : a.cost.r0[k]) : 0.f;
   auto run = [&](auto cwrap) {
   constexpr bool CWRAP = decltype(cwrap)::value;
   for (int32_t t = 0; t < a.T; ++t) {
@@ -239,7 +254,7 @@ __global__ void __launch_bounds__(256) rollout_kernel(const __grid_constant__ Ro
 #pragma unroll
       for (int i = 0; i < N; ++i) zn[i] = z[i];
       float l = 0.f;
-      if constexpr (COST != COST_NONE) l = running_cost<S, COST, CWRAP>(a.cost, z, u, 0.f);
+      if constexpr (COST != COST_NONE) l = running_cost<S, COST, CWRAP>(a.cost, c0r, r0r, z, u, 0.f);
       if constexpr (!C::kClips) clip_u<S>(a.sys, u);
       integrate<S, INTEG>(a.sys, zn, tr, u);
       if (alive) {
@@ -249,7 +264,7 @@ __global__ void __launch_bounds__(256) rollout_kernel(const __grid_constant__ Ro
         ++nsteps;
       }
     } else {
-      if constexpr (COST != COST_NONE) J = running_cost<S, COST, CWRAP>(a.cost, z, u, J);
+      if constexpr (COST != COST_NONE) J = running_cost<S, COST, CWRAP>(a.cost, c0r, r0r, z, u, J);
       // Dynamics.simulate's own clip (dynamics_basic.py:118); idempotent when the controller already clipped
       if constexpr (!C::kClips) clip_u<S>(a.sys, u);
       integrate<S, INTEG>(a.sys, z, tr, u);
