@@ -202,7 +202,7 @@ class VhjbKernels:
         return st
 
     def train_step_host(self, params_flat, opt: AdamState, xs_h, dones_h, costs_h, reg: float, lr: float, group=None,
-                        chunks: int = 4):
+                        chunks: Optional[int] = None):
         """``train_step`` on host tensors ([B, n], [B], [B] float32 CPU, ideally pinned).  The done flags go up first
         (the normalisers of vhjb.py:241, 253 are sums over the WHOLE batch and must be known before any gradient
         piece); the states and costs follow in ``chunks`` pieces on a copy stream while the fused loss+gradient kernel
@@ -214,11 +214,21 @@ class VhjbKernels:
         st = self._host_staging(B)
         xs, dones, costs = st["xs"][:B], st["dones"][:B], st["costs"][:B]
         cur, cp = t.cuda.current_stream(), st["copy"]
-        chunks = max(1, min(int(chunks), B // 32768))
         # pieces of whole waves of tiles (one 64-state tile per SM and wave): no CTA idles at the end of a piece
         wave = 64 * t.cuda.get_device_properties(t.cuda.current_device()).multi_processor_count
-        step = -(-B // chunks)
-        step = -(-step // wave) * wave
+        if chunks is None:
+            # default schedule: a small first piece (only ITS copy is exposed), then doubling — the copy engine moves
+            # states faster than the kernel consumes them, so every later copy hides under the previous piece's kernel
+            bounds, lo, size = [], 0, 4 * wave
+            while B - lo > 2 * size:
+                bounds.append((lo, lo + size))
+                lo, size = lo + size, 2 * size
+            bounds.append((lo, B))
+        else:
+            chunks = max(1, min(int(chunks), B // 32768))
+            step = -(-B // chunks)
+            step = -(-step // wave) * wave
+            bounds = [(lo, min(B, lo + step)) for lo in range(0, B, step)]
         ev0 = t.cuda.Event()
         ev0.record(cur)
         ups = []
@@ -227,8 +237,8 @@ class VhjbKernels:
             dones.copy_(dones_h, non_blocking=True)
             evd = t.cuda.Event()
             evd.record(cp)
-            for lo in range(0, B, step):
-                sl = slice(lo, min(B, lo + step))
+            for lo, hi in bounds:
+                sl = slice(lo, hi)
                 xs[sl].copy_(xs_h[sl], non_blocking=True)
                 costs[sl].copy_(costs_h[sl], non_blocking=True)
                 ev = t.cuda.Event()

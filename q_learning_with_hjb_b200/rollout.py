@@ -160,12 +160,13 @@ class BatchedRollout:
             self._pipe = {"h2d": t.cuda.Stream(), "d2h": t.cuda.Stream(), "run": [t.cuda.Stream(), t.cuda.Stream()]}
         return self._pipe
 
-    def run_host(self, x0_host, copy_in: bool = True, chunks: int = 8):
+    def run_host(self, x0_host, copy_in: bool = True, chunks: int = 32):
         """x0 on the host -> (x_final, cost) on the host.  Copies x0 into pinned staging unless it already IS
         the staging buffer (``copy_in=False`` after writing into ``self.pinned_x0()``), then H2D, launch, D2H of
         the final states and per-environment costs, and a synchronise.
 
-        Final-state plans (record_stride = 0) are software-pipelined over ``chunks`` ranges of environments: the
+        Final-state plans (record_stride = 0) are software-pipelined over ``chunks`` ranges of environments (measured on
+        C4: 1 range 42.5 ms, 8 ranges 28.7 ms, 32 ranges 27.2 ms against 26.7 ms for the kernel alone): the
         H2D copy of range c + 1 and the D2H copy of range c - 1 run on their own streams under the kernel of range
         c (PCIe is full duplex), and consecutive ranges alternate between two launch streams so that the tail wave
         of one overlaps the head of the next.  Recorded trajectories are time-major, so those plans run as one

@@ -30,8 +30,22 @@ xs, dones, costs = sample_batch("quad10d", B, seed=1)
 host = [torch.as_tensor(a).pin_memory() for a in (xs, dones, costs)]
 dev = [h.cuda() for h in host]
 print("device batch train_step: %.3f ms" % timed(lambda: k.train_step(params, opt, *dev, 1e-5, 1e-3)))
-for c in (1, 2, 3, 4, 6, 8, 12, 16, 32):
+for c in (None, 1, 2, 4, 6, 8):
     def f():
         k.train_step_host(params, opt, host[0], host[1], host[2], 1e-5, 1e-3, chunks=c)
         torch.cuda.current_stream().synchronize()
-    print("train_step_host chunks=%2d: %.3f ms" % (c, timed(f)))
+    print("train_step_host chunks=%s: %.3f ms" % (c, timed(f)))
+
+# ---- rollout run_host: number of environment ranges ----
+from tests.helpers import make_controller, make_dynamics
+from q_learning_with_hjb_b200.rollout import BatchedRollout, RunningCost
+dyn = make_dynamics("quad2d"); dyn.fast_trig = True
+ctl = make_controller("quad2d_hover", dyn)
+N = 1 << 24
+plan = BatchedRollout(dyn, ctl, N, 1000, cost=RunningCost(np.eye(6), np.eye(2), np.zeros(6), np.asarray(ctl.uf)))
+pin = plan.pinned_x0()
+pin.copy_(torch.rand((N, 6)) * 2 - 1)
+x0d = pin.cuda()
+print("rollout kernel alone: %.2f ms" % timed(lambda: plan.launch(x0d), 5))
+for c in (1, 4, 8, 12, 16, 24, 32):
+    print("run_host chunks=%2d: %.2f ms" % (c, timed(lambda: plan.run_host(pin, copy_in=False, chunks=c), 5)))
