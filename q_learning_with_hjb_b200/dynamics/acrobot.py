@@ -79,3 +79,9 @@ class Acrobot(Dynamics):
         A[2:, :2] = -Minv @ dG_dq
         B = np.concatenate([np.zeros(2), Minv @ self.get_B()]).reshape(4, 1)
         return A, B
+
+    def plot_trajectory(self, ts, xs, margin=0.5):
+        """Animation of a trajectory (reference: dynamics/acrobot.py:82-110); needs matplotlib."""
+        from q_learning_with_hjb_b200.utils import plotting as P
+        reach = self.l1 + self.l2 + margin
+        return P.animate(ts, xs, lambda x: P.acrobot_frame(x, self.l1, self.l2), (-reach, reach), (-reach, reach))

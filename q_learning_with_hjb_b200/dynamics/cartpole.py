@@ -40,3 +40,9 @@ class Cartpole(Dynamics):
         A[2:, :2] = -Minv @ dG_dq
         B = np.concatenate([np.zeros(2), Minv @ self.get_B()]).reshape(4, 1)
         return A, B
+
+    def plot_trajectory(self, ts, xs, cart_width=0.4, cart_height=0.2, pole_radius=0.05, x_range=np.array([-2, 2]),
+                        y_range=np.array([-1, 3])):
+        """Animation of a trajectory (reference: dynamics/cartpole.py:66-103); needs matplotlib."""
+        from q_learning_with_hjb_b200.utils import plotting as P
+        return P.animate(ts, xs, lambda x: P.cartpole_frame(x, self.l, cart_width, cart_height), tuple(x_range), tuple(y_range))

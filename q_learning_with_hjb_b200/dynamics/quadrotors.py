@@ -32,6 +32,13 @@ class Quadrotors2D(Dynamics):
         B[5, :] = [self.r / self.I, -self.r / self.I]
         return A, B
 
+    def plot_trajectory(self, ts, xs):
+        """Animation of a trajectory (reference: dynamics/quadrotors.py:72-104); needs matplotlib."""
+        from q_learning_with_hjb_b200.utils import plotting as P
+        xs = np.asarray(xs)
+        return P.animate(ts, xs, lambda x: P.quad2d_frame(x, self.r), P.span(xs[:, 0], 2 * self.r), P.span(xs[:, 1], 2 * self.r),
+                         trail=lambda x: x[:2])
+
 
 class NearHoverQuadcopter(Dynamics):
     """x = [p_x, p_y, p_z, theta_x, theta_y, v_x, v_y, v_z, omega_x, omega_y], u = [Tz, Sx, Sy]."""
@@ -55,3 +62,10 @@ class NearHoverQuadcopter(Dynamics):
         B[7, 0] = self.kT / self.m
         B[8, 1] = B[9, 2] = self.n0
         return A, B
+
+    def plot_trajectory(self, ts, xs):
+        """3-D animation of a trajectory (reference: dynamics/quadrotors.py:172-196); needs matplotlib."""
+        from q_learning_with_hjb_b200.utils import plotting as P
+        xs = np.asarray(xs)
+        return P.animate(ts, xs, P.quad10d_frame, P.span(xs[:, 0], 0.5), P.span(xs[:, 1], 0.5), P.span(xs[:, 2], 0.5),
+                         three_d=True, trail=lambda x: x[:3])

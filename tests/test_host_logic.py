@@ -96,3 +96,26 @@ def test_gin_files_bind_like_the_reference():
     assert list(cfg.features) == [128, 128, 64] and cfg.batch_size == 256 and cfg.epsilon == 1e-10
     assert cfg.Q.shape == (6, 6) and cfg.Q.dtype == np.float32
     np.testing.assert_allclose(cfg.uf, [4.905, 4.905], rtol=1e-6)
+
+
+def test_plot_trajectory_geometry_and_optional_matplotlib():
+    """plot_trajectory is kept for drop-in compatibility (off the hot path): the frame geometry is plain NumPy, and the
+    methods exist on every system the reference animates; without matplotlib they raise ImportError, not AttributeError."""
+    from q_learning_with_hjb_b200.utils import plotting as P
+    cart, pole = P.cartpole_frame([0.5, np.pi, 0, 0], l=1.0)
+    np.testing.assert_allclose(pole[1], [0.5, 1.0], atol=1e-12)            # theta = pi: upright
+    (links,) = P.acrobot_frame([np.pi, 0.0, 0, 0], 0.5, 1.0)
+    np.testing.assert_allclose(links[-1], [0.0, 1.5], atol=1e-12)          # both links up
+    (links,) = P.acrobot_frame([0.0, 0.0, 0, 0], 0.5, 1.0)
+    np.testing.assert_allclose(links[-1], [0.0, -1.5], atol=1e-12)         # hanging
+    body = P.quad2d_frame([1.0, 2.0, 0.0, 0, 0, 0], 0.25)[0]
+    np.testing.assert_allclose(body, [[0.75, 2.0], [1.25, 2.0]])
+    assert len(P.quad10d_frame(np.zeros(10))) == 2
+    for kind in ("cartpole", "acrobot", "quad2d", "quad10d"):
+        dyn = make_dynamics(kind)
+        assert callable(dyn.plot_trajectory)
+    try:
+        import matplotlib  # noqa: F401
+    except ImportError:
+        with pytest.raises(ImportError):
+            make_dynamics("cartpole").plot_trajectory(np.arange(3) * 0.1, np.zeros((3, 4)))
