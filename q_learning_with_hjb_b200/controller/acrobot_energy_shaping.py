@@ -4,7 +4,7 @@ reference recomputes per step (:112) is solved once."""
 import numpy as np
 
 from q_learning_with_hjb_b200 import _lib as L
-from q_learning_with_hjb_b200.controller.controller_basic import DeviceController, lqr_gain
+from q_learning_with_hjb_b200.controller.controller_basic import DeviceController, closed_loop, lqr_gain, unclipped
 from q_learning_with_hjb_b200.dynamics.acrobot import Acrobot
 
 
@@ -47,3 +47,23 @@ class AcrobotEnergyShapingController(DeviceController):
         L.fill(c.xf, self.xf)
         L.fill(c.aux, [self.K[0], self.K[1], self.K[2], self.eps])
         return c
+
+    def get_swingup_input(self, x):
+        """The collocated swing-up branch alone, un-clipped (:74-98): the device law with the LQR catch region emptied."""
+        c = self.control_spec()
+        c.aux[3] = -1.0                                   # dx^T P dx < eps never holds
+        return self._efforts(unclipped(self.acrobot.system_spec()), c, x)
+
+
+def test_acrobot(acrobot: Acrobot, acrobot_controller: AcrobotEnergyShapingController, tf=25.0, plot=True):
+    """The reference's demo (:123-160): 25 s of closed loop from x0 = [0.001, 0, 0, 0] — one rollout launch.
+    Returns (t, xs, us, energy)."""
+    t = np.arange(0, tf, acrobot.dt)
+    xs, us = closed_loop(acrobot, acrobot_controller, np.array([0.001, 0, 0, 0]), t)
+    e = np.array([acrobot.energy(x) for x in xs])
+    if plot:
+        try:
+            acrobot.plot_trajectory(t, xs)
+        except ImportError:
+            pass
+    return t, xs, us, e

@@ -7,7 +7,7 @@ constants of (cartpole, Q, R), so they are solved once here and live in the kern
 import numpy as np
 
 from q_learning_with_hjb_b200 import _lib as L
-from q_learning_with_hjb_b200.controller.controller_basic import DeviceController, lqr_gain
+from q_learning_with_hjb_b200.controller.controller_basic import DeviceController, closed_loop, lqr_gain, unclipped
 from q_learning_with_hjb_b200.dynamics.cartpole import Cartpole
 
 
@@ -51,3 +51,22 @@ class CartpoleEnergyShapingController(DeviceController):
         L.fill(c.xf, self.xf)
         L.fill(c.aux, [self.K[0], self.K[1], self.K[2], self.eps_energy, self.eps_state])
         return c
+
+    def get_energy_shaping_input(self, x):
+        """The energy-pumping branch alone, un-clipped (:97-110): the device law with the LQR catch region emptied."""
+        c = self.control_spec()
+        c.aux[3] = -1.0                                   # |dE| < eps_energy never holds
+        return self._efforts(unclipped(self.cartpole.system_spec()), c, x)
+
+
+def test_cartpole(cartpole: Cartpole, cartpole_controller: CartpoleEnergyShapingController, tf=10.0, plot=True):
+    """The reference's demo (:113-141): 10 s of closed loop from a random initial state, then the animation — the loop is
+    one rollout launch.  Returns (t, xs, us)."""
+    t = np.arange(0, tf, cartpole.dt)
+    xs, us = closed_loop(cartpole, cartpole_controller, cartpole.get_initial_state(), t)
+    if plot:
+        try:
+            cartpole.plot_trajectory(t, xs)
+        except ImportError:
+            pass
+    return t, xs, us

@@ -43,7 +43,7 @@ def quad10d_frame(x, arm=0.25):
 
 
 def animate(ts, xs, frame, xlim=None, ylim=None, zlim=None, three_d=False, trail=None):
-    """matplotlib FuncAnimation over the rows of ``xs`` (one frame per row, titled with ``ts``)."""
+    """matplotlib FuncAnimation over the rows of ``xs`` (one frame per row, titled with ``ts``) -> (anim, fig)."""
     try:
         import matplotlib.pyplot as plt
         from matplotlib.animation import FuncAnimation
@@ -71,7 +71,7 @@ def animate(ts, xs, frame, xlim=None, ylim=None, zlim=None, three_d=False, trail
 
     interval = 1000.0 * float(ts[1] - ts[0]) if len(ts) > 1 else 50.0
     anim = FuncAnimation(fig, draw, frames=len(ts), interval=interval, repeat=False)
-    return anim
+    return anim, fig          # the reference's plot_trajectory returns this pair
 
 
 def span(values, margin):

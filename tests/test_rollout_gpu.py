@@ -443,3 +443,36 @@ def test_staged_bulk_stores_equal_direct_stores(N):
         for a, b in zip(staged, direct):
             assert torch.equal(a, b)
     assert torch.isfinite(staged[0]).all()
+
+
+def test_energy_shaping_branch_methods_and_demo_loops():
+    """get_energy_shaping_input / get_swingup_input (the un-clipped pumping branches, reference:
+    cartpole_energy_shaping.py:97-110, acrobot_energy_shaping.py:74-98) against the oracle's branch, and the module-level
+    demo loops (the reference's test_cartpole / test_acrobot) as single rollout launches."""
+    import copy
+    _cuda()
+    from q_learning_with_hjb_b200.controller import acrobot_energy_shaping as AE, cartpole_energy_shaping as CE
+    for skind, ckind, method, never in (("cartpole", "cartpole_es", "get_energy_shaping_input", {"eps_energy": -1.0}),
+                                        ("acrobot", "acrobot_es", "get_swingup_input", {"eps": -1.0})):
+        dyn = make_dynamics(skind)
+        ctl = make_controller(ckind, dyn)
+        osys, octl = oracle_pair(skind, ckind)
+        osys, octl = copy.deepcopy(osys), copy.deepcopy(octl)
+        osys.umin, osys.umax = np.full(1, -np.inf), np.full(1, np.inf)
+        for k, v in never.items():
+            setattr(octl, k, v)
+        x = _x0(skind, 512).astype(np.float64)
+        x[:, 1] += np.linspace(-3, 3, 512)               # all over the circle, far beyond the clip limits
+        got = getattr(ctl, method)(x.astype(np.float32))
+        ref = octl.control(osys, x.astype(np.float32).astype(np.float64))
+        assert got.shape == ref.shape
+        assert np.abs(got - ref).max() <= 2e-5 * max(1.0, np.abs(ref).max())
+        assert np.abs(ref).max() > float(np.max(dyn.get_control_limit()[1]))     # really un-clipped
+        assert getattr(ctl, method)(x[0].astype(np.float32)).shape == (1,)
+    cp = make_dynamics("cartpole")
+    t, xs, us = CE.test_cartpole(cp, make_controller("cartpole_es", cp), tf=2.0, plot=False)
+    assert xs.shape == (len(t), 4) and us.shape == (len(t) - 1, 1) and np.isfinite(xs).all()
+    ac = make_dynamics("acrobot")
+    t, xs, us, e = AE.test_acrobot(ac, make_controller("acrobot_es", ac), tf=5.0, plot=False)
+    assert xs.shape == (len(t), 4) and e.shape == (len(t),) and np.isfinite(e).all()
+    np.testing.assert_allclose(xs[0], [0.001, 0, 0, 0], atol=1e-7)
