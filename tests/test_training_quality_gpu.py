@@ -46,3 +46,42 @@ def test_double_integrator_training_reproduces_the_notebook():
     assert t_opt.mean() < t_learned.mean() < 0.75 * t_lqr.mean()
     assert abs(t_learned.mean() / t_opt.mean() - NOTEBOOK_LEARNED_TIME / NOTEBOOK_ANALYTIC_TIME) < 0.45
     assert (t_learned < 15.0).mean() > 0.97            # (almost) every trajectory reaches the origin
+
+
+# examples/cartpole_balancing.ipynb cell 10 output, epochs 10..100: (loss, cumulated cost), all trajectories of length 200
+NOTEBOOK_CARTPOLE = [(0.17703275382518768, 9.412116827742574), (0.06387361139059067, 5.343564955591024),
+                     (0.0400521457195282, 5.933801207191339), (0.03183622658252716, 5.798194449711079),
+                     (0.024344438686966896, 8.910167146305296), (0.020757876336574554, 8.823061486922237),
+                     (0.01737324707210064, 4.941694227031621), (0.01516214944422245, 5.651786526654595),
+                     (0.01314554363489151, 7.476192060070356), (0.01217166893184185, 6.429701570859391)]
+NOTEBOOK_CARTPOLE_PD_COST = 9.140910175230598       # cell 16: "mean pd"
+NOTEBOOK_CARTPOLE_LQR_COST = 9.140986134043468      # cell 16: "mean lqr"
+
+
+def test_cartpole_balancing_training_reproduces_the_notebook():
+    """The notebook's "ours" run (tanh net, clipped control, normalised residual, data gathered by the current policy):
+    NumPy's global RNG is aligned with the notebook's, so every epoch rolls out from the notebook's own 20 initial states;
+    the loss curve and the rollout costs follow its printout and the trained policy reaches the LQR's closed-loop cost on
+    the notebook's ten evaluation states, as the reference's did (9.14091 against 9.14099)."""
+    import torch
+    assert torch.cuda.is_available()
+    sys.path.insert(0, os.path.join(ROOT, "examples"))
+    import cartpole_balancing as C
+    dyn, k = C.make_problem()
+    dyn.get_initial_state()                              # one draw precedes training in the notebook
+    params, history = C.train(dyn, k, epochs=100, log=None)
+    ours = np.array(history[9::10])
+    ref = np.array(NOTEBOOK_CARTPOLE)
+    ratio = ours[:, 0] / ref[:, 0]
+    assert (ratio > 0.5).all() and (ratio < 1.8).all(), ratio
+    assert abs(np.exp(np.log(ratio).mean()) - 1.0) < 0.3, ratio
+    assert ours[-1, 0] < 0.02
+    # rollouts start from the notebook's initial states: once the policy is near-optimal (epoch 50 on) their mean cost is
+    # the notebook's to within a few percent at most readings, and always in its range
+    assert (np.array(history)[:, 1] > 3.5).all() and (np.array(history)[10:, 1] < 12).all()
+    close = np.abs(ours[4:, 1] / ref[4:, 1] - 1.0) < 0.05
+    assert close.sum() >= 3, (ours[:, 1], ref[:, 1])
+    assert (np.array(history)[9:, 2] == 200).all()       # no trajectory leaves the observation box from epoch 10 on
+    pd, lqr = C.evaluate(dyn, k, params)
+    assert abs(lqr.mean() - NOTEBOOK_CARTPOLE_LQR_COST) < 2e-4 * NOTEBOOK_CARTPOLE_LQR_COST     # THE ten states (fp32 loop)
+    assert abs(pd.mean() - NOTEBOOK_CARTPOLE_PD_COST) < 5e-3 * NOTEBOOK_CARTPOLE_PD_COST
