@@ -19,146 +19,55 @@ import time
 import numpy as np
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+
+import onpolicy_hjb as H  # noqa: E402  (examples/ is on sys.path when run as a script or from the tests)
 
 XF = np.array([0, 3.1415926, 0, 0])
-OBS_MIN = np.array([-4.8, -0.418, -1000, -1000])
-OBS_MAX = np.array([4.8, 0.418, 1000, 1000])
-ROLLOUT_STEPS, TRAJ_PER_EPOCH, BATCH = 200, 20, 256
 
 
 def make_problem():
     from q_learning_with_hjb_b200.configs import gin_compat as gin
     from q_learning_with_hjb_b200.configs.dynamics.dynamics_config import CartpoleDynamicsConfig
-    from q_learning_with_hjb_b200.controller.vhjb import VhjbKernels
     from q_learning_with_hjb_b200.dynamics.cartpole import Cartpole
     import q_learning_with_hjb_b200 as pkg
     gin.parse_config_file(os.path.join(os.path.dirname(pkg.__file__), "configs", "dynamics", "cartpole.gin"))
     dyn = Cartpole(CartpoleDynamicsConfig())          # seeds NumPy's global RNG with 0 like the reference
-    k = VhjbKernels(dyn, XF, np.zeros(1), np.eye(4), np.eye(1), np.zeros(4), np.ones(4), 1e-10, 1e-3, act="tanh")
-    return dyn, k
+    p = H.Problem(dyn, XF, np.zeros(1), np.array([-4.8, -0.418, -1000, -1000]), np.array([4.8, 0.418, 1000, 1000]), act="tanh")
+    return p, p.kernels()
 
 
-class Policy:
-    """u(x) of the value net, batched on the device."""
-
-    def __init__(self, k, params):
-        import torch
-        self.k, self.params, self.torch = k, params, torch
-
-    def __call__(self, x):
-        z = self.torch.zeros(x.shape[0], device="cuda")
-        out, _ = self.k.residual(self.params, x, z, z, want=("u",))
-        return out["u"]
+def train(p, k, epochs=100, log=print):
+    return H.train(p, k, epochs, log=log)
 
 
-def running_cost(dyn, x, u):
-    """l(x, u) = z^T z + u^T u (Q = I, R = I, uf = 0), z = wrap(x - xf); device tensors."""
-    import torch
-    z = x - torch.as_tensor(XF, dtype=torch.float32, device="cuda")
-    z = torch.cat([z[:, :1], torch.remainder(z[:, 1:2] + np.pi, 2 * np.pi) - np.pi, z[:, 2:]], dim=1)
-    return (z * z).sum(1) + (u * u).sum(1), z
-
-
-def rollout(dyn, policy, x0, steps):
-    """The notebook's rollout_trajectory (cell 9) for all rows of x0 at once: states are collected while the trajectory has
-    not left the observation box; cumulated_cost += dt l(x_next, u) over ALL steps.  Returns (states [K, 4], costs [N],
-    lengths [N])."""
-    import torch
-    lo = torch.as_tensor(OBS_MIN, dtype=torch.float32, device="cuda")
-    hi = torch.as_tensor(OBS_MAX, dtype=torch.float32, device="cuda")
-    x = torch.as_tensor(np.asarray(x0, dtype=np.float32)).cuda()
-    within = torch.ones(x.shape[0], dtype=torch.bool, device="cuda")
-    cost = torch.zeros(x.shape[0], device="cuda")
-    kept, masks = [], []
-    for _ in range(steps):
-        _, z = running_cost(dyn, x, torch.zeros((x.shape[0], 1), device="cuda"))
-        within = within & ~(((z > hi) | (z < lo)).any(dim=1))
-        kept.append(x)
-        masks.append(within)
-        u = policy(x)
-        x = dyn.simulate(x, u)
-        cost = cost + dyn.dt * running_cost(dyn, x, u)[0]
-    states = torch.stack(kept, dim=1)                    # [N, T, 4]: trajectory by trajectory like dataset.xs.extend
-    mask = torch.stack(masks, dim=1)
-    return states[mask], cost, mask.sum(1)
-
-
-def closed_loop_cost(dyn, policy, x0, steps):
-    """test_learned_policy (cell 15): sum_t l(x_t, u_t) dt."""
-    import torch
-    x = torch.as_tensor(np.asarray(x0, dtype=np.float32)).cuda()
-    cost = torch.zeros(x.shape[0], device="cuda")
-    for _ in range(steps):
-        u = policy(x)
-        cost = cost + dyn.dt * running_cost(dyn, x, u)[0]
-        x = dyn.simulate(x, u)
-    return cost.cpu().numpy().astype(np.float64)
-
-
-def train(dyn, k, epochs=100, seed=0, log=print):
-    import torch
-    from q_learning_with_hjb_b200.controller.vhjb import AdamState, DeviceReplayBuffer, FEATURES, lecun_normal
-    rng = np.random.default_rng(seed)
-    torch.manual_seed(seed)
-    dims = [4, *FEATURES]
-    params = torch.as_tensor(np.concatenate([lecun_normal(rng, dims[i], dims[i + 1]).reshape(-1) for i in range(3)])).cuda()
-    opt = AdamState(0, torch.zeros_like(params), torch.zeros_like(params))
-    policy = Policy(k, params)
-    data = DeviceReplayBuffer(4, BATCH + epochs * TRAJ_PER_EPOCH * ROLLOUT_STEPS)
-    data.extend(np.tile(XF, (BATCH, 1)), np.ones(BATCH), np.zeros(BATCH))       # dataset = [xf] * 256 (cell 10)
-    history = []
-    for epoch in range(epochs):
-        x0 = np.stack([dyn.get_initial_state() for _ in range(TRAJ_PER_EPOCH)])
-        states, costs, lengths = rollout(dyn, policy, x0, ROLLOUT_STEPS)
-        if states.shape[0]:
-            data.extend(states, torch.ones(states.shape[0], device="cuda"), torch.zeros(states.shape[0], device="cuda"))
-        total, nb = torch.zeros((), device="cuda"), 0
-        for xs, cs, ds in data.batches(BATCH):
-            sums, norm = k.train_step(params, opt, xs, ds, cs, 0.0, 1e-3)
-            total += sums[0] / norm[0]
-            nb += 1
-        history.append((float(total) / nb, float(costs.mean()), float(lengths.float().mean())))
-        if log and (epoch + 1) % 10 == 0:
-            log(f"epoch:{epoch + 1} loss:{history[-1][0]:.5f}, cumulated cost:{history[-1][1]:.3f}, "
-                f"avg trajectory length: {history[-1][2]:.1f}")
-    return params, history
-
-
-def lqr_policy(dyn):
-    import torch
+def evaluate(p, k, params, notebook_draws=4000):
+    """Cell 16: closed-loop cost over 10 s from ten initial states, learned policy and LQR.  The notebook trains two more
+    nets (2 x 100 epochs x 20 initial states) between cell 10 and cell 16; the same number of draws is skipped here so
+    that the ten states are THE ten of the notebook (its LQR line reads 9.140986134043468)."""
     from q_learning_with_hjb_b200.controller.cartpole_energy_shaping import CartpoleEnergyShapingController
-    K, _ = CartpoleEnergyShapingController(dyn).get_lqr_term()
-    Kt = torch.as_tensor(K, dtype=torch.float32, device="cuda")
-
-    def policy(x):
-        _, z = running_cost(dyn, x, torch.zeros((x.shape[0], 1), device="cuda"))
-        return -(z @ Kt.T)                               # un-clipped like get_lqr_control (cell 4); simulate clips
-    return policy
+    dyn = p.dyn
+    for _ in range(notebook_draws):
+        dyn.get_initial_state()
+    x0 = np.stack([dyn.get_initial_state() for _ in range(10)])
+    steps = int(round(10 / dyn.dt))
+    K, _ = CartpoleEnergyShapingController(dyn).get_lqr_term()     # the upright linearisation + Riccati of cell 4
+    return (H.closed_loop_cost(p, H.Policy(k, params), x0, steps),
+            H.closed_loop_cost(p, H.lqr_policy(p, K), x0, steps))
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--epochs", type=int, default=100)
     args = ap.parse_args()
-    dyn, k = make_problem()
-    dyn.get_initial_state()                              # the notebook draws one initial state before training
+    p, k = make_problem()
+    p.dyn.get_initial_state()                            # the notebook draws one initial state before training
     t0 = time.time()
-    params, history = train(dyn, k, args.epochs)
+    params, history = train(p, k, args.epochs)
     print(f"trained {args.epochs} epochs in {time.time() - t0:.1f} s")
-    pd, lqr = evaluate(dyn, k, params)
+    pd, lqr = evaluate(p, k, params)
     print("mean pd: ", pd.mean())
     print("mean lqr: ", lqr.mean())
-
-
-def evaluate(dyn, k, params, notebook_draws=4000):
-    """Cell 16: closed-loop cost over 10 s from ten initial states, learned policy and LQR.  The notebook trains two more
-    nets (2 x 100 epochs x 20 initial states) between cell 10 and cell 16; the same number of draws is skipped here so
-    that the ten states are THE ten of the notebook (its LQR line reads 9.140986134043468)."""
-    for _ in range(notebook_draws):
-        dyn.get_initial_state()
-    x0 = np.stack([dyn.get_initial_state() for _ in range(10)])
-    steps = int(round(10 / dyn.dt))
-    return closed_loop_cost(dyn, Policy(k, params), x0, steps), closed_loop_cost(dyn, lqr_policy(dyn), x0, steps)
 
 
 if __name__ == "__main__":

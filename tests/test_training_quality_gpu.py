@@ -67,9 +67,9 @@ def test_cartpole_balancing_training_reproduces_the_notebook():
     assert torch.cuda.is_available()
     sys.path.insert(0, os.path.join(ROOT, "examples"))
     import cartpole_balancing as C
-    dyn, k = C.make_problem()
-    dyn.get_initial_state()                              # one draw precedes training in the notebook
-    params, history = C.train(dyn, k, epochs=100, log=None)
+    p, k = C.make_problem()
+    p.dyn.get_initial_state()                            # one draw precedes training in the notebook
+    params, history = C.train(p, k, epochs=100, log=None)
     ours = np.array(history[9::10])
     ref = np.array(NOTEBOOK_CARTPOLE)
     ratio = ours[:, 0] / ref[:, 0]
@@ -82,6 +82,44 @@ def test_cartpole_balancing_training_reproduces_the_notebook():
     close = np.abs(ours[4:, 1] / ref[4:, 1] - 1.0) < 0.05
     assert close.sum() >= 3, (ours[:, 1], ref[:, 1])
     assert (np.array(history)[9:, 2] == 200).all()       # no trajectory leaves the observation box from epoch 10 on
-    pd, lqr = C.evaluate(dyn, k, params)
+    pd, lqr = C.evaluate(p, k, params)
     assert abs(lqr.mean() - NOTEBOOK_CARTPOLE_LQR_COST) < 2e-4 * NOTEBOOK_CARTPOLE_LQR_COST     # THE ten states (fp32 loop)
     assert abs(pd.mean() - NOTEBOOK_CARTPOLE_PD_COST) < 5e-3 * NOTEBOOK_CARTPOLE_PD_COST
+
+
+# examples/10D_quadcopte.ipynb cell 10 output: loss at epochs 10, 20, ..., 190 (relu net: the tcgen05 kernels' home case)
+NOTEBOOK_QUAD10D_LOSS = [0.838606595993042, 0.41695377230644226, 0.2863415479660034, 0.21997720003128052, 0.18350590765476227,
+                         0.1576915830373764, 0.13448160886764526, 0.106891930103302, 0.06911955773830414, 0.05488620325922966,
+                         0.04754112660884857, 0.042472753673791885, 0.03934410214424133, 0.035824619233608246,
+                         0.03234047442674637, 0.02830219268798828, 0.023855412378907204, 0.02061299793422222,
+                         0.018832053989171982]
+NOTEBOOK_QUAD10D_LENGTH = [2.3, 14.4, 13.35, 15.5, 16.65, 15.7, 16.2, 13.75, 11.9, 10.55, 11.7, 15.35, 15.4, 16.2, 33.25, 65.0,
+                           114.9, 147.0]
+NOTEBOOK_QUAD10D_LEARNED_COST = 51.124755724297565   # cell 14
+NOTEBOOK_QUAD10D_LQR_COST = 9.085334056081662        # cell 14
+
+
+def test_quadcopter_10d_training_reproduces_the_notebook():
+    """The 10-D quadcopter notebook's "ours" run (relu net — BASELINE C5's kernel — with on-policy data): the loss follows
+    the printed curve (the first readings, before the data depends much on the policy, within 10 %), the policy goes
+    through the same phases (a handful of in-box states per trajectory for ~100 epochs, then most of the 200 steps), and
+    the evaluation state is the notebook's (NumPy's RNG is aligned): its LQR cost reads 9.08533."""
+    import torch
+    assert torch.cuda.is_available()
+    sys.path.insert(0, os.path.join(ROOT, "examples"))
+    import onpolicy_hjb as H
+    import quadcopter_10d as Q
+    p, k = Q.make_problem()
+    params, history = H.train(p, k, epochs=200, log=None)
+    h = np.array(history)
+    ours = h[9:190:10, 0]
+    ref = np.array(NOTEBOOK_QUAD10D_LOSS)
+    ratio = ours / ref
+    assert (ratio > 0.4).all() and (ratio < 1.6).all(), ratio
+    assert (np.abs(ratio[:4] - 1.0) < 0.12).all(), ratio[:4]
+    assert h[-1, 0] < 0.03 and (np.diff(ours) < 0).all()
+    assert h[9, 2] < 5 and 8 < h[9:90, 2].mean() < 30            # notebook: 2.3, then 10-17 states per trajectory
+    assert h[-10:, 2].mean() > 100                                  # notebook: 115, 147 at epochs 170, 180
+    learned, lqr = Q.evaluate(p, k, params)
+    assert abs(lqr - NOTEBOOK_QUAD10D_LQR_COST) < 1e-5 * NOTEBOOK_QUAD10D_LQR_COST
+    assert lqr < learned < 3 * NOTEBOOK_QUAD10D_LEARNED_COST
