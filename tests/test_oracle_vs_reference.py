@@ -106,3 +106,48 @@ def test_closed_loop_trajectory_matches_reference(skind, ckind, steps):
         tol = 1e-6 if skind == "acrobot" else 1e-9
         np.testing.assert_allclose(xs[:, e], xr, rtol=tol, atol=tol)
         np.testing.assert_allclose(us[:, e], ur, rtol=tol * 100, atol=tol * 100)
+
+
+def test_config_classes_and_gin_files_bind_like_the_reference():
+    """Drop-in boundary: every config class has the reference's fields in the reference's order, and every
+    .gin file of this repo binds exactly the values the reference's file of the same name binds."""
+    import ast
+    import dataclasses
+    import os
+    import re
+    from q_learning_with_hjb_b200.configs.controller import vhjb_controller_config as CC
+    from q_learning_with_hjb_b200.configs.dynamics import dynamics_config as DC
+    ref = "/root/reference/configs"
+    pkg = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "q_learning_with_hjb_b200", "configs")
+
+    def ref_fields(path):            # {class: [field, ...]} from the reference's dataclass source (annotated assignments)
+        out, tree = {}, ast.parse(open(path).read())
+        for node in tree.body:
+            if isinstance(node, ast.ClassDef):
+                out[node.name] = ([b.id for b in node.bases if isinstance(b, ast.Name)],
+                                  [s.target.id for s in node.body if isinstance(s, ast.AnnAssign)])
+        return out
+
+    for mod, path in ((DC, f"{ref}/dynamics/dynamics_config.py"), (CC, f"{ref}/controller/vhjb_controller_config.py")):
+        classes = ref_fields(path)
+        for name, (bases, own) in classes.items():
+            inherited = [f for b in bases for f in classes.get(b, ([], []))[1]]
+            ours = [f.name for f in dataclasses.fields(getattr(mod, name))]
+            assert ours == inherited + own, name
+
+    def bindings(path):
+        out = {}
+        for raw in open(path):
+            line = raw.split("#", 1)[0].strip()
+            if line:
+                k, v = line.split("=", 1)
+                out[k.strip()] = ast.literal_eval(v.strip())
+        return out
+
+    checked = 0
+    for sub in ("dynamics", "controller"):
+        for f in sorted(os.listdir(f"{ref}/{sub}")):
+            if f.endswith(".gin"):
+                assert bindings(os.path.join(pkg, sub, f)) == bindings(f"{ref}/{sub}/{f}"), f
+                checked += 1
+    assert checked == 7
