@@ -445,3 +445,24 @@ def test_device_replay_buffer_has_deque_semantics():
         assert xs.shape == (8, n) and cs.shape == (8,) and ds.shape == (8,)
         seen += [tuple(np.concatenate([x, [c, d]]).tolist()) for x, c, d in zip(xs.cpu().numpy(), cs.cpu().numpy(), ds.cpu().numpy())]
     assert len(seen) == (cap // 8) * 8 and len(set(seen)) == len(seen) and set(seen) <= rows
+
+
+@pytest.mark.parametrize("name", ["quad10d", "cartpole_tanh", "di_mintime"])
+def test_tiny_ragged_and_empty_batches(name):
+    """Edge cases of the batch dimension on the tensor path: one state, one short of / one over a 64-state tile, fewer
+    tiles than SMs, and the empty batch (loss sums and gradient are zeros, nothing is read)."""
+    torch, k, p, orc, params, xs, dones, costs = _setup(name, 200, seed=17, wseed=6)
+    for B in (1, 63, 65, 129):
+        xd, dd, cd = _dev(torch, xs[:B], dones[:B], costs[:B])
+        out, sums = k.residual(params, xd, dd, cd)
+        q = orc.pieces(xs[:B], running=costs[:B] if p.residual_form == "min_time" else None)
+        np.testing.assert_allclose(out["V"].cpu().numpy(), q["V"].detach().numpy(), rtol=2e-5, atol=1e-6)
+        k.norm.copy_(torch.tensor([float(B), 1.0]))
+        k.loss_grad(params, xd, dd, cd, 0.0)
+        assert torch.isfinite(k.grad).all() and torch.isfinite(k.sums).all()
+    empty = torch.empty((0, p.sys.n), device="cuda"), torch.empty(0, device="cuda"), torch.empty(0, device="cuda")
+    out, sums = k.residual(params, *empty)
+    assert out["V"].shape == (0,) and float(sums.abs().sum()) == 0.0
+    k.norm.copy_(torch.tensor([1.0, 1.0]))
+    grad, sums = k.loss_grad(params, *empty, 0.0)
+    assert float(grad.abs().sum()) == 0.0 and float(sums.abs().sum()) == 0.0
