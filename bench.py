@@ -175,7 +175,11 @@ def run_reference_arm(args, w, integ, rank, world):
         "impl": "reference", "metric": "closed-loop env-steps/s", "value": value, "unit": "env-steps/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_all / max(1, args.steps),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": w["label"], "integrator": integ, "sample": sample},
+        # the b200 arm's config keys (same workload), plus what the bounded sample of one step was
+        "config": {"workload": w["label"], "envs_per_gpu": args.envs or w["envs"], "horizon": T, "integrator": integ,
+                   "record": "final state + per-env cost" if args.record_stride == 0 else f"every {args.record_stride} steps",
+                   "trig": "libm (NumPy fp64)", "parallelism": f"{cores} host processes", "seed": "1234 + rank",
+                   "sample": sample},
         "cpu_baseline": {"value": value, "unit": "env-steps/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
