@@ -235,6 +235,19 @@ int hjb_vhjb_loss_grad_accumulate(const hjb_system* sys, const hjb_vnet* net, co
                                   float* grad, float* sums, void* workspace, void* stream);
 
 /*
+ * One whole single-GPU training step (VHJBController.params_update, controller/vhjb.py:255-288) in one call and three
+ * launches: the normalisers (hjb_vhjb_count with this task's eps; MIN_TIME: {B, 1}), the fused loss + gradient kernel, and
+ * one kernel that reduces the per-CTA partials in the same fixed order as hjb_vhjb_loss_grad and applies the optax.adam
+ * update to net->params in place (step = 1-based update index).  Bit-identical to hjb_vhjb_count + hjb_vhjb_loss_grad +
+ * hjb_adam; exists because the reference trains with minibatches of 256, where seven launches and as many host
+ * round trips cost more than the arithmetic.  Multi-GPU callers keep the separate entry points (the all-reduce sits between
+ * the gradient and Adam).  grad, sums, norm, the saturation count: as for hjb_vhjb_loss_grad.
+ */
+int hjb_vhjb_train_step(const hjb_system* sys, const hjb_vnet* net, const hjb_task* task, const float* xs, const float* dones,
+                        const float* costs, int64_t B, float reg, float lr, float b1, float b2, float adam_eps, int32_t step,
+                        float* m, float* v, float* norm, float* grad, float* sums, void* workspace, void* stream);
+
+/*
  * Range check of the last hjb_vhjb_loss_grad on this workspace (device float `count`, stream-ordered).  The
  * tensor-core gradient pass carries per-state adjoints in fp16 with per-state power-of-two scaling (vhjb_tc.cuh);
  * a state whose adjoint seed exceeds 2^26 times the batch-typical weight (only |x - xf| and |u - uf| ~ 1e-4 and

@@ -60,6 +60,52 @@ __global__ void count_stage2(const float* __restrict__ part, int nblk, int64_t B
   }
 }
 
+// Small batches (the reference trains with minibatches of 256): one block counts, adds eps and writes norm — one
+// launch instead of two.  Done flags are 0 / 1, so the float sums are exact integers whatever the order.
+__global__ void __launch_bounds__(1024) count_one_block(const float* __restrict__ dones, int64_t B, float eps0, float eps1,
+                                                        int min_time, float* __restrict__ norm) {
+  float s1 = 0.f;
+  for (int64_t i = threadIdx.x; i < B; i += blockDim.x) s1 += __ldg(dones + i);
+  __shared__ float sh[32];
+#pragma unroll
+  for (int s = 16; s > 0; s >>= 1) s1 += __shfl_xor_sync(0xffffffffu, s1, s);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s1;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += (double)sh[w];
+    norm[0] = (float)((double)B - t + (double)eps0);
+    norm[1] = min_time ? 1.0f : (float)(t + (double)eps1);
+  }
+}
+
+// grad[j] = sum over CTAs (same fixed order as vhjb_reduce_kernel) followed by the optax.adam update of element j; the
+// thread that owns j = 0 also reduces the loss sums and the saturation count.  One launch instead of four.
+__global__ void __launch_bounds__(256) vhjb_reduce_adam_kernel(const float* __restrict__ partial, int64_t pstride, int ncta, int P,
+                                                               float* __restrict__ grad, float* __restrict__ sums,
+                                                               float* __restrict__ sat, float* __restrict__ w,
+                                                               float* __restrict__ m, float* __restrict__ v, float lr, float b1,
+                                                               float b2, float eps, float bc1, float bc2) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < P) {
+    float g = 0.f;
+    for (int c = 0; c < ncta; ++c) g += partial[(int64_t)c * pstride + j];
+    grad[j] = g;
+    const float mi = fmaf(b1, m[j], (1.f - b1) * g);
+    const float vi = fmaf(b2, v[j], (1.f - b2) * g * g);
+    m[j] = mi;
+    v[j] = vi;
+    const float mhat = mi / bc1, vhat = vi / bc2;
+    w[j] = w[j] - lr * mhat / (sqrtf(vhat) + eps);
+  }
+  if (j < 3) {
+    float t = 0.f;
+    for (int c = 0; c < ncta; ++c) t += partial[(int64_t)c * pstride + P + j];
+    if (j < 2) sums[j] = t;
+    else *sat = t;
+  }
+}
+
 // ---- optax.adam ----
 __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ w, float* __restrict__ m, float* __restrict__ v,
                                                    const float* __restrict__ g, int64_t len, float lr, float b1, float b2,
@@ -85,9 +131,15 @@ static int sm_count() {
   return cached > 0 ? (cached < kMaxCtas ? cached : kMaxCtas) : 148;
 }
 
+struct AdamTail {   // when set, run_vhjb ends with vhjb_reduce_adam_kernel instead of the three reductions
+  float *w, *m, *v;
+  float lr, b1, b2, eps, bc1, bc2;
+};
+
 static int run_vhjb(const hjb_system* sys, const hjb_vnet* net, const hjb_task* task, const float* xs, const float* dones,
                     const float* costs, int64_t B, const float* norm, float reg, float* V, float* p, float* u, float* r,
-                    float* grad, float* sums, void* workspace, bool want_grad, bool accumulate, cudaStream_t st) {
+                    float* grad, float* sums, void* workspace, bool want_grad, bool accumulate, cudaStream_t st,
+                    const AdamTail* tail = nullptr) {
   if (!sys || !net || !task || B < 0) return HJB_ERR_BAD_ARG;
   if (net->n != sys->n || net->features[0] != VH1 || net->features[1] != VH2 || net->features[2] != VH3)
     return HJB_ERR_UNSUPPORTED;
@@ -175,6 +227,13 @@ static int run_vhjb(const hjb_system* sys, const hjb_vnet* net, const hjb_task* 
     std::fprintf(stderr, "\n");
   }
   const int P = vhjb_param_count(n);
+  if (tail) {
+    vhjb_reduce_adam_kernel<<<(P + 255) / 256, 256, 0, st>>>(a.partial, a.pstride, l.grid, P, grad, sums,
+                                                             a.partial + (int64_t)kMaxCtas * a.pstride, tail->w, tail->m, tail->v,
+                                                             tail->lr, tail->b1, tail->b2, tail->eps, tail->bc1, tail->bc2);
+    e = cudaGetLastError();
+    return e == cudaSuccess ? HJB_OK : (int)e;
+  }
   if (want_grad) {
     vhjb_reduce_kernel<<<(P + 255) / 256, 256, 0, st>>>(a.partial, a.pstride, l.grid, 0, P, grad, (int)accumulate);
     e = cudaGetLastError();
@@ -243,6 +302,39 @@ int hjb_vhjb_loss_grad_accumulate(const hjb_system* sys, const hjb_vnet* net, co
                                   float* grad, float* sums, void* workspace, void* stream) {
   return run_vhjb(sys, net, task, xs, dones, costs, B, norm, reg, nullptr, nullptr, nullptr, nullptr, grad, sums, workspace,
                   true, true, (cudaStream_t)stream);
+}
+
+int hjb_vhjb_train_step(const hjb_system* sys, const hjb_vnet* net, const hjb_task* task, const float* xs, const float* dones,
+                        const float* costs, int64_t B, float reg, float lr, float b1, float b2, float adam_eps, int32_t step,
+                        float* m, float* v, float* norm, float* grad, float* sums, void* workspace, void* stream) {
+  if (!sys || !net || !task || !net->params || !m || !v || !norm || !grad || !sums || !workspace || B <= 0 || step < 1)
+    return HJB_ERR_BAD_ARG;
+  if (!xs || !dones || !costs) return HJB_ERR_BAD_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int min_time = task->residual_form == HJB_RES_MIN_TIME;
+  if (B <= (int64_t)1 << 18) {
+    count_one_block<<<1, 1024, 0, st>>>(dones, B, min_time ? 0.f : task->eps, task->eps, min_time, norm);
+  } else {
+    const int nblk = sm_count();
+    float* part = static_cast<float*>(workspace);
+    count_stage1<<<nblk, 256, 0, st>>>(dones, B, part);
+    count_stage2<<<1, 32, 0, st>>>(part, nblk, B, min_time ? 0.f : task->eps, norm);
+    if (min_time) {
+      const float one = 1.0f;   // plain mean over the batch: no boundary term (double_integrator notebook, cell 11)
+      cudaMemcpyAsync(norm + 1, &one, sizeof(float), cudaMemcpyHostToDevice, st);
+    }
+  }
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return (int)e;
+  AdamTail tail;
+  tail.w = const_cast<float*>(net->params);
+  tail.m = m;
+  tail.v = v;
+  tail.lr = lr; tail.b1 = b1; tail.b2 = b2; tail.eps = adam_eps;
+  tail.bc1 = (float)(1.0 - std::pow((double)b1, (double)step));
+  tail.bc2 = (float)(1.0 - std::pow((double)b2, (double)step));
+  return run_vhjb(sys, net, task, xs, dones, costs, B, norm, reg, nullptr, nullptr, nullptr, nullptr, grad, sums, workspace, true,
+                  false, st, &tail);
 }
 
 int hjb_adam(float* params, float* m, float* v, const float* grad, int64_t len, float lr, float b1, float b2, float eps,

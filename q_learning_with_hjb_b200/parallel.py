@@ -18,6 +18,11 @@ def dist_info() -> Tuple[int, int]:
     return 0, 1
 
 
+def is_distributed() -> bool:
+    """True when a default process group with more than one rank is initialised."""
+    return dist_info()[1] > 1
+
+
 def shard_bounds(total: int, rank: int, world: int) -> Tuple[int, int]:
     """Contiguous [lo, hi) slice of ``total`` items owned by ``rank`` — sizes differ by at most one."""
     if not (0 <= rank < world):

@@ -466,3 +466,38 @@ def test_tiny_ragged_and_empty_batches(name):
     k.norm.copy_(torch.tensor([1.0, 1.0]))
     grad, sums = k.loss_grad(params, *empty, 0.0)
     assert float(grad.abs().sum()) == 0.0 and float(sums.abs().sum()) == 0.0
+
+
+@pytest.mark.parametrize("name,B", [("quad10d", 256), ("di_mintime", 256), ("cartpole_tanh", 4096 + 7), ("quad10d", (1 << 18) + 100)])
+def test_single_call_train_step_is_bit_identical_to_the_separate_entry_points(name, B):
+    """hjb_vhjb_train_step (count + fused loss/gradient + reduce-and-Adam: one call, three launches — the small-batch path of
+    VhjbKernels.train_step) against hjb_vhjb_count + hjb_vhjb_loss_grad + hjb_adam, three consecutive updates."""
+    from q_learning_with_hjb_b200 import parallel
+    from q_learning_with_hjb_b200.controller.vhjb import AdamState
+    torch, k, p, orc, params, xs, dones, costs = _setup(name, B, seed=23, wseed=7)
+    xd, dd, cd = _dev(torch, xs, dones, costs)
+
+    def separate(w, opt, reg):
+        k.counts(dd, 0.0)
+        if p.residual_form == "min_time":
+            k.norm[1] = 1.0
+        else:
+            k.norm.add_(p.eps)
+        k.loss_grad(w, xd, dd, cd, reg)
+        opt.count += 1
+        k.adam(w, opt.mu, opt.nu, k.grad, opt.count, 1e-3)
+
+    results = []
+    for fused in (False, True):
+        w = params.clone()
+        opt = AdamState(0, torch.zeros_like(w), torch.zeros_like(w))
+        for i in range(3):
+            if fused:
+                assert not parallel.is_distributed()
+                k.train_step(w, opt, xd, dd, cd, 0.1 * i, 1e-3)
+            else:
+                separate(w, opt, 0.1 * i)
+        results.append((w.clone(), opt.mu.clone(), opt.nu.clone(), k.grad.clone(), k.sums.clone(), k.norm.clone()))
+    for a, b in zip(*results):
+        assert torch.equal(a, b)
+    assert not torch.equal(results[0][0], params)
