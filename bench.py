@@ -489,7 +489,9 @@ def measure_vhjb(w, steps, warmup, rank, world, local, want_cpu):
         "residual_only_states_per_s": res_rate,
         "e2e": {"value": e2e_rate, "unit": "states/s", "h2d_bytes_per_step": int(sum(h.numel() * 4 for h in host)),
                 "d2h_bytes_per_step": 16, "ms_per_step": e2e_ms / steps},
-        "gpu_launches": steps * 7,   # count x2, fused pass, reduce x3, adam
+        # single process: count x2, fused pass, reduce-and-Adam (hjb_vhjb_train_step); multi-GPU: count x2, fused pass,
+        # reduce x3, Adam (the two NCCL all-reduces are not counted)
+        "gpu_launches": steps * (4 if world == 1 else 7),
         "kernel_ms": grad_ms / steps,
         "clocks": clk,
     }
