@@ -270,6 +270,18 @@ int hjb_policy_step(const hjb_system* sys, const hjb_task* task, const float* xf
                     float* rec_cost, float* rec_done, int64_t N, void* stream);
 
 /*
+ * The whole learned-policy rollout of N trajectories (VHJBController.rollout_trajectory, controller/vhjb.py:171-193, for all
+ * of an epoch's trajectories at once) in ONE call: T + 1 rounds of hjb_vhjb_residual (-> u, skipped in the closing round)
+ * and hjb_policy_step, 2 T + 1 launches queued on the stream without returning to the caller.  x [N, n] in / out,
+ * u [N, m] scratch, zeros / ones [N] (the dones / costs the residual entry point wants), alive [N] = 1 and total_cost [N] = 0
+ * on entry; rec_x [T + 1, N, n], rec_cost / rec_done [T + 1, N] receive every time slice (rec_done = -1: no sample).
+ */
+int hjb_policy_rollout(const hjb_system* sys, const hjb_vnet* net, const hjb_task* task, const float* xf, const float* obs_lo,
+                       const float* obs_hi, const float* P, int32_t T, float* x, float* u, const float* zeros, const float* ones,
+                       float* alive, float* total_cost, float* rec_x, float* rec_cost, float* rec_done, int64_t N,
+                       void* workspace, void* stream);
+
+/*
  * Device-resident replay buffer (second half of SURVEY.md 8f row 1).  The reference keeps (state, cost, done) samples in
  * a deque(maxlen) behind a torch Dataset / shuffling DataLoader (controller/vhjb.py:62-73, :153-154) and extends it
  * trajectory by trajectory (:299-305).  Here the samples are a ring of `capacity` rows in HBM (buf_x [capacity, n],

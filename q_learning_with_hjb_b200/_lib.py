@@ -93,6 +93,9 @@ SYMBOLS = {
     "hjb_policy_step": (C.c_int, [C.POINTER(HjbSystem), C.POINTER(HjbTask), C.POINTER(C.c_float), C.POINTER(C.c_float),
                                   C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_int32, _P, _P, _P, _P, _P, _P, _P,
                                   C.c_int64, _P]),
+    "hjb_policy_rollout": (C.c_int, [C.POINTER(HjbSystem), C.POINTER(HjbVnet), C.POINTER(HjbTask), C.POINTER(C.c_float),
+                                     C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_int32, _P, _P, _P, _P,
+                                     _P, _P, _P, _P, _P, C.c_int64, _P, _P]),
     "hjb_replay_append": (C.c_int, [_P, _P, _P, _P, C.c_int64, C.c_int64, C.c_int32, C.c_int64, C.c_int64, C.c_int64, _P, _P,
                                     _P, _P]),
     "hjb_replay_gather": (C.c_int, [_P, _P, _P, _P, C.c_int64, C.c_int32, _P, _P, _P, _P]),

@@ -383,25 +383,21 @@ class VHJBController(Controller):
         alive = torch.ones(N, device="cuda", dtype=torch.float32)
         total = torch.zeros(N, device="cuda", dtype=torch.float32)
         rec_x = torch.empty((T + 1, N, n), device="cuda", dtype=torch.float32)
-        rec_c = torch.zeros((T + 1, N), device="cuda", dtype=torch.float32)
-        rec_d = torch.full((T + 1, N), -1.0, device="cuda", dtype=torch.float32)
-        u_dummy = torch.zeros((N, self.control_dim), device="cuda", dtype=torch.float32)
+        rec_c = torch.empty((T + 1, N), device="cuda", dtype=torch.float32)
+        rec_d = torch.empty((T + 1, N), device="cuda", dtype=torch.float32)
+        u = torch.zeros((N, self.control_dim), device="cuda", dtype=torch.float32)
+        zeros, ones = torch.zeros(N, device="cuda"), torch.ones(N, device="cuda")
         xf = L.c_floats(self.xf, n)
         lo = L.c_floats(self.obs_min, n)
         hi = L.c_floats(self.obs_max, n)
         P = L.c_floats(np.asarray(self.P, dtype=np.float64).reshape(-1), n * n)
-        for i in range(T + 1):
-            terminal = i == T
-            if terminal:
-                u = u_dummy                                           # vhjb.py:188-191: close what is still running
-            else:
-                out, _ = self._residual(self.model_params, x, want=("u",))
-                u = out["u"]
-            L.check(L.lib().hjb_policy_step(self.kernels.sys_spec, self.kernels.task, xf, lo, hi, P, int(terminal),
-                                            L.ptr(x), L.ptr(u), L.ptr(alive), L.ptr(total), L.ptr(rec_x[i]), L.ptr(rec_c[i]),
-                                            L.ptr(rec_d[i]), N, L.stream_ptr()), "hjb_policy_step")
-            if i % 32 == 31 and not bool(alive.any()):                # every trajectory has left the box
-                break
+        k = self.kernels
+        k._bind(self.model_params.flat)
+        # one library call: 2 T + 1 launches queued back to back (the per-step Python round trips cost more than the
+        # kernels for an epoch's 20 trajectories)
+        L.check(L.lib().hjb_policy_rollout(k.sys_spec, k.net, k.task, xf, lo, hi, P, T, L.ptr(x), L.ptr(u), L.ptr(zeros),
+                                           L.ptr(ones), L.ptr(alive), L.ptr(total), L.ptr(rec_x), L.ptr(rec_c), L.ptr(rec_d), N,
+                                           L.ptr(k.workspace), L.stream_ptr()), "hjb_policy_rollout")
         return rec_x, rec_c, rec_d, total
 
     def get_trajectory_cost(self, trajectory):

@@ -314,6 +314,27 @@ int hjb_policy_step(const hjb_system* sys, const hjb_task* task, const float* xf
   return to_status(step_policy(sys->kind, a, (cudaStream_t)stream));
 }
 
+int hjb_policy_rollout(const hjb_system* sys, const hjb_vnet* net, const hjb_task* task, const float* xf, const float* obs_lo,
+                       const float* obs_hi, const float* P, int32_t T, float* x, float* u, const float* zeros, const float* ones,
+                       float* alive, float* total_cost, float* rec_x, float* rec_cost, float* rec_done, int64_t N,
+                       void* workspace, void* stream) {
+  if (!sys || !net || !task || T < 0 || N < 0) return HJB_ERR_BAD_ARG;
+  if (N == 0) return HJB_OK;
+  if (!x || !u || !zeros || !ones || !alive || !total_cost || !rec_x || !rec_cost || !rec_done || !workspace) return HJB_ERR_BAD_ARG;
+  const int64_t n = sys->n;
+  for (int32_t i = 0; i <= T; ++i) {
+    const int32_t terminal = i == T;   // controller/vhjb.py:188-191: what is still running ends with a boundary sample
+    if (!terminal) {
+      const int rc = hjb_vhjb_residual(sys, net, task, x, zeros, ones, N, nullptr, nullptr, u, nullptr, nullptr, workspace, stream);
+      if (rc != HJB_OK) return rc;
+    }
+    const int rc = hjb_policy_step(sys, task, xf, obs_lo, obs_hi, P, terminal, x, u, alive, total_cost, rec_x + (int64_t)i * N * n,
+                                   rec_cost + (int64_t)i * N, rec_done + (int64_t)i * N, N, stream);
+    if (rc != HJB_OK) return rc;
+  }
+  return HJB_OK;
+}
+
 int hjb_fma_peak_probe(float* sink, int64_t sink_len, int32_t iters, double* flops, void* stream) {
   if (!sink || sink_len <= 0 || iters <= 0) return HJB_ERR_BAD_ARG;
   return to_status(fma_probe(sink, sink_len, iters, flops, (cudaStream_t)stream));
