@@ -176,7 +176,8 @@ typedef struct hjb_vnet {
   int32_t n;
   int32_t act; /* hjb_activation */
   int32_t features[3];
-  int32_t _pad;
+  int32_t impl; /* 0: tensor-core kernels (fp16 x 3, vhjb_tc.cuh); 1: fp32 CUDA-core kernels (vhjb_simt.cuh) — exact for
+                   batches whose adjoint seeds or chain gain leave the fp16 range management (hjb_vhjb_saturation) */
   const float* params; /* DEVICE pointer, 128 n + 24576 floats */
   float mean[HJB_MAX_N], std[HJB_MAX_N], xf[HJB_MAX_N];
   float eps_s; /* config.epsilon_scalar */
@@ -250,11 +251,16 @@ int hjb_vhjb_train_step(const hjb_system* sys, const hjb_vnet* net, const hjb_ta
 /*
  * Range check of the last hjb_vhjb_loss_grad on this workspace (device float `count`, stream-ordered).  The
  * tensor-core gradient pass carries per-state adjoints in fp16 with per-state power-of-two scaling (vhjb_tc.cuh);
- * a state whose adjoint seed exceeds 2^26 times the batch-typical weight (only |x - xf| and |u - uf| ~ 1e-4 and
- * below reach that with the reference's eps = 1e-10) is under-weighted and counted here.  0 for every other batch;
- * callers that need those states exactly set HJB_VHJB_IMPL=simt (the fp32 CUDA-core kernel).
+ * a state whose adjoint seed exceeds 2^12 times the batch-typical weight (|x - xf| and |u - uf| ~ 1e-2 and below reach
+ * that with the reference's eps = 1e-10), or whose adjoint chain grows past fp16's 65504 (a gain above ~1000 between the
+ * seeds and the first layer: conversions saturate, nothing becomes inf / NaN), is clipped and counted here.  0 for every
+ * other batch; callers that need those states exactly set hjb_vnet.impl = 1 (the fp32 CUDA-core kernels).
  */
 int hjb_vhjb_saturation(const void* workspace, int32_t n, float* count, void* stream);
+/* The same count summed over every gradient launch on this workspace since the last reset (count nullable; reset != 0
+ * zeroes the total after reading it; zero it once — or zero-fill the workspace — before the first use): what a training
+ * loop polls once per epoch instead of once per update. */
+int hjb_vhjb_saturation_total(void* workspace, int32_t n, float* count, int32_t reset, void* stream);
 
 /*
  * One step of the learned-policy rollout for N trajectories at once (VHJBController.rollout_trajectory,

@@ -54,7 +54,7 @@ RES_NORMALIZED, RES_MIN_TIME = 0, 1
 
 
 class HjbVnet(C.Structure):
-    _fields_ = [("n", C.c_int32), ("act", C.c_int32), ("features", C.c_int32 * 3), ("_pad", C.c_int32),
+    _fields_ = [("n", C.c_int32), ("act", C.c_int32), ("features", C.c_int32 * 3), ("impl", C.c_int32),
                 ("params", C.c_void_p),
                 ("mean", C.c_float * HJB_MAX_N), ("std", C.c_float * HJB_MAX_N), ("xf", C.c_float * HJB_MAX_N),
                 ("eps_s", C.c_float)]
@@ -90,6 +90,7 @@ SYMBOLS = {
                                       C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int32, _P, _P, _P, _P, _P,
                                       _P, _P]),
     "hjb_vhjb_saturation": (C.c_int, [_P, C.c_int32, _P, _P]),
+    "hjb_vhjb_saturation_total": (C.c_int, [_P, C.c_int32, _P, C.c_int32, _P]),
     "hjb_policy_step": (C.c_int, [C.POINTER(HjbSystem), C.POINTER(HjbTask), C.POINTER(C.c_float), C.POINTER(C.c_float),
                                   C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_int32, _P, _P, _P, _P, _P, _P, _P,
                                   C.c_int64, _P]),

@@ -120,12 +120,21 @@ class VhjbKernels:
         self.residual_form = residual_form
         self.eps = float(eps)
         ws = int(L.lib().hjb_vhjb_workspace_bytes(self.n))
-        self.workspace = torch.empty(ws // 4, device="cuda", dtype=torch.float32)
+        self.workspace = torch.zeros(ws // 4, device="cuda", dtype=torch.float32)    # (zero: the saturation total starts at 0)
         self.norm = torch.empty(2, device="cuda", dtype=torch.float32)
         # gradient and the two loss sums live back to back so that ONE all-reduce covers both
         self.grad_and_sums = torch.zeros(self.P + 2, device="cuda", dtype=torch.float32)
         self.grad = self.grad_and_sums[: self.P]
         self.sums = self.grad_and_sums[self.P:]
+
+    @property
+    def impl(self) -> str:
+        """'tensor' (tcgen05, fp16 x 3: the default) or 'simt' (fp32 CUDA-core kernels: exact for any range of seeds)."""
+        return "simt" if self.net.impl == 1 else "tensor"
+
+    @impl.setter
+    def impl(self, which: str):
+        self.net.impl = {"tensor": 0, "simt": 1}[which]
 
     def _bind(self, params_flat):
         assert params_flat.is_cuda and params_flat.dtype == self.torch.float32 and params_flat.numel() == self.P
@@ -166,6 +175,14 @@ class VhjbKernels:
         Synchronises the stream."""
         out = self.torch.zeros(1, device="cuda", dtype=self.torch.float32)
         L.check(L.lib().hjb_vhjb_saturation(L.ptr(self.workspace), self.n, L.ptr(out), L.stream_ptr()), "hjb_vhjb_saturation")
+        return int(out.item())
+
+    def saturated_total(self, reset: bool = True) -> int:
+        """The same count summed over every gradient launch since the last reset (``hjb_vhjb_saturation_total``): what a
+        training loop polls once per epoch.  Synchronises the stream."""
+        out = self.torch.zeros(1, device="cuda", dtype=self.torch.float32)
+        L.check(L.lib().hjb_vhjb_saturation_total(L.ptr(self.workspace), self.n, L.ptr(out), int(reset), L.stream_ptr()),
+                "hjb_vhjb_saturation_total")
         return int(out.item())
 
     def adam(self, params_flat, mu, nu, grad, step: int, lr: float, b1=0.9, b2=0.999, eps=1e-8):
@@ -495,6 +512,13 @@ class VHJBController(Controller):
                 avg_total.append(float(totals) / n_batches)
                 avg_hjb.append(float(hjbs) / n_batches)
                 avg_term.append(float(terms) / n_batches)
+            # Range check of the tensor-core gradient pass, once per epoch (one host read): a state whose adjoint seeds
+            # or chain gain left the fp16 range management was clipped and counted, never silently — from here on the
+            # fp32 CUDA-core kernels take over (they are exact for any range; ~10x slower on large batches, no
+            # difference at the reference's batch size of 256).
+            if n_batches and self.kernels.impl == "tensor" and self.kernels.saturated_total() > 0:
+                self.kernels.impl = "simt"
+                print(f"epoch:{epoch + 1}, adjoint range check tripped: continuing with the fp32 CUDA-core kernels")
             if (epoch + 1) % 10 == 0:
                 if self.num_of_trajectories_per_epoch > 0:
                     print(f"epoch:{epoch + 1}, average trajectory cost:{avg_cost[-1]:.2f}, "

@@ -16,8 +16,7 @@ constexpr int kMaxCtas = 160;  // >= SM count (148 on B200)
 // Kernel selection: the tcgen05 kernel (vhjb_tc.cuh) for every compiled combination (relu / tanh / sin value nets);
 // the CUDA-core kernel (vhjb_simt.cuh) is the fp32 reference implementation on the device.  HJB_VHJB_IMPL=simt forces the CUDA-core kernel (A/B measurements, parity).
 static bool use_tensor_path(const hjb_vnet* net, int64_t B) {
-  if (B <= 0) return false;
-  (void)net;
+  if (B <= 0 || net->impl == 1) return false;
   const char* e = std::getenv("HJB_VHJB_IMPL");
   return !(e && std::strcmp(e, "simt") == 0);
 }
@@ -33,6 +32,17 @@ __global__ void __launch_bounds__(256) vhjb_reduce_kernel(const float* __restric
   float s = 0.f;
   for (int c = 0; c < ncta; ++c) s += partial[(int64_t)c * pstride + first + j];
   out[j] = accumulate ? out[j] + s : s;
+}
+
+// saturation count of one launch -> tail[0] (this batch; added when the batch arrives in pieces) and tail[1] (running total)
+__global__ void vhjb_sat_kernel(const float* __restrict__ partial, int64_t pstride, int ncta, int at, float* __restrict__ tail,
+                                int accumulate) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    float s = 0.f;
+    for (int c = 0; c < ncta; ++c) s += partial[(int64_t)c * pstride + at];
+    tail[0] = accumulate ? tail[0] + s : s;
+    tail[1] += s;
+  }
 }
 
 // ---- sum(1 - done), sum(done): two-stage, fixed order ----
@@ -102,7 +112,7 @@ __global__ void __launch_bounds__(256) vhjb_reduce_adam_kernel(const float* __re
     float t = 0.f;
     for (int c = 0; c < ncta; ++c) t += partial[(int64_t)c * pstride + P + j];
     if (j < 2) sums[j] = t;
-    else *sat = t;
+    else { sat[0] = t; sat[1] += t; }   // [0]: this launch, [1]: running total (hjb_vhjb_saturation_total)
   }
 }
 
@@ -245,7 +255,7 @@ static int run_vhjb(const hjb_system* sys, const hjb_vnet* net, const hjb_task* 
     if (e != cudaSuccess) return (int)e;
   }
   if (want_grad) {  // saturation count of the fp16 range management (vhjb_tc.cuh) -> workspace tail
-    vhjb_reduce_kernel<<<1, 256, 0, st>>>(a.partial, a.pstride, l.grid, P + 2, 1, a.partial + (int64_t)kMaxCtas * a.pstride, (int)accumulate);
+    vhjb_sat_kernel<<<1, 32, 0, st>>>(a.partial, a.pstride, l.grid, P + 2, a.partial + (int64_t)kMaxCtas * a.pstride, (int)accumulate);
     e = cudaGetLastError();
     if (e != cudaSuccess) return (int)e;
   }
@@ -269,6 +279,15 @@ int hjb_vhjb_saturation(const void* workspace, int32_t n, float* count, void* st
   if (!workspace || !count || n <= 0 || n > HJB_MAX_N) return HJB_ERR_BAD_ARG;
   const float* tail = static_cast<const float*>(workspace) + (int64_t)kMaxCtas * pstride_of(n);
   cudaError_t e = cudaMemcpyAsync(count, tail, sizeof(float), cudaMemcpyDeviceToDevice, (cudaStream_t)stream);
+  return e == cudaSuccess ? HJB_OK : (int)e;
+}
+
+int hjb_vhjb_saturation_total(void* workspace, int32_t n, float* count, int32_t reset, void* stream) {
+  if (!workspace || n <= 0 || n > HJB_MAX_N) return HJB_ERR_BAD_ARG;
+  float* tail = static_cast<float*>(workspace) + (int64_t)kMaxCtas * pstride_of(n);
+  cudaError_t e = cudaSuccess;
+  if (count) e = cudaMemcpyAsync(count, tail + 1, sizeof(float), cudaMemcpyDeviceToDevice, (cudaStream_t)stream);
+  if (e == cudaSuccess && reset) e = cudaMemsetAsync(tail + 1, 0, sizeof(float), (cudaStream_t)stream);
   return e == cudaSuccess ? HJB_OK : (int)e;
 }
 

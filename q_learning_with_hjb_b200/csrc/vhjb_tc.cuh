@@ -46,6 +46,12 @@ constexpr int kThreads = 32 * (kComputeWarps + 1);
 // kFlushTiles tiles: tcgen05.mma accumulates with truncation, and the bias of a longer chain was measured
 // (7.7e-5 of the gradient over 110 tiles = 3960 accumulating MMAs; 576 keep it near 1e-5).
 constexpr int kFlushTiles = 16;
+// Largest exponent (relative to the batch-typical seed) at which a state's adjoint seeds enter the fp16 chain; what a
+// heavier state carries beyond it moves onto the forward partners (<= kFwdCap more binades).  fp16 tops out at 2^16, so
+// the chain may grow by 2^(16 - kSeedCap) = 1024 x between the seeds and a1bar.  8 was too tight for trained nets: the
+// reference's linear_vhjb_controller.gin run reached a gain of 267 on a state 1.6e-3 from the goal at update 13,606,
+// a1bar_pre = 68,398 overflowed, and inf x 0 poisoned W1bar (found by tools/train_wall_time.py).
+constexpr int kSeedCap = 6, kFwdCap = 6;
 
 // ---- shared-memory map (bytes); every 16-bit matrix is stored as [hi piece | lo piece] ----
 constexpr uint32_t kW2 = 0, kW2Piece = VH1 * VH2 * 2;
@@ -116,14 +122,19 @@ template <> struct Fm<kBF16> {
     lo = *reinterpret_cast<const uint32_t*>(&l);
   }
 };
+// two floats -> packed fp16 pair (x0 in the low half), round to nearest, SATURATING at +-65504: an adjoint chain whose
+// gain outruns the range management (see kSeedCap) must not turn into inf and, one multiplication by zero later, NaN
+__device__ __forceinline__ uint32_t f2h2_sat(float x0, float x1) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(x1), "f"(x0));
+  return r;
+}
 template <> struct Fm<kF16> {
   static constexpr float ws = 1.f, iws = 1.f;
   static __device__ __forceinline__ void pack2(float x0, float x1, uint32_t& hi, uint32_t& lo) {
-    const __half2 h = __floats2half2_rn(x0, x1);
-    const float2 hf = __half22float2(h);
-    const __half2 l = __floats2half2_rn(x0 - hf.x, x1 - hf.y);
-    hi = *reinterpret_cast<const uint32_t*>(&h);
-    lo = *reinterpret_cast<const uint32_t*>(&l);
+    hi = f2h2_sat(x0, x1);
+    const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hi));
+    lo = f2h2_sat(x0 - hf.x, x1 - hf.y);
   }
 };
 
@@ -193,6 +204,7 @@ __global__ void __launch_bounds__(kThreads, 1) vhjb_tc_kernel(const __grid_const
   uint32_t* tptr = reinterpret_cast<uint32_t*>(smem + kMisc + 568);
   float* sF = reinterpret_cast<float*>(smem + kMisc + 576);    // 2^f_s: weight-gradient scale of the forward operands
   float* sYm = reinterpret_cast<float*>(smem + kMisc + 832);   // max_c |2 y_c| of the state (second column half)
+  int* sOvf = reinterpret_cast<int*>(smem + kMisc + 1088);     // threads whose adjoint chain reached the fp16 ceiling
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
   // ---- weights -> shared memory (scaled, split, core-matrix layout), once per CTA ----
@@ -224,6 +236,7 @@ __global__ void __launch_bounds__(kThreads, 1) vhjb_tc_kernel(const __grid_const
     }
   }
   if (tid == 0) {
+    *sOvf = 0;
     mbar_init(bar_pass, kComputeWarps);
     mbar_init(bar_mma, 1);
     mbar_init(bar_wg6, 1);
@@ -397,6 +410,14 @@ __global__ void __launch_bounds__(kThreads, 1) vhjb_tc_kernel(const __grid_const
       if constexpr (ACT == HJB_ACT_RELU) return st > 0.f ? d * iws : 0.f;
       else return d * (iws * tc_d1<ACT>(st));
     };
+    // the chain is largest at its end (a2bar, a1bar): those two passes watch for values at the fp16 ceiling, where the
+    // saturating conversion clips — reported through the saturation count, never silent
+    float chain_max = 0.f;
+    auto watched = [&](float d, float st) {
+      const float o = masked(d, st);
+      chain_max = fmaxf(chain_max, fabsf(o));
+      return o;
+    };
     // smooth activations: the b1 chain (b1 sigma''(a1), then g1bar b1 sigma''(a1)) of this thread's 32 states
     float chain1[kSmooth ? 32 : 1];
     // feature pass with the column index handed to fn (for chain1)
@@ -450,11 +471,11 @@ __global__ void __launch_bounds__(kThreads, 1) vhjb_tc_kernel(const __grid_const
     // Gradient pass, fp16 range management.  The reverse pass of one state is linear in its adjoint seeds
     // (g0bar, Vbar), whose size varies by many decades over a batch (1 / (l + eps), 1 / (cost + eps), 1 / batch).
     // With E = exponent of the batch-typical seed weight and seeds_s = 2^k_s x (numbers in [1/2, 1)), t_s = k_s - E:
-    // the adjoint chain of state s carries 2^(a_s - k_s) x its true values, a_s = clamp(t_s, -24, 8), so typical
+    // the adjoint chain of state s carries 2^(a_s - k_s) x its true values, a_s = clamp(t_s, -24, kSeedCap = 6), so typical
     // states sit near 2^0 and seeds down to 2^-24 x typical keep their exact weight (losing bits gradually);
-    // a state with t_s > 8 (|x - xf|, |u - uf| of order 1e-2 and below) moves the excess f_s = t_s - a_s <= 6 onto
+    // a state with t_s > 6 (|x - xf|, |u - uf| of order 1e-2 and below) moves the excess f_s = t_s - a_s <= 6 onto
     // the forward partners of its weight-gradient GEMMs (those columns are rescaled in place: rare path).  The TMEM
-    // accumulators hold 2^-E x gradient.  Seeds beyond 2^(14+E) are under-weighted and COUNTED in partial[P + 2]
+    // accumulators hold 2^-E x gradient.  Seeds beyond 2^(12+E) are under-weighted and COUNTED in partial[P + 2]
     // (hjb_vhjb_saturation): nothing overflows silently.
     int expE = 0;
     if constexpr (GRAD) {
@@ -693,9 +714,9 @@ __global__ void __launch_bounds__(kThreads, 1) vhjb_tc_kernel(const __grid_const
           float lam = 0.f, fs = 0.f;
           if (eb > 8 && eb < 226) {
             const int ks = eb - 126, ts = ks - expE;
-            const int as = max(-24, min(8, ts));
-            const int fe = min(6, ts - as);                                  // >= 0; 0 for all but near-goal states
-            if (sact && ts - as > 6) sat_count += 1.f;                               // seed beyond 2^(14+E): under-weighted
+            const int as = max(-24, min(kSeedCap, ts));
+            const int fe = min(kFwdCap, ts - as);                            // >= 0; 0 for all but near-goal states
+            if (sact && ts - as > kFwdCap) sat_count += 1.f;                 // seed beyond 2^(12+E): under-weighted
             lam = __uint_as_float((uint32_t)(as - ks + 127) << 23);          // 2^(a_s - k_s), exponent in [19, 252]
             fs = __uint_as_float((uint32_t)(fe + 127) << 23);                // 2^fe, fe in [0, 6]
           }
@@ -811,8 +832,8 @@ __global__ void __launch_bounds__(kThreads, 1) vhjb_tc_kernel(const __grid_const
         wait_mma();
         tmark(it);
         if constexpr (kSmooth)
-          feature_pass_x(cWk, cA2, cB2, kF1, std::false_type{}, [&](float d, float st, float& x) { return masked(d, st) + x; });
-        else feature_pass(cWk, cA2, kF1, masked);
+          feature_pass_x(cWk, cA2, cB2, kF1, std::false_type{}, [&](float d, float st, float& x) { return watched(d, st) + x; });
+        else feature_pass(cWk, cA2, kF1, watched);
         tmark(it);
         pass_done();                                            // -> G10a
         // P10b (under G10a): h1 2^f_s -> F0 once W3bar's GEMM of step 9 has read h2 (and ybar in F2)
@@ -823,8 +844,8 @@ __global__ void __launch_bounds__(kThreads, 1) vhjb_tc_kernel(const __grid_const
         wait_mma();
         tmark(it);
         if constexpr (kSmooth)
-          feature_pass_k(cWk, cA1, kF2, [&](float d, float st, int k) { return masked(d, st) + chain1[k]; });
-        else feature_pass(cWk, cA1, kF2, masked);
+          feature_pass_k(cWk, cA1, kF2, [&](float d, float st, int k) { return watched(d, st) + chain1[k]; });
+        else feature_pass(cWk, cA1, kF2, watched);
         tmark(it);
         pass_done();                                            // -> G11 (+ G0 of the next tile)
       }
@@ -838,6 +859,10 @@ __global__ void __launch_bounds__(kThreads, 1) vhjb_tc_kernel(const __grid_const
       if (n_iter > 0) drain_accumulators(drained);
       else
         for (int i = tid; i < vhjb_param_count(N); i += 32 * kComputeWarps) part[i] = 0.f;
+    }
+    if constexpr (GRAD) {
+      if (chain_max > 6.0e4f) atomicAdd(sOvf, 1);
+      asm volatile("bar.sync 1, 256;" ::: "memory");           // all pass warps: the counter is complete
     }
     if (epi_warp) {
       if (!sact) { hjb_sum = 0.f; term_sum = 0.f; sat_count = 0.f; }
@@ -856,7 +881,7 @@ __global__ void __launch_bounds__(kThreads, 1) vhjb_tc_kernel(const __grid_const
       if (tid == 0) {
         part[vhjb_param_count(N)] = (sV[0] + sV[4]) + (sV[8] + sV[12]);
         part[vhjb_param_count(N) + 1] = (sV[1] + sV[5]) + (sV[9] + sV[13]);
-        part[vhjb_param_count(N) + 2] = (sV[2] + sV[6]) + (sV[10] + sV[14]);
+        part[vhjb_param_count(N) + 2] = (sV[2] + sV[6]) + (sV[10] + sV[14]) + (float)*sOvf;
       }
     }
   }

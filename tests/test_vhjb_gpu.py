@@ -501,3 +501,64 @@ def test_single_call_train_step_is_bit_identical_to_the_separate_entry_points(na
     for a, b in zip(*results):
         assert torch.equal(a, b)
     assert not torch.equal(results[0][0], params)
+
+
+def test_adjoint_chain_overflow_is_clipped_and_counted_not_nan():
+    """A net with a large backward gain (weights of a trained net scaled up) and states next to the goal, whose seeds
+    enter the fp16 chain at its cap: the chain passes fp16's 65504.  Conversions saturate (finite gradient), the
+    saturation count reports it, the running total accumulates over launches, and impl = 'simt' computes the batch
+    exactly.  (Found in the wild: the reference's linear_vhjb_controller.gin run turned NaN at update 13,606.)"""
+    B = 1024
+    torch, k, p, orc, params, xs, dones, costs = _setup("linear", B, seed=31, wseed=9)
+    scale = torch.ones_like(params)
+    n1 = 2 * 128
+    scale[:n1] = 1e-4                                    # W1 x 1e-4, W2 x 100, W3 x 100: forward values stay moderate
+    scale[n1:] = 100.0                                   # (|y| ~ |z|), the backward chain gains 1e-4 x 100^4 = 1e4
+    big = (params * scale).contiguous()
+    rng = np.random.default_rng(0)
+    xs[:8] = (p.xf + 2e-3 * rng.uniform(-1, 1, size=(8, p.sys.n))).astype(np.float32)
+    dones[:] = 0
+    xd, dd, cd = _dev(torch, xs, dones, costs)
+    k.counts(dd, p.eps)
+    k.saturated_total(reset=True)
+    g_tc = k.loss_grad(big, xd, dd, cd, 0.0)[0].clone()
+    assert torch.isfinite(g_tc).all()
+    first = k.saturated()
+    assert first >= 1
+    k.loss_grad(big, xd, dd, cd, 0.0)
+    assert k.saturated_total(reset=True) == 2 * first and k.saturated_total() == 0
+    k.impl = "simt"
+    try:
+        g_cc = k.loss_grad(big, xd, dd, cd, 0.0)[0].clone()
+        assert k.saturated() == 0
+    finally:
+        k.impl = "tensor"
+    W64 = [w.astype(np.float64) for w in np.split(big.cpu().numpy(), [n1, n1 + 128 * 128])]
+    orc2 = V.VhjbOracle(p, [W64[0].reshape(2, 128), W64[1].reshape(128, 128), W64[2].reshape(128, 64)])
+    _, _, _, grads, _ = orc2.loss_and_grad(xs, dones, costs, 0.0)
+    go = np.concatenate([x.reshape(-1) for x in grads])
+    assert np.abs(g_cc.cpu().numpy() - go).max() <= TOL * np.abs(go).max()
+
+
+def test_wild_batch_that_overflowed_the_first_range_management():
+    """tests/golden/vhjb_linear_overflow_batch.npz: weights and minibatch of update 13,606 of the reference's
+    linear_vhjb_controller.gin run, where a state 1.6e-3 from the goal (seeds 2^8 x typical) met a backward gain of 267:
+    68,398 in fp16.  With the seed cap at 2^6 it is inside the range again: finite, not saturated, within tolerance."""
+    import os
+    torch = _cuda()
+    d = np.load(os.path.join(os.path.dirname(__file__), "golden", "vhjb_linear_overflow_batch.npz"))
+    k, p = make_kernels("linear")
+    params = torch.as_tensor(d["params"]).cuda()
+    xs, dones, costs, reg = d["xs"], d["dones"], d["costs"], float(d["reg"])
+    xd, dd, cd = _dev(torch, xs, dones, costs)
+    k.counts(dd, p.eps)
+    grad = k.loss_grad(params, xd, dd, cd, reg)[0]
+    assert torch.isfinite(grad).all() and k.saturated() == 0
+    W = np.split(d["params"].astype(np.float64), [256, 256 + 128 * 128])
+    orc = V.VhjbOracle(p, [W[0].reshape(2, 128), W[1].reshape(128, 128), W[2].reshape(128, 64)])
+    _, _, _, grads, _ = orc.loss_and_grad(xs, dones, costs, reg)
+    g = grad.cpu().numpy().astype(np.float64)
+    off = 0
+    for gi in grads:
+        sl = slice(off, off + gi.size); off += gi.size
+        assert np.abs(g[sl] - gi.reshape(-1)).max() <= TOL * np.abs(gi).max()
