@@ -543,7 +543,11 @@ def test_adjoint_chain_overflow_is_clipped_and_counted_not_nan():
 def test_wild_batch_that_overflowed_the_first_range_management():
     """tests/golden/vhjb_linear_overflow_batch.npz: weights and minibatch of update 13,606 of the reference's
     linear_vhjb_controller.gin run, where a state 1.6e-3 from the goal (seeds 2^8 x typical) met a backward gain of 267:
-    68,398 in fp16.  With the seed cap at 2^6 it is inside the range again: finite, not saturated, within tolerance."""
+    68,398 in fp16.  With the seed cap at 2^6 it is inside the range again: finite and not saturated.  Tolerance 3e-4
+    here instead of 1e-4: a third of this minibatch lies within 0.02 of the goal, where the trained net's dV/dx is what is
+    left after a ~100-fold cancellation in g1 W1^T, and tcgen05.mma accumulates with truncation (a -2.5e-6 relative bias
+    on the uncancelled terms): the seeds of such a state are good to ~2.5e-4 (tools/wild_batch_check.py: 5e-6 ... 3.6e-4
+    per state against the fp32 kernel, which itself is at 2.7e-7 on this batch) and they carry most of the gradient."""
     import os
     torch = _cuda()
     d = np.load(os.path.join(os.path.dirname(__file__), "golden", "vhjb_linear_overflow_batch.npz"))
@@ -561,4 +565,11 @@ def test_wild_batch_that_overflowed_the_first_range_management():
     off = 0
     for gi in grads:
         sl = slice(off, off + gi.size); off += gi.size
-        assert np.abs(g[sl] - gi.reshape(-1)).max() <= TOL * np.abs(gi).max()
+        assert np.abs(g[sl] - gi.reshape(-1)).max() <= 3e-4 * np.abs(gi).max()
+    k.impl = "simt"
+    try:
+        g32 = k.loss_grad(params, xd, dd, cd, reg)[0].cpu().numpy().astype(np.float64)
+    finally:
+        k.impl = "tensor"
+    go = np.concatenate([gi.reshape(-1) for gi in grads])
+    assert np.abs(g32 - go).max() <= 1e-5 * np.abs(go).max()          # the fp32 kernels: 2.7e-7
