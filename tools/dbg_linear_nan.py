@@ -1,3 +1,6 @@
+"""Developer tool (kept as the record of how the fp16 overflow of the adjoint chain was found): runs VHJBController.train()
+with the reference's linear config, stops at the first update that leaves non-finite weights, saves that minibatch and
+compares the tensor-core and fp32 gradients on it.  Run on a GPU box."""
 import os, sys
 sys.path.insert(0, os.getcwd())
 import numpy as np, torch

@@ -1,3 +1,6 @@
+"""Developer tool: gradient error of the tensor-core and fp32 kernels on tests/golden/vhjb_linear_overflow_batch.npz against
+the float64 oracle, for the whole minibatch and for its near-goal states one by one (where the truncating accumulation of
+tcgen05.mma meets a ~100-fold cancellation in dV/dx).  Run on a GPU box."""
 import os, sys
 sys.path.insert(0, os.getcwd())
 import numpy as np, torch
