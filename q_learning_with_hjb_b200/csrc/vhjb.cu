@@ -37,9 +37,12 @@ __global__ void __launch_bounds__(256) vhjb_reduce_kernel(const float* __restric
 // saturation count of one launch -> tail[0] (this batch; added when the batch arrives in pieces) and tail[1] (running total)
 __global__ void vhjb_sat_kernel(const float* __restrict__ partial, int64_t pstride, int ncta, int at, float* __restrict__ tail,
                                 int accumulate) {
-  if (threadIdx.x == 0 && blockIdx.x == 0) {
-    float s = 0.f;
-    for (int c = 0; c < ncta; ++c) s += partial[(int64_t)c * pstride + at];
+  // one warp: lane l sums the CTAs l, l + 32, ... (counts are small integers: exact in any order), then a shuffle tree
+  float s = 0.f;
+  for (int c = threadIdx.x; c < ncta; c += 32) s += partial[(int64_t)c * pstride + at];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (threadIdx.x == 0) {
     tail[0] = accumulate ? tail[0] + s : s;
     tail[1] += s;
   }
