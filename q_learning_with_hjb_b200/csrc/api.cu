@@ -175,7 +175,10 @@ static int cost_mode(const hjb_system* s, const hjb_cost* c) {
   for (int i = 0; i < s->m; ++i)
     for (int j = 0; j < s->m; ++j)
       if (i != j && c->R[i * s->m + j] != 0.f) return COST_DENSE;
-  return COST_DIAG;
+  bool unit = true;   // Q = I, R = I, goal with zero non-angle components: the cheaper COST_UNIT form
+  for (int i = 0; i < s->n; ++i) unit = unit && c->Q[i * s->n + i] == 1.f && (is_angle(s->kind, i) || c->xf[i] == 0.f);
+  for (int i = 0; i < s->m; ++i) unit = unit && c->R[i * s->m + i] == 1.f;
+  return unit ? COST_UNIT : COST_DIAG;
 }
 
 static int to_status(cudaError_t e) { return e == cudaSuccess ? HJB_OK : (e == cudaErrorNotSupported ? HJB_ERR_UNSUPPORTED : (int)e); }

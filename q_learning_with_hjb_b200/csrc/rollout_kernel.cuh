@@ -12,7 +12,9 @@
 
 namespace hjb {
 
-enum CostMode { COST_NONE = 0, COST_DIAG = 1, COST_DENSE = 2 };
+// COST_UNIT: Q = I, R = I and a goal whose non-angle components are 0 (every reference notebook and gin file) — one FFMA per
+// state component, FADD + FFMA per input, instead of two FFMAs each
+enum CostMode { COST_NONE = 0, COST_DIAG = 1, COST_DENSE = 2, COST_UNIT = 3 };
 
 struct RolloutArgs {
   DevSys sys;
@@ -55,7 +57,21 @@ __device__ __forceinline__ void error_coords(const float* z, const float* xf, co
 template <class S, int COST, bool CWRAP>
 __device__ __forceinline__ float running_cost(const DevCost& pc, const float* c0r, const float* r0r, const float* z,
                                               const float* u, float l) {
-  if constexpr (COST == COST_DIAG) {
+  if constexpr (COST == COST_UNIT) {
+#pragma unroll
+    for (int i = 0; i < S::N; ++i) {
+      float d = z[i];
+#pragma unroll
+      for (int k = 0; k < S::NANG; ++k)
+        if (CWRAP && S::ang(k) == i && pc.dang[k] != 0.f) d = wrap_pi_<S::kFast>(z[i] + pc.dang[k]);
+      l = fmaf(d, d, l);
+    }
+#pragma unroll
+    for (int k = 0; k < S::M; ++k) {
+      const float y = u[k] + pc.r0[k];                       // r0 = -uf
+      l = fmaf(y, y, l);
+    }
+  } else if constexpr (COST == COST_DIAG) {
 #pragma unroll
     for (int i = 0; i < S::N; ++i) {
       bool is_ang = false;
@@ -330,6 +346,7 @@ inline cudaError_t launch_cost(const RolloutArgs& a, const RolloutVariant& v, cu
   switch (v.cost) {
     case COST_NONE: return launch_box<S, C, INTEG, REC, COST_NONE>(a, v, st);
     case COST_DIAG: return launch_box<S, C, INTEG, REC, COST_DIAG>(a, v, st);
+    case COST_UNIT: return launch_box<S, C, INTEG, REC, COST_UNIT>(a, v, st);
     default: return launch_box<S, C, INTEG, REC, COST_DENSE>(a, v, st);
   }
 }
