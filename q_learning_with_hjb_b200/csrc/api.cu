@@ -111,6 +111,13 @@ static void make_dev_ctl(const hjb_system* s, const hjb_control* c, DevSys& ds, 
   }
   std::memcpy(d.K, c->K, sizeof(d.K));
   std::memcpy(d.P, c->P, sizeof(d.P));
+  if (c->kind == HJB_CTL_ACROBOT_ES) {
+    // dx^T P dx is evaluated over the upper triangle: P_ii dx_i^2 + (P_ij + P_ji) dx_i dx_j, j > i (14 instead of 20
+    // instructions; the same value for any P, symmetric or not)
+    for (int i = 0; i < 4; ++i)
+      for (int j = 0; j < 4; ++j)
+        d.P[i * 4 + j] = j > i ? (float)((double)c->P[i * 4 + j] + (double)c->P[j * 4 + i]) : (j == i ? c->P[i * 4 + i] : 0.f);
+  }
   std::memcpy(d.xf, c->xf, sizeof(d.xf));
   std::memcpy(d.uf, c->uf, sizeof(d.uf));
   std::memcpy(d.aux, c->aux, sizeof(d.aux));

@@ -333,12 +333,12 @@ struct AcrobotESCtl {
     dx[1] = pc.xf[1] != 0.f ? wrap_pi_<S::kFast>(x[1] - pc.xf[1]) : x[1];
     dx[2] = x[2] - pc.xf[2];
     dx[3] = x[3] - pc.xf[3];
-    float quad = 0.f;                                                // :114  dx^T P dx
+    float quad = 0.f;                                                // :114  dx^T P dx (upper triangle, folded on the host)
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      float row = 0.f;
+      float row = pc.P[i * 4 + i] * dx[i];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) row = fmaf(pc.P[i * 4 + j], dx[j], row);
+      for (int j = i + 1; j < 4; ++j) row = fmaf(pc.P[i * 4 + j], dx[j], row);
       quad = fmaf(dx[i], row, quad);
     }
     float ulqr = 0.f;                                                // :115
