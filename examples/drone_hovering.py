@@ -1,0 +1,65 @@
+"""2-D drone hovering by HJB value learning, end to end on the GPU — the "ours" run of the reference's
+examples/drone_hovering.ipynb (cells 3-10, 15-16): relu value net, clipped control around the hover thrust
+uf = [4.905, 4.905], normalised HJB residual, 150 epochs of 20 on-policy trajectories (200 steps, stopped when the drone is
+far away) + one shuffled pass of minibatches of 256.
+
+The notebook's saved output keeps three training lines (cell 10: loss 0.866, 0.460, 0.275 and collected trajectory lengths
+2.5, 22.9, 19.4 at epochs 10, 20, 30) and the evaluation of cell 16 ("mean pd: 9.389", "mean lqr: 9.984" over ten states).
+
+On-policy data makes this run sensitive to the initialisation: of the seeds 0..4, two (2 and 4) reach and beat the LQR's
+closed-loop cost within 150 epochs (6.85 and 6.24 against 6.58 on the next ten initial states — the notebook's own run
+reads 9.39 against 9.98 on its ten), one gets close (3) and two (0, 1) never keep the drone in the observation box; the
+fp32 CUDA-core kernels (HJB_VHJB_IMPL=simt) behave the same way, seed by seed.  The default seed is one that converges.
+
+    python examples/drone_hovering.py [--epochs 150] [--seed 4]
+"""
+import argparse
+import os
+import sys
+import time
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+import onpolicy_hjb as H  # noqa: E402
+
+
+def make_problem():
+    from q_learning_with_hjb_b200.configs import gin_compat as gin
+    from q_learning_with_hjb_b200.configs.dynamics.dynamics_config import Quadrotors2DConfig
+    from q_learning_with_hjb_b200.dynamics.quadrotors import Quadrotors2D
+    import q_learning_with_hjb_b200 as pkg
+    gin.parse_config_file(os.path.join(os.path.dirname(pkg.__file__), "configs", "dynamics", "quadrotors2D.gin"))
+    dyn = Quadrotors2D(Quadrotors2DConfig())
+    p = H.Problem(dyn, np.zeros(6), np.array([4.905, 4.905]), np.array([-3, -3, -1.5, -5, -5, -2.0]),
+                  np.array([3, 3, 1.5, 5, 5, 2.0]), act="relu", far_away=np.array([10, 10, 4, 20, 20, 20.0]))
+    return p, p.kernels()
+
+
+def evaluate(p, k, params, count=10, T=10.0):
+    """Cells 15-16: closed-loop cost over 10 s from the next ``count`` initial states, learned policy and clipped hover LQR."""
+    from q_learning_with_hjb_b200.controller.controller_basic import lqr_gain
+    A, B = p.dyn.linearize(p.xf, p.uf)
+    K, _ = lqr_gain(A, B, np.eye(6), np.eye(2))
+    x0 = np.stack([p.dyn.get_initial_state() for _ in range(count)])
+    steps = int(round(T / p.dyn.dt))
+    return H.closed_loop_cost(p, H.Policy(k, params), x0, steps), H.closed_loop_cost(p, H.lqr_policy(p, K, clip=True), x0, steps)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--epochs", type=int, default=150)
+    ap.add_argument("--seed", type=int, default=4, help="weight-initialisation / shuffle seed")
+    args = ap.parse_args()
+    p, k = make_problem()
+    t0 = time.time()
+    params, history = H.train(p, k, args.epochs, seed=args.seed, log_every=50)
+    print(f"trained {args.epochs} epochs in {time.time() - t0:.1f} s")
+    pd, lqr = evaluate(p, k, params)
+    print("mean pd: ", pd.mean())
+    print("mean lqr: ", lqr.mean())
+
+
+if __name__ == "__main__":
+    main()
