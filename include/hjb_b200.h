@@ -236,6 +236,25 @@ int hjb_vhjb_loss_grad_accumulate(const hjb_system* sys, const hjb_vnet* net, co
                                   float* grad, float* sums, void* workspace, void* stream);
 
 /*
+ * hjb_vhjb_loss_grad for a batch that is still ARRIVING from the host: one launch; the kernel reads the states / costs of
+ * piece k (piece_states states each, a multiple of 64; the last piece may be shorter) only after ready[k] != 0.  The caller
+ * queues, on a copy stream, H2D(piece k of xs and costs) followed by a 4-byte H2D write of a non-zero value to ready[k],
+ * for k = 0, 1, ... (pieces become ready in order); dones and norm must be complete before the launch (the normalisers
+ * are sums over the whole batch).  ready must be zeroed before the copies start.  The poll is bounded: a flag that is
+ * never set yields wrong numbers after a few seconds, not a hung device.  Tensor-core kernels only
+ * (HJB_ERR_UNSUPPORTED otherwise: use the piecewise entry points above).
+ */
+/* The copy side of a streamed batch, queued in one call (a dozen pieces x 3 cudaMemcpyAsync): piece k of xs_host / costs_host
+ * (PINNED host memory) -> xs / costs, then ones_host[k] (pinned, non-zero) -> ready[k], all on copy_stream.  Call it BEFORE
+ * hjb_vhjb_loss_grad_streamed: a polling kernel must never wait for work that is queued behind it (two streams may share a
+ * hardware queue). */
+int hjb_vhjb_stream_batch(const float* xs_host, const float* costs_host, float* xs, float* costs, int64_t B, int32_t n,
+                          int64_t piece_states, int32_t* ready, const int32_t* ones_host, void* copy_stream);
+int hjb_vhjb_loss_grad_streamed(const hjb_system* sys, const hjb_vnet* net, const hjb_task* task, const float* xs,
+                                const float* dones, const float* costs, int64_t B, const float* norm, float reg, float* grad,
+                                float* sums, void* workspace, const int32_t* ready, int64_t piece_states, void* stream);
+
+/*
  * One whole single-GPU training step (VHJBController.params_update, controller/vhjb.py:255-288) in one call and three
  * launches: the normalisers (hjb_vhjb_count with this task's eps; MIN_TIME: {B, 1}), the fused loss + gradient kernel, and
  * one kernel that reduces the per-CTA partials in the same fixed order as hjb_vhjb_loss_grad and applies the optax.adam

@@ -86,6 +86,9 @@ SYMBOLS = {
                                      _P, C.c_float, _P, _P, _P, _P]),
     "hjb_vhjb_loss_grad_accumulate": (C.c_int, [C.POINTER(HjbSystem), C.POINTER(HjbVnet), C.POINTER(HjbTask), _P, _P, _P,
                                                 C.c_int64, _P, C.c_float, _P, _P, _P, _P]),
+    "hjb_vhjb_stream_batch": (C.c_int, [_P, _P, _P, _P, C.c_int64, C.c_int32, C.c_int64, _P, _P, _P]),
+    "hjb_vhjb_loss_grad_streamed": (C.c_int, [C.POINTER(HjbSystem), C.POINTER(HjbVnet), C.POINTER(HjbTask), _P, _P, _P,
+                                              C.c_int64, _P, C.c_float, _P, _P, _P, _P, C.c_int64, _P]),
     "hjb_vhjb_train_step": (C.c_int, [C.POINTER(HjbSystem), C.POINTER(HjbVnet), C.POINTER(HjbTask), _P, _P, _P, C.c_int64,
                                       C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int32, _P, _P, _P, _P, _P,
                                       _P, _P]),

@@ -152,7 +152,7 @@ struct AdamTail {   // when set, run_vhjb ends with vhjb_reduce_adam_kernel inst
 static int run_vhjb(const hjb_system* sys, const hjb_vnet* net, const hjb_task* task, const float* xs, const float* dones,
                     const float* costs, int64_t B, const float* norm, float reg, float* V, float* p, float* u, float* r,
                     float* grad, float* sums, void* workspace, bool want_grad, bool accumulate, cudaStream_t st,
-                    const AdamTail* tail = nullptr) {
+                    const AdamTail* tail = nullptr, const int32_t* ready = nullptr, int64_t piece_states = 0) {
   if (!sys || !net || !task || B < 0) return HJB_ERR_BAD_ARG;
   if (net->n != sys->n || net->features[0] != VH1 || net->features[1] != VH2 || net->features[2] != VH3)
     return HJB_ERR_UNSUPPORTED;
@@ -188,6 +188,11 @@ static int run_vhjb(const hjb_system* sys, const hjb_vnet* net, const hjb_task* 
   const bool tensor = use_tensor_path(net, B);
   const int tile = tensor ? tc::TS : VBM;
   a.n_tiles = (B + tile - 1) / tile;
+  if (ready) {   // streamed batch: tensor-core gradient kernel only, pieces of whole tiles
+    if (!tensor || !want_grad || piece_states <= 0 || piece_states % tc::TS != 0) return HJB_ERR_UNSUPPORTED;
+    a.ready = ready;
+    a.piece_tiles = piece_states / tc::TS;
+  }
 
   static long long* dbg_buf = nullptr;
   const bool dbg = tensor && std::getenv("HJB_TC_DEBUG_TIMING") != nullptr;
@@ -324,6 +329,30 @@ int hjb_vhjb_loss_grad_accumulate(const hjb_system* sys, const hjb_vnet* net, co
                                   float* grad, float* sums, void* workspace, void* stream) {
   return run_vhjb(sys, net, task, xs, dones, costs, B, norm, reg, nullptr, nullptr, nullptr, nullptr, grad, sums, workspace,
                   true, true, (cudaStream_t)stream);
+}
+
+int hjb_vhjb_stream_batch(const float* xs_host, const float* costs_host, float* xs, float* costs, int64_t B, int32_t n,
+                          int64_t piece_states, int32_t* ready, const int32_t* ones_host, void* copy_stream) {
+  if (!xs_host || !costs_host || !xs || !costs || !ready || !ones_host || B < 0 || n <= 0 || n > HJB_MAX_N || piece_states <= 0)
+    return HJB_ERR_BAD_ARG;
+  cudaStream_t st = (cudaStream_t)copy_stream;
+  int k = 0;
+  for (int64_t lo = 0; lo < B; lo += piece_states, ++k) {
+    const int64_t cnt = (B - lo < piece_states) ? B - lo : piece_states;
+    cudaError_t e = cudaMemcpyAsync(xs + lo * n, xs_host + lo * n, (size_t)cnt * n * sizeof(float), cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(costs + lo, costs_host + lo, (size_t)cnt * sizeof(float), cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(ready + k, ones_host + k, sizeof(int32_t), cudaMemcpyHostToDevice, st);
+    if (e != cudaSuccess) return (int)e;
+  }
+  return HJB_OK;
+}
+
+int hjb_vhjb_loss_grad_streamed(const hjb_system* sys, const hjb_vnet* net, const hjb_task* task, const float* xs,
+                                const float* dones, const float* costs, int64_t B, const float* norm, float reg, float* grad,
+                                float* sums, void* workspace, const int32_t* ready, int64_t piece_states, void* stream) {
+  if (!ready) return HJB_ERR_BAD_ARG;
+  return run_vhjb(sys, net, task, xs, dones, costs, B, norm, reg, nullptr, nullptr, nullptr, nullptr, grad, sums, workspace,
+                  true, false, (cudaStream_t)stream, nullptr, ready, piece_states);
 }
 
 int hjb_vhjb_train_step(const hjb_system* sys, const hjb_vnet* net, const hjb_task* task, const float* xs, const float* dones,

@@ -45,6 +45,10 @@ struct VhjbArgs {
   int64_t pstride;
   int64_t n_tiles;
   long long* dbg;     // developer timing probe (HJB_TC_DEBUG_TIMING=1), else null
+  // streamed batches (tensor-core gradient kernel only): the states / costs of tile t may be read once
+  // ready[t / piece_tiles] != 0 — the flags are written by the copy stream behind each piece of the batch
+  const int* ready;
+  int64_t piece_tiles;
 };
 
 __host__ __device__ constexpr int vhjb_param_count(int n) { return n * VH1 + VH1 * VH2 + VH2 * VH3; }

@@ -180,6 +180,28 @@ __device__ __forceinline__ float tc_d2(float st) {
   else return -__sinf(st);
 }
 
+// Streamed batches: block until the piece that holds `tile` has landed (flags written by the copy engine behind each
+// piece, in order, so a set flag implies the earlier ones).  `have` caches how many pieces this thread knows to be there.
+// The poll is bounded (~seconds): a caller that never sets a flag gets wrong numbers, not a hung GPU.
+__device__ __forceinline__ void wait_piece(const VhjbArgs& a, int64_t tile, int& have) {
+  if (a.ready == nullptr) return;
+  const int piece = (int)(tile / a.piece_tiles);
+  if (piece < have) return;
+  // ONE lane per warp polls, 2 us apart: ~1200 pollers per GPU.  (Every lane polling 100 ns apart — 38,000 threads on one
+  // L2 line — starved the copy engine's own write of that line: the flag was not seen for seconds.)
+  if ((threadIdx.x & 31) == 0) {
+    const int* f = a.ready + piece;
+    int v = 0;
+    for (unsigned spins = 0; spins < (1u << 22); ++spins) {
+      asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+      if (v != 0) break;
+      __nanosleep(2000);
+    }
+  }
+  __syncwarp();
+  have = piece + 1;
+}
+
 template <class S, int ACT, int UFORM, int RFORM, bool GRAD, int FMT>
 __global__ void __launch_bounds__(kThreads, 1) vhjb_tc_kernel(const __grid_constant__ VhjbArgs a) {
   constexpr int N = S::N, M = S::M;
@@ -498,7 +520,9 @@ __global__ void __launch_bounds__(kThreads, 1) vhjb_tc_kernel(const __grid_const
       tc_fence_after();
     };
     // states of a tile -> error coordinates z = wrap(x - xf) (vhjb.py:39); registers of the calling thread
+    int pieces_here = 0;
     auto fetch_raw = [&](int64_t tile) {   // global loads issued early, consumed by to_error() later
+      if constexpr (GRAD) wait_piece(a, tile, pieces_here);
       idx = tile * TS + sj;
       valid = sact && idx < a.B;
       if (valid) load_row<N>(a.xs, idx, xraw);
@@ -670,6 +694,7 @@ __global__ void __launch_bounds__(kThreads, 1) vhjb_tc_kernel(const __grid_const
       wait_mma();
       tmark(it);
       if (epi_warp && more) {   // issue the next tile's loads now; they are consumed under its G1
+        if constexpr (GRAD) wait_piece(a, tile + gridDim.x, pieces_here);
         const int64_t nidx = (tile + gridDim.x) * TS + sj;
         vnext = sact && nidx < a.B;
         if (vnext) load_row<N>(a.xs, nidx, xnext);

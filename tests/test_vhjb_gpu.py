@@ -393,6 +393,11 @@ def test_host_batch_train_step_matches_device_batch(name):
         assert torch.equal(n0, n2)
         assert (g2 - g0).abs().max() <= 2e-5 * g0.abs().max()
         assert ((s2 - s0).abs() <= 1e-5 * s0.abs() + 1e-30).all()
+    # default: ONE streamed launch that waits for per-piece arrival flags — the same launch geometry as the device batch,
+    # hence the same bits, and repeatable while the staging buffers are being overwritten step after step
+    for _ in range(3):
+        w3, g3, s3, n3 = run(lambda w, opt: k.train_step_host(w, opt, host[0], host[1], host[2], 0.3, 1e-3))
+        assert torch.equal(g0, g3) and torch.equal(w0, w3) and torch.equal(s0, s3) and torch.equal(n0, n3)
     assert not torch.equal(w0, params)                  # the step really updated the weights
 
 
