@@ -181,28 +181,32 @@ __device__ __forceinline__ float tc_d2(float st) {
 }
 
 // Streamed batches: block until the piece that holds `tile` has landed (flags written by the copy engine behind each
-// piece, in order, so a set flag implies the earlier ones).  `have` caches how many pieces this thread knows to be there.
+// piece, in order, so a set flag implies the earlier ones).
 // The poll is bounded (~seconds): a caller that never sets a flag gets wrong numbers, not a hung GPU.
-__device__ __forceinline__ void wait_piece(const VhjbArgs& a, int64_t tile, int& have) {
-  if (a.ready == nullptr) return;
-  const int piece = (int)(tile / a.piece_tiles);
-  if (piece < have) return;
-  // ONE lane per warp polls, 2 us apart: ~1200 pollers per GPU.  (Every lane polling 100 ns apart — 38,000 threads on one
-  // L2 line — starved the copy engine's own write of that line: the flag was not seen for seconds.)
-  if ((threadIdx.x & 31) == 0) {
-    const int* f = a.ready + piece;
-    int v = 0;
-    for (unsigned spins = 0; spins < (1u << 22); ++spins) {
-      asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
-      if (v != 0) break;
-      __nanosleep(2000);
+__device__ __forceinline__ void wait_piece(const VhjbArgs& a, int64_t tile, int64_t& next_tile, int& piece) {
+  // next_tile = first tile of the first piece not yet known to be there (LLONG_MAX when the batch is resident): the
+  // common case is one 64-bit compare
+  while (tile >= next_tile) {
+    // ONE lane per warp polls, 2 us apart: ~1200 pollers per GPU.  (Every lane polling 100 ns apart — 38,000 threads on
+    // one L2 line — starved the copy engine's own write of that line: the flag was not seen for seconds.)
+    if ((threadIdx.x & 31) == 0) {
+      const int* f = a.ready + piece;
+      int v = 0;
+      for (unsigned spins = 0; spins < (1u << 22); ++spins) {
+        asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+        if (v != 0) break;
+        __nanosleep(2000);
+      }
     }
+    __syncwarp();
+    ++piece;
+    next_tile += a.piece_tiles;
   }
-  __syncwarp();
-  have = piece + 1;
 }
 
-template <class S, int ACT, int UFORM, int RFORM, bool GRAD, int FMT>
+// STREAM: the batch may still be arriving (hjb_vhjb_loss_grad_streamed) — a separate instantiation, because the kernel
+// sits at its register cap and even the three registers of the arrival bookkeeping cost the resident-batch path 1.7 %.
+template <class S, int ACT, int UFORM, int RFORM, bool GRAD, int FMT, bool STREAM = false>
 __global__ void __launch_bounds__(kThreads, 1) vhjb_tc_kernel(const __grid_constant__ VhjbArgs a) {
   constexpr int N = S::N, M = S::M;
   // Smooth activations (tanh, sin) carry the sigma'' terms of SURVEY.md 8a-V6: a2bar += g2bar b2 sigma''(a2) and
@@ -520,9 +524,10 @@ __global__ void __launch_bounds__(kThreads, 1) vhjb_tc_kernel(const __grid_const
       tc_fence_after();
     };
     // states of a tile -> error coordinates z = wrap(x - xf) (vhjb.py:39); registers of the calling thread
-    int pieces_here = 0;
+    int64_t next_piece_tile = 0;
+    int piece_idx = 0;
     auto fetch_raw = [&](int64_t tile) {   // global loads issued early, consumed by to_error() later
-      if constexpr (GRAD) wait_piece(a, tile, pieces_here);
+      if constexpr (STREAM) wait_piece(a, tile, next_piece_tile, piece_idx);
       idx = tile * TS + sj;
       valid = sact && idx < a.B;
       if (valid) load_row<N>(a.xs, idx, xraw);
@@ -694,7 +699,7 @@ __global__ void __launch_bounds__(kThreads, 1) vhjb_tc_kernel(const __grid_const
       wait_mma();
       tmark(it);
       if (epi_warp && more) {   // issue the next tile's loads now; they are consumed under its G1
-        if constexpr (GRAD) wait_piece(a, tile + gridDim.x, pieces_here);
+        if constexpr (STREAM) wait_piece(a, tile + gridDim.x, next_piece_tile, piece_idx);
         const int64_t nidx = (tile + gridDim.x) * TS + sj;
         vnext = sact && nidx < a.B;
         if (vnext) load_row<N>(a.xs, nidx, xnext);
@@ -1276,7 +1281,12 @@ __global__ void __launch_bounds__(kResThreads, 1) vhjb_tc_residual_kernel(const 
 template <class S, int ACT, int UFORM, int RFORM>
 inline cudaError_t launch_vhjb_tc_variant(const VhjbArgs& a, const VhjbLaunch& l, cudaStream_t st) {
   cudaError_t e;
-  if (l.grad) {
+  if (l.grad && a.ready != nullptr) {
+    auto k = vhjb_tc_kernel<S, ACT, UFORM, RFORM, true, kF16, true>;
+    e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
+    if (e != cudaSuccess) return e;
+    k<<<l.grid, kThreads, kSmemBytes, st>>>(a);
+  } else if (l.grad) {
     auto k = vhjb_tc_kernel<S, ACT, UFORM, RFORM, true, kF16>;
     e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
     if (e != cudaSuccess) return e;
