@@ -119,3 +119,13 @@ def test_plot_trajectory_geometry_and_optional_matplotlib():
     except ImportError:
         with pytest.raises(ImportError):
             make_dynamics("cartpole").plot_trajectory(np.arange(3) * 0.1, np.zeros((3, 4)))
+
+
+def test_sgdr_schedule_of_the_product_matches_the_oracle():
+    """The termination-loss weight schedule of the product (controller/vhjb.py::sgdr_schedule, a host scalar handed to the
+    kernels) against the oracle's restatement of optax.sgdr_schedule with the gin files' values (vhjb.py:123-126)."""
+    from oracle import vhjb_oracle as V
+    from q_learning_with_hjb_b200.controller.vhjb import sgdr_schedule
+    for step in list(range(0, 4200, 37)) + [999, 1000, 1001, 1999, 2000, 2001, 19999, 20000, 20001, 10 ** 6]:
+        ours = sgdr_schedule(step, init=0.0, peak=1e-5, end=0.0, cycles=10, warmup=1000, total=2000)
+        assert abs(ours - V.sgdr_schedule(step)) < 1e-18, step
