@@ -261,11 +261,14 @@ int hjb_vhjb_loss_grad_streamed(const hjb_system* sys, const hjb_vnet* net, cons
  * update to net->params in place (step = 1-based update index).  Bit-identical to hjb_vhjb_count + hjb_vhjb_loss_grad +
  * hjb_adam; exists because the reference trains with minibatches of 256, where seven launches and as many host
  * round trips cost more than the arithmetic.  Multi-GPU callers keep the separate entry points (the all-reduce sits between
- * the gradient and Adam).  grad, sums, norm, the saturation count: as for hjb_vhjb_loss_grad.
+ * the gradient and Adam).  grad, sums, norm, the saturation count: as for hjb_vhjb_loss_grad.  loss_acc (device, 3 floats,
+ * nullable): the step's losses {hjb + reg term, hjb, term} (the values params_update returns) are ADDED to it, so that a
+ * training loop reads its epoch averages once instead of doing tensor arithmetic after every update.
  */
 int hjb_vhjb_train_step(const hjb_system* sys, const hjb_vnet* net, const hjb_task* task, const float* xs, const float* dones,
                         const float* costs, int64_t B, float reg, float lr, float b1, float b2, float adam_eps, int32_t step,
-                        float* m, float* v, float* norm, float* grad, float* sums, void* workspace, void* stream);
+                        float* m, float* v, float* norm, float* grad, float* sums, float* loss_acc, void* workspace,
+                        void* stream);
 
 /*
  * Range check of the last hjb_vhjb_loss_grad on this workspace (device float `count`, stream-ordered).  The

@@ -98,7 +98,9 @@ __global__ void __launch_bounds__(256) vhjb_reduce_adam_kernel(const float* __re
                                                                float* __restrict__ grad, float* __restrict__ sums,
                                                                float* __restrict__ sat, float* __restrict__ w,
                                                                float* __restrict__ m, float* __restrict__ v, float lr, float b1,
-                                                               float b2, float eps, float bc1, float bc2) {
+                                                               float b2, float eps, float bc1, float bc2,
+                                                               const float* __restrict__ norm, float reg,
+                                                               float* __restrict__ loss_acc) {
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j < P) {
     float g = 0.f;
@@ -116,6 +118,16 @@ __global__ void __launch_bounds__(256) vhjb_reduce_adam_kernel(const float* __re
     for (int c = 0; c < ncta; ++c) t += partial[(int64_t)c * pstride + P + j];
     if (j < 2) sums[j] = t;
     else { sat[0] = t; sat[1] += t; }   // [0]: this launch, [1]: running total (hjb_vhjb_saturation_total)
+  }
+  if (j == 0 && loss_acc != nullptr) {
+    // running sums of the step losses (total, hjb, term) of params_update, controller/vhjb.py:282-288: a training loop
+    // reads them once per epoch instead of doing tensor arithmetic on two scalars after every update
+    float s0 = 0.f, s1 = 0.f;
+    for (int c = 0; c < ncta; ++c) { s0 += partial[(int64_t)c * pstride + P]; s1 += partial[(int64_t)c * pstride + P + 1]; }
+    const float hjb = s0 / norm[0], term = s1 / norm[1];
+    loss_acc[0] += hjb + reg * term;
+    loss_acc[1] += hjb;
+    loss_acc[2] += term;
   }
 }
 
@@ -147,6 +159,7 @@ static int sm_count() {
 struct AdamTail {   // when set, run_vhjb ends with vhjb_reduce_adam_kernel instead of the three reductions
   float *w, *m, *v;
   float lr, b1, b2, eps, bc1, bc2;
+  float* loss_acc;
 };
 
 static int run_vhjb(const hjb_system* sys, const hjb_vnet* net, const hjb_task* task, const float* xs, const float* dones,
@@ -248,7 +261,8 @@ static int run_vhjb(const hjb_system* sys, const hjb_vnet* net, const hjb_task* 
   if (tail) {
     vhjb_reduce_adam_kernel<<<(P + 255) / 256, 256, 0, st>>>(a.partial, a.pstride, l.grid, P, grad, sums,
                                                              a.partial + (int64_t)kMaxCtas * a.pstride, tail->w, tail->m, tail->v,
-                                                             tail->lr, tail->b1, tail->b2, tail->eps, tail->bc1, tail->bc2);
+                                                             tail->lr, tail->b1, tail->b2, tail->eps, tail->bc1, tail->bc2, norm, reg,
+                                                             tail->loss_acc);
     e = cudaGetLastError();
     return e == cudaSuccess ? HJB_OK : (int)e;
   }
@@ -357,7 +371,8 @@ int hjb_vhjb_loss_grad_streamed(const hjb_system* sys, const hjb_vnet* net, cons
 
 int hjb_vhjb_train_step(const hjb_system* sys, const hjb_vnet* net, const hjb_task* task, const float* xs, const float* dones,
                         const float* costs, int64_t B, float reg, float lr, float b1, float b2, float adam_eps, int32_t step,
-                        float* m, float* v, float* norm, float* grad, float* sums, void* workspace, void* stream) {
+                        float* m, float* v, float* norm, float* grad, float* sums, float* loss_acc, void* workspace,
+                        void* stream) {
   if (!sys || !net || !task || !net->params || !m || !v || !norm || !grad || !sums || !workspace || B <= 0 || step < 1)
     return HJB_ERR_BAD_ARG;
   if (!xs || !dones || !costs) return HJB_ERR_BAD_ARG;
@@ -384,6 +399,7 @@ int hjb_vhjb_train_step(const hjb_system* sys, const hjb_vnet* net, const hjb_ta
   tail.lr = lr; tail.b1 = b1; tail.b2 = b2; tail.eps = adam_eps;
   tail.bc1 = (float)(1.0 - std::pow((double)b1, (double)step));
   tail.bc2 = (float)(1.0 - std::pow((double)b2, (double)step));
+  tail.loss_acc = loss_acc;
   return run_vhjb(sys, net, task, xs, dones, costs, B, norm, reg, nullptr, nullptr, nullptr, nullptr, grad, sums, workspace, true,
                   false, st, &tail);
 }

@@ -578,3 +578,23 @@ def test_wild_batch_that_overflowed_the_first_range_management():
         k.impl = "tensor"
     go = np.concatenate([gi.reshape(-1) for gi in grads])
     assert np.abs(g32 - go).max() <= 1e-5 * np.abs(go).max()          # the fp32 kernels: 2.7e-7
+
+
+def test_train_loop_loss_accumulator_matches_params_update():
+    """VHJBController.train()'s fast path (fused step + device accumulator of the step losses) returns the same epoch
+    averages as the loop over params_update (taken when the method is overridden), update for update."""
+    import torch
+    results = []
+    for override in (False, True):
+        np.random.seed(0)
+        dyn, ctl = _cartpole_controller(12)
+        ctl.epochs, ctl.batch_size = 3, 16                                # (the seed data set holds 20 samples)
+        if override:
+            orig = ctl.params_update
+            ctl.params_update = lambda *a, **kw: orig(*a, **kw)          # an instance override: the generic loop
+        lists = ctl.train()
+        results.append((lists, ctl.model_params.flat.clone(), ctl.update_counter))
+    (la, wa, ca), (lb, wb, cb) = results
+    assert ca == cb and ca > 0 and torch.equal(wa, wb)
+    for a, b in zip(la, lb):
+        np.testing.assert_allclose(a, b, rtol=2e-6, atol=1e-9)
