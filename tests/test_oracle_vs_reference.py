@@ -151,3 +151,38 @@ def test_config_classes_and_gin_files_bind_like_the_reference():
                 assert bindings(os.path.join(pkg, sub, f)) == bindings(f"{ref}/{sub}/{f}"), f
                 checked += 1
     assert checked == 7
+
+
+def test_waypoints_planner_matches_the_reference():
+    """Quadrotors2DWaypointsPlanner (host-side minimum-snap planner + differential flatness) against
+    the reference class, run unmodified through the import stubs: coefficients, and reference state / feed-forward input
+    along and past the trajectory; the batched plan(ts) against update(t)."""
+    import importlib
+    R.make_quad2d()                                              # sets up the stubs / sys.path for the reference tree
+    ref_mod = importlib.import_module("controller.quadrotors_model_based_controller")
+    from q_learning_with_hjb_b200.controller.quadrotors_model_based_controller import Quadrotors2DWaypointsPlanner
+    dyn_ref = R.make_quad2d()
+    for pts in (np.array([[0.0, 0.0], [1.0, 0.5], [2.0, -0.3], [2.5, 1.0]]), np.array([[0.0, 0.0], [0.7, 1.1]])):
+        ref = ref_mod.Quadrotors2DWaypointsPlanner(pts, dyn_ref, avg_speed=0.4)
+        ours = Quadrotors2DWaypointsPlanner(pts, dyn_ref, avg_speed=0.4)
+        np.testing.assert_allclose(ours.cumulated_t, ref.cumulated_t, rtol=1e-14)
+        np.testing.assert_allclose(ours.coeff, ref.coeff, rtol=1e-6, atol=1e-8 * np.abs(ref.coeff).max())
+        ts = np.linspace(0.0, ref.cumulated_t[-1] * 1.2, 41)
+        xs_plan, us_plan = ours.plan(ts)
+        for i, t in enumerate(ts):
+            xr, ur = ref.update(t)
+            xo, uo = ours.update(t)
+            np.testing.assert_allclose(xo, xr, rtol=1e-6, atol=1e-7)
+            np.testing.assert_allclose(uo, ur, rtol=1e-6, atol=1e-7)
+            np.testing.assert_allclose(xs_plan[i], xr, rtol=1e-6, atol=1e-7)
+            np.testing.assert_allclose(us_plan[i], ur, rtol=1e-6, atol=1e-7)
+        # with the consistent second derivative of theta (the reference's drops a factor in one term) the plan is a
+        # trajectory of the model: x' = f(x) + g(x) u along it (central differences of the states); the reference's is not
+        exact = Quadrotors2DWaypointsPlanner(pts, dyn_ref, avg_speed=0.4, exact_theta_ddot=True)
+        h = 1e-5
+        t0 = 0.37 * ref.cumulated_t[-1]
+        xm, _ = exact.update(t0 - h); xp, _ = exact.update(t0 + h); x0, u0 = exact.update(t0)
+        f, g = O.std_system("quad2d").f_g(x0[None])
+        np.testing.assert_allclose((xp - xm) / (2 * h), f[0] + g[0] @ u0, rtol=1e-5, atol=1e-7)
+        xr, ur = ref.update(t0)
+        assert abs(((xp - xm) / (2 * h))[5] - (f[0] + g[0] @ ur)[5]) > 1e-5

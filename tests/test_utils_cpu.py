@@ -62,3 +62,38 @@ def test_linearize_batched_on_the_oracle_dynamics():
     np.testing.assert_allclose(A[0], Aref, atol=1e-6)
     np.testing.assert_allclose(B[0], Bref, atol=1e-6)
     assert A.shape == (2, 4, 4) and B.shape == (2, 4, 1) and not np.allclose(A[0], A[1])
+
+
+def test_waypoints_planner_interpolates_and_is_a_model_trajectory():
+    """Quadrotors2DWaypointsPlanner without the reference at hand: the minimum-snap polynomials pass through the way-points
+    at the segment times, start and end at rest, are C^6 across interior points, hover after the last one, and — with the
+    consistent theta'' — (x(t), u(t)) satisfies x' = f(x) + g(x) u of the planar quadrotor."""
+    from oracle import rollout_oracle as O
+    from q_learning_with_hjb_b200.controller.quadrotors_model_based_controller import Quadrotors2DWaypointsPlanner
+    from tests.helpers import make_dynamics
+    dyn = make_dynamics("quad2d")
+    pts = np.array([[0.0, 0.0], [1.0, 0.5], [2.0, -0.3], [2.5, 1.0]])
+    pl = Quadrotors2DWaypointsPlanner(pts, dyn, avg_speed=0.5, exact_theta_ddot=True)
+    assert pl.coeff.shape == (2, 3, 8)
+    for i, t in enumerate(pl.cumulated_t):
+        x, u = pl.update(min(t, pl.cumulated_t[-1] - 1e-12) if i == len(pts) - 1 else t)
+        np.testing.assert_allclose(x[:2], pts[i], atol=1e-8)
+    x0, u0 = pl.update(0.0)
+    np.testing.assert_allclose(x0[2:], 0.0, atol=1e-9)                              # at rest, level
+    np.testing.assert_allclose(u0.sum(), dyn.m * dyn.g, rtol=1e-9)                  # hover thrust (the snap is free: a torque)
+    xe, ue = pl.update(pl.cumulated_t[-1] + 3.0)                                    # past the end: hover at the last point
+    np.testing.assert_allclose(xe, [2.5, 1.0, 0, 0, 0, 0], atol=1e-12)
+    np.testing.assert_allclose(ue, [dyn.m * dyn.g / 2] * 2, rtol=1e-12)
+    for n in range(0, 7):                                                            # continuity of derivatives 0..6
+        for i in range(1, len(pts) - 1):
+            left = pl.coeff[:, i - 1, :] @ pl.get_polynomial_term(pl.interval_t[i - 1], n)
+            right = pl.coeff[:, i, :] @ pl.get_polynomial_term(0.0, n)
+            np.testing.assert_allclose(left, right, atol=1e-6 * max(1.0, np.abs(left).max()))
+    sys = O.std_system("quad2d")
+    ts = np.linspace(0.05, 0.95, 7) * pl.cumulated_t[-1]
+    xs, us = pl.plan(ts)
+    h = 1e-5
+    for t, x, u in zip(ts, xs, us):
+        xm, _ = pl.update(t - h); xp, _ = pl.update(t + h)
+        f, g = sys.f_g(x[None])
+        np.testing.assert_allclose((xp - xm) / (2 * h), f[0] + g[0] @ u, rtol=1e-5, atol=1e-6)
