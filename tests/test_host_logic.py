@@ -129,3 +129,31 @@ def test_sgdr_schedule_of_the_product_matches_the_oracle():
     for step in list(range(0, 4200, 37)) + [999, 1000, 1001, 1999, 2000, 2001, 19999, 20000, 20001, 10 ** 6]:
         ours = sgdr_schedule(step, init=0.0, peak=1e-5, end=0.0, cycles=10, warmup=1000, total=2000)
         assert abs(ours - V.sgdr_schedule(step)) < 1e-18, step
+
+
+def test_header_is_plain_c_and_a_c_caller_links():
+    """The boundary is a C ABI: include/hjb_b200.h compiles as C99 (no C++ or torch types in the signatures) and a C
+    translation unit that takes the address of every declared entry point links against libhjb_b200.so (no call is made:
+    there is no GPU here)."""
+    import shutil
+    import subprocess
+    import tempfile
+    from q_learning_with_hjb_b200 import _lib as L
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("gcc not available")
+    header = os.path.join(ROOT, "include", "hjb_b200.h")
+    subprocess.run([gcc, "-std=c99", "-Wall", "-Wextra", "-Werror", "-fsyntax-only", "-x", "c", header], check=True)
+    names = sorted(L.SYMBOLS)
+    with tempfile.TemporaryDirectory() as tmp:
+        src = os.path.join(tmp, "caller.c")
+        with open(src, "w") as fh:
+            fh.write('#include "hjb_b200.h"\n#include <stdio.h>\nint main(void) {\n  const void* table[] = {\n')
+            fh.write("".join(f"    (const void*)&{n},\n" for n in names))
+            fh.write('  };\n  printf("%d\\n", (int)(sizeof(table) / sizeof(table[0])));\n  return hjb_abi_version() == 1 ? 0 : 1;\n}\n')
+        exe = os.path.join(tmp, "caller")
+        libdir = os.path.dirname(L.lib_path())
+        subprocess.run([gcc, "-std=c99", "-I", os.path.join(ROOT, "include"), src, "-o", exe, "-L", libdir, "-lhjb_b200",
+                        f"-Wl,-rpath,{libdir}"], check=True)
+        out = subprocess.run([exe], check=True, capture_output=True, text=True).stdout.strip()
+        assert int(out) == len(names)
