@@ -25,6 +25,14 @@ def test_shard_bounds_partition():
         parallel.shard_bounds(10, 2, 2)
 
 
+def test_single_process_is_not_distributed():
+    """No process group: VhjbKernels.train_step takes its one-call path (hjb_vhjb_train_step) and the collectives are no-ops."""
+    assert parallel.dist_info() == (0, 1) and not parallel.is_distributed()
+    t = torch.tensor([3.0, 5.0], dtype=torch.float64)
+    assert parallel.global_counts(t.clone(), 0.5).tolist() == [3.5, 5.5]
+    assert parallel.sum_across_ranks(t.clone()).tolist() == [3.0, 5.0]
+
+
 def _free_port():
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
@@ -37,7 +45,7 @@ def _worker(rank, world, port, out):
     try:
         from oracle import vhjb_oracle as V
         from tests.helpers_vhjb import problem, sample_batch
-        assert parallel.dist_info() == (rank, world)
+        assert parallel.dist_info() == (rank, world) and parallel.is_distributed()   # -> the multi-GPU branch of train_step
         p = problem("quad2d")
         W = V.init_weights(p.sys.n, seed=3)
         xs, dones, costs = sample_batch("quad2d", 1000, seed=4)       # the GLOBAL batch, identical on every rank
