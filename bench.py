@@ -543,7 +543,10 @@ def run_vhjb(args, w):
             "impl": "reference", "metric": "HJB-residual states/s (residual + loss-gradient + Adam train step)",
             "value": value, "unit": "states/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * t_all / max(1, args.steps), "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": {"workload": w["label"], "sample": sample},
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            # the b200 arm's config keys (same workload), plus what the bounded sample of one step was
+            "config": {"workload": w["label"], "states_per_gpu": w["states"], "value_net": "[n, 128, 128, 64]",
+                       "parallelism": f"{cores} host threads (torch)", "seed": "1234 + rank", "sample": sample},
             "cpu_baseline": {"value": value, "unit": "states/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": "states/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}), flush=True)
