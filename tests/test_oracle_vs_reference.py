@@ -186,3 +186,55 @@ def test_waypoints_planner_matches_the_reference():
         np.testing.assert_allclose((xp - xm) / (2 * h), f[0] + g[0] @ u0, rtol=1e-5, atol=1e-7)
         xr, ur = ref.update(t0)
         assert abs(((xp - xm) / (2 * h))[5] - (f[0] + g[0] @ ur)[5]) > 1e-5
+
+
+def test_host_side_class_methods_match_the_reference_classes():
+    """The drop-in classes against the reference's, method by method, for everything that stays on the host: manipulator
+    matrices, energy, control limits, dimensions, the initial-state stream of NumPy's global RNG, NumPy ``states_wrap``
+    (in place, returns its argument) and the linearisations behind the model-based gains."""
+    from tests.helpers import make_dynamics
+    rng = np.random.default_rng(7)
+    makers = {"cartpole": R.make_cartpole, "acrobot": R.make_acrobot, "quad2d": R.make_quad2d, "quad10d": R.make_quad10d,
+              "linear": R.make_linear}
+    for kind, make in makers.items():
+        ref = make()
+        ours = make_dynamics(kind)
+        n, m = ours.get_dimension()
+        assert tuple(ref.get_dimension()) == (n, m)
+        ulo, uhi = ours.get_control_limit()
+        if kind != "acrobot":                             # (the reference's Acrobot never sets umin: acrobot.py:29-30)
+            rlo, rhi = ref.get_control_limit()
+            np.testing.assert_allclose(ulo, rlo); np.testing.assert_allclose(uhi, rhi)
+        for _ in range(5):
+            x = rng.uniform(-2, 2, size=n)
+            if kind in ("cartpole", "acrobot"):
+                np.testing.assert_allclose(ours.get_M(x), ref.get_M(x), rtol=1e-12, atol=1e-12)
+                np.testing.assert_allclose(ours.get_C(x), ref.get_C(x), rtol=1e-12, atol=1e-12)
+                np.testing.assert_allclose(ours.get_G(x), ref.get_G(x), rtol=1e-12, atol=1e-12)
+                np.testing.assert_allclose(np.asarray(ours.get_B()).ravel(), np.asarray(ref.get_B()).ravel())
+            if kind == "acrobot":
+                assert abs(ours.energy(x) - ref.energy(x)) < 1e-10
+            if kind in ("cartpole", "quad2d", "quad10d"):
+                y = x * 3.0
+                a, b = y.copy(), y.copy()
+                ra, rb = ours.states_wrap(a), ref.states_wrap(b)
+                np.testing.assert_allclose(ra, rb, rtol=1e-12, atol=1e-12)
+                assert ra is a                                # NumPy input: wrapped in place and returned
+        if kind != "acrobot":                             # both constructors seed NumPy's global RNG with the config's seed
+            ref2, ours2 = make(), None
+            seq_ref = [ref2.get_initial_state() for _ in range(4)]
+            ours2 = make_dynamics(kind)
+            seq_ours = [ours2.get_initial_state() for _ in range(4)]
+            np.testing.assert_allclose(np.stack(seq_ours), np.stack(seq_ref), rtol=1e-12, atol=1e-12)
+    # linearisations about the goal (used once, on the host, for every model-based gain) against finite differences of
+    # the REFERENCE's dynamics_step
+    for kind, xf, uf in (("cartpole", np.array([0, np.pi, 0, 0.0]), np.zeros(1)), ("quad2d", np.zeros(6), np.array([4.905, 4.905])),
+                         ("quad10d", np.zeros(10), np.array([9.81 / 0.91, 0, 0]))):
+        ref, ours = makers[kind](), make_dynamics(kind)
+        A, B = ours.linearize(xf, uf)
+        h = 1e-6
+        n, m = ours.get_dimension()
+        Afd = np.stack([(ref.dynamics_step(xf + h * e, uf) - ref.dynamics_step(xf - h * e, uf)) / (2 * h) for e in np.eye(n)], axis=1)
+        Bfd = np.stack([(ref.dynamics_step(xf, uf + h * e) - ref.dynamics_step(xf, uf - h * e)) / (2 * h) for e in np.eye(m)], axis=1)
+        np.testing.assert_allclose(A, Afd, atol=1e-6)
+        np.testing.assert_allclose(B, Bfd, atol=1e-6)
