@@ -238,3 +238,39 @@ def test_host_side_class_methods_match_the_reference_classes():
         Bfd = np.stack([(ref.dynamics_step(xf, uf + h * e) - ref.dynamics_step(xf, uf - h * e)) / (2 * h) for e in np.eye(m)], axis=1)
         np.testing.assert_allclose(A, Afd, atol=1e-6)
         np.testing.assert_allclose(B, Bfd, atol=1e-6)
+
+
+def test_controller_gains_match_the_reference_classes():
+    """Constructor-time quantities of the model-based controllers (solved once on the host) against the reference's own
+    classes: LQR K / P, the hover controllers' K and trim input, the energy-shaping controllers' catch gains and energy."""
+    import importlib
+    from tests.helpers import make_controller, make_dynamics
+    # LQR on the double integrator (controller/lqr.py:25-26)
+    rdyn, odyn = R.make_linear(), make_dynamics("linear")
+    rlqr = importlib.import_module("controller.lqr").LQR(rdyn, np.eye(2), np.eye(1))
+    from q_learning_with_hjb_b200.controller.lqr import LQR
+    olqr = LQR(odyn, np.eye(2), np.eye(1))
+    np.testing.assert_allclose(olqr.K, rlqr.K, rtol=1e-10)
+    np.testing.assert_allclose(olqr.P, rlqr.P, rtol=1e-10)
+    # hover controllers (controller/quadrotors_model_based_controller.py:11-34, :40-71)
+    rmod = importlib.import_module("controller.quadrotors_model_based_controller")
+    from q_learning_with_hjb_b200.controller import quadrotors_model_based_controller as omod
+    for kind, rmake, cls, n, m in (("quad2d", R.make_quad2d, "Quadrotors2DHoveringController", 6, 2),
+                                   ("quad10d", R.make_quad10d, "NearHoverQuadcopterHoveringController", 10, 3)):
+        rc = getattr(rmod, cls)(rmake(), np.zeros(n), np.eye(n), np.eye(m))
+        oc = getattr(omod, cls)(make_dynamics(kind), np.zeros(n), np.eye(n), np.eye(m))
+        np.testing.assert_allclose(oc.K, rc.K, rtol=1e-9, atol=1e-12)
+        np.testing.assert_allclose(oc.uf, rc.uf, rtol=1e-12)
+        with pytest.raises(ValueError):
+            getattr(omod, cls)(make_dynamics(kind), np.ones(n), np.eye(n), np.eye(m))     # moving goal: rejected like :20-21
+    # energy-shaping controllers: the LQR catch (get_lqr_term) and the pole energy
+    rcp = importlib.import_module("controller.cartpole_energy_shaping").CartpoleEnergyShapingController(R.make_cartpole())
+    ocp = make_controller("cartpole_es", make_dynamics("cartpole"))
+    for a, b in zip(ocp.get_lqr_term(), rcp.get_lqr_term()):
+        np.testing.assert_allclose(a, b, rtol=1e-9, atol=1e-12)
+    x = np.array([0.3, 2.5, -0.4, 1.2])
+    assert abs(ocp.energy(x) - rcp.energy(x)) < 1e-14
+    rac = importlib.import_module("controller.acrobot_energy_shaping").AcrobotEnergyShapingController(R.make_acrobot())
+    oac = make_controller("acrobot_es", make_dynamics("acrobot"))
+    for a, b in zip(oac.get_lqr_term(), rac.get_lqr_term()):
+        np.testing.assert_allclose(a, b, rtol=1e-8, atol=1e-10)
