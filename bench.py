@@ -41,7 +41,7 @@ ROLLOUTS = {
                          label="C1: cartpole LQR balancing, 4096 initial states x 500 steps"),
     "cartpole_lqr_big": dict(sys="cartpole", ctl="cartpole_lqr", envs=1 << 24, T=500, flops={"euler": 50, "rk4": 151},
                              label="cartpole LQR balancing, 16M initial states x 500 steps"),
-    "acrobot_es": dict(sys="acrobot", ctl="acrobot_es", envs=1 << 22, T=2000, flops={"euler": 156, "rk4": 302},
+    "acrobot_es": dict(sys="acrobot", ctl="acrobot_es", envs=1 << 22, T=2000, flops={"euler": 156, "rk4": 302}, parity_T=25,
                        label="C3: acrobot energy-shaping swing-up, 4M envs x 2000 steps"),
     "quad10d_hover": dict(sys="quad10d", ctl="quad10d_hover", envs=1 << 23, T=1000, flops={"euler": 124, "rk4": 258},
                           label="10-D quadcopter hover LQR, 8M envs x 1000 steps"),
@@ -57,6 +57,43 @@ def synthetic_x0_host(sysname, count, seed):
             "linear": ([0, 0], [1, 1])}[sysname]
     mean, std = np.float32(spec[0]), np.float32(spec[1])
     return (rng.uniform(-1, 1, size=(count, len(mean))).astype(np.float32) * std + mean).astype(np.float32)
+
+
+def rollout_parity(w, integ, fast=True, envs=4096, seed=1234, record_stride=0):
+    """Untimed parity leg of the timed plan: the SAME kernel instantiation (fast / accurate trigonometry, final state +
+    Q = I, R = I cost, record stride) on the first `envs` environments of the SAME synthetic x0, against the oracle
+    (oracle/rollout_oracle.py, NumPy fp64) over the workload's horizon — the acrobot (chaotic) over its stated 50 steps.
+    Errors are |a - b| / max(1, |b|), angles modulo 2 pi (tests/helpers.py::rel_err).  Bounds: final states 1e-5 (the
+    north star's trajectory bound); the accumulated cost 1e-4 (the bound of the notebook known-answer tests: l contains
+    u = -K dx, which amplifies the state error by |K| — 34 for the cart-pole)."""
+    import torch
+    from oracle import rollout_oracle as O
+    from tests.helpers import WRAP_IDX, make_controller, make_dynamics, rel_err
+    from q_learning_with_hjb_b200.rollout import BatchedRollout, RunningCost
+
+    T = w.get("parity_T", w["T"])
+    dyn = make_dynamics(w["sys"])
+    dyn.fast_trig = bool(fast)
+    ctl = make_controller(w["ctl"], dyn)
+    n, m = dyn.get_dimension()
+    xf = getattr(ctl, "xf", np.zeros(n)); uf = getattr(ctl, "uf", np.zeros(m))
+    plan = BatchedRollout(dyn, ctl, envs, T, integrator=integ, record_stride=record_stride,
+                          cost=RunningCost(np.eye(n), np.eye(m), xf, uf))
+    x0 = synthetic_x0_host(w["sys"], envs, seed)
+    res = plan.launch(torch.as_tensor(x0).cuda())
+    torch.cuda.synchronize()
+    osys = O.std_system(w["sys"])
+    octl = O.std_controller(w["ctl"], osys)
+    ocost = O.OracleCost(np.eye(n), np.eye(m), np.asarray(xf, dtype=np.float64), np.asarray(uf, dtype=np.float64))
+    _, _, xfo, Jo = O.rollout(osys, octl, x0.astype(np.float64), T, integ, record_stride=0, cost=ocost)
+    ex = rel_err(res.x_final.cpu().numpy(), xfo, WRAP_IDX[w["sys"]])
+    ec = rel_err(res.cost.cpu().numpy(), Jo)
+    return {"against": "oracle/rollout_oracle.py (NumPy fp64 restatement of the reference loop)", "envs": envs, "horizon": T,
+            "integrator": integ, "kernel_variant": plan.kernel_variant(), "max_rel_err_x_final": ex,
+            "max_rel_err_cost": ec, "max_rel_err": ex, "tolerance": 1e-5, "tolerance_cost": 1e-4,
+            "ok": bool(ex <= 1e-5 and ec <= 1e-4),
+            "checksum_mean_cost": float(res.cost.double().mean()), "oracle_mean_cost": float(Jo.mean()),
+            "error_measure": "|a - b| / max(1, |b|), angles modulo 2 pi"}
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -260,6 +297,12 @@ def run_rollout(args, w, integ):
     checksum = float(cost_host.double().mean())
     h2d_bytes, d2h_bytes = plan.h2d_bytes(), plan.d2h_bytes()
 
+    # ---- untimed: the timed instantiation against the oracle on the first 4096 environments of the same x0 ----
+    parity = None
+    if rank == 0 and not args.no_parity:
+        parity = rollout_parity(w, integ, fast=not args.accurate_trig, envs=min(4096, envs), seed=1234 + rank,
+                                record_stride=args.record_stride)
+
     times = torch.tensor([total_ms, e2e_ms], device="cuda", dtype=torch.float64)
     if world > 1:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
@@ -330,14 +373,14 @@ def run_rollout(args, w, integ):
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": w["label"], "envs_per_gpu": envs, "horizon": T, "integrator": integ,
                        "record": "final state + per-env cost" if args.record_stride == 0 else f"every {args.record_stride} steps",
-                       "trig": "accurate" if args.accurate_trig else "mufu", "parallelism": f"env-shard x{world}",
+                       "trig": "libdevice" if args.accurate_trig else "in-line polynomial sin/cos + MUFU.RCP (fast_trig)", "parallelism": f"env-shard x{world}",
                        "l2": "inputs larger than L2 (x0 >= 400 MB per launch)" if envs * n * 4 > 126e6 else "small workload",
                        "seed": "1234 + rank"},
             "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": h2d_bytes,
                     "d2h_bytes_per_step": d2h_bytes, "ms_per_step": e2e_ms / args.steps, "checksum_mean_cost": checksum},
             "gpu_launches": args.steps,
             "kernel_ms": kernel_ms,
-            "roofline": roof, "cpu_baseline": cpu, "clocks": clk,
+            "roofline": roof, "cpu_baseline": cpu, "clocks": clk, "parity": parity,
             "vhjb": vhjb,
         }
         print(json.dumps(line), flush=True)
@@ -604,6 +647,7 @@ def main():
     ap.add_argument("--record-stride", type=int, default=0)
     ap.add_argument("--accurate-trig", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the untimed oracle check of the timed instantiation")
     ap.add_argument("--no-vhjb", action="store_true", help="skip the secondary vhjb measurement of the default line")
     ap.add_argument("--watchdog", type=int, default=900,
                     help="seconds after which a hung run dumps every thread's stack to stderr and exits (0 = off)")

@@ -106,7 +106,8 @@ typedef enum hjb_integrator {
 typedef struct hjb_rollout_opts {
   int32_t integrator;    /* hjb_integrator */
   int32_t record_stride; /* 0: no trajectory output; s > 0: record x after every s-th step (and x0)      */
-  int32_t fast_trig;     /* 1: MUFU sin/cos/rcp (__sinf ...), 0: IEEE-accurate libdevice versions        */
+  int32_t fast_trig;     /* 1: in-line sin/cos (quadrant reduction + minimax polynomials, 7e-8 abs) and
+                            MUFU.RCP, round-to-nearest wrap; 0: libdevice sincosf / tanf, IEEE division    */
   int32_t box_enabled;   /* freeze an environment once wrap(x - box_xf) leaves [box_lo, box_hi]
                             (controller/vhjb.py:176-181; examples/drone_hovering.ipynb cell 15:27)        */
   float box_xf[HJB_MAX_N], box_lo[HJB_MAX_N], box_hi[HJB_MAX_N];
@@ -129,6 +130,15 @@ typedef struct hjb_rollout_opts {
 int hjb_rollout(const hjb_system* sys, const hjb_control* ctl, const hjb_cost* cost_spec,
                 const hjb_rollout_opts* opts, const float* x0, int64_t N, int32_t T, float* xs, float* us,
                 float* x_final, float* cost, int32_t* steps, void* stream);
+
+/*
+ * Which kernel instantiation hjb_rollout dispatches to for these arguments (no device work; used by the parity tests
+ * and bench.py to state WHICH instantiation a number belongs to).  `recorded` = xs or us requested.
+ *   out[0] integrator  out[1] recorded (0/1)  out[2] cost mode (0 none, 1 diagonal, 2 dense, 3 unit: Q = I, R = I)
+ *   out[3] box (0/1)   out[4] fast_trig (0/1) out[5] controller clips (0/1)
+ */
+int hjb_rollout_variant(const hjb_system* sys, const hjb_control* ctl, const hjb_cost* cost_spec,
+                        const hjb_rollout_opts* opts, int32_t recorded, int32_t out[6]);
 
 /*
  * Batched single-step pieces of the same path, for per-step use and per-step parity checks:

@@ -73,6 +73,8 @@ SYMBOLS = {
     "hjb_status_string": (C.c_char_p, [C.c_int]),
     "hjb_rollout": (C.c_int, [C.POINTER(HjbSystem), C.POINTER(HjbControl), C.POINTER(HjbCost),
                               C.POINTER(HjbRolloutOpts), _P, C.c_int64, C.c_int32, _P, _P, _P, _P, _P, _P]),
+    "hjb_rollout_variant": (C.c_int, [C.POINTER(HjbSystem), C.POINTER(HjbControl), C.POINTER(HjbCost),
+                                      C.POINTER(HjbRolloutOpts), C.c_int32, C.POINTER(C.c_int32)]),
     "hjb_dynamics": (C.c_int, [C.POINTER(HjbSystem), C.c_int32, C.c_int32, _P, _P, C.c_int64, _P, _P, _P, _P, _P]),
     "hjb_control_efforts": (C.c_int, [C.POINTER(HjbSystem), C.POINTER(HjbControl), C.c_int32, _P, C.c_int64, _P, _P]),
     "hjb_states_wrap": (C.c_int, [C.POINTER(HjbSystem), _P, C.c_int64, _P]),

@@ -13,8 +13,8 @@ control, the Hamiltonian residual, both losses and the full parameter gradient a
   optimizer_state   ``AdamState(count, mu, nu)`` — the fields of optax's ScaleByAdamState
 
 ``params_update`` updates these buffers IN PLACE and returns them (the reference rebinds the returned values, so
-both styles work).  Host-side bookkeeping stays on the host as in the reference: RNG seeding, the replay buffer
-(a ring of NumPy arrays instead of deque + torch DataLoader), the SGDR schedule, Riccati setup.
+both styles work).  Host-side bookkeeping stays on the host as in the reference: RNG seeding, the SGDR schedule, the
+Riccati setup.  The replay buffer (the reference's deque + torch DataLoader) is ``DeviceReplayBuffer``, a ring in HBM.
 
 Several GPUs: when ``torch.distributed`` is initialised, ``params_update`` treats ``xs`` as this rank's shard of
 the batch: the two done-counts and then the gradient are all-reduced (sum), every rank applies the same Adam step.
@@ -661,44 +661,3 @@ class DeviceReplayBuffer:
         torch = self.torch
         order = (torch.arange(self.size, device="cuda") + self.head) % self.capacity
         return self.xs[order].cpu().numpy(), self.costs[order].cpu().numpy(), self.dones[order].cpu().numpy()
-
-
-class ReplayBuffer:
-    """Host version of the same ring (NumPy); the reference semantics in plain Python for tests and CPU-side tooling
-    (deque(maxlen) + DataLoader with shuffle=True, drop_last=True; vhjb.py:62-73, :154)."""
-
-    def __init__(self, state_dim: int, max_size: int):
-        self.max_size = int(max_size)
-        cap = min(self.max_size, 1 << 16)
-        self.xs = np.zeros((cap, state_dim), dtype=np.float32)
-        self.costs = np.zeros(cap, dtype=np.float32)
-        self.dones = np.zeros(cap, dtype=np.float32)
-        self.size, self.head = 0, 0
-
-    def __len__(self):
-        return self.size
-
-    def _grow(self):
-        cap = min(self.max_size, 2 * self.xs.shape[0])
-        for name in ("xs", "costs", "dones"):
-            old = getattr(self, name)
-            new = np.zeros((cap, *old.shape[1:]), dtype=old.dtype)
-            new[: old.shape[0]] = old
-            setattr(self, name, new)
-
-    def append(self, x, cost, done):
-        if self.size < self.max_size and self.size == self.xs.shape[0]:
-            self._grow()
-        if self.size < self.max_size:
-            i = self.size
-            self.size += 1
-        else:  # full: overwrite the oldest (deque(maxlen) semantics)
-            i = self.head
-            self.head = (self.head + 1) % self.max_size
-        self.xs[i], self.costs[i], self.dones[i] = x, cost, done
-
-    def batches(self, batch_size: int):
-        perm = np.random.permutation(self.size)
-        for b in range(self.size // batch_size):
-            idx = perm[b * batch_size:(b + 1) * batch_size]
-            yield self.xs[idx], self.costs[idx], self.dones[idx]

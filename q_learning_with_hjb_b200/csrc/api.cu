@@ -270,6 +270,19 @@ int hjb_rollout(const hjb_system* sys, const hjb_control* ctl, const hjb_cost* c
   return to_status(e);
 }
 
+int hjb_rollout_variant(const hjb_system* sys, const hjb_control* ctl, const hjb_cost* cost_spec, const hjb_rollout_opts* opts,
+                        int32_t recorded, int32_t out[6]) {
+  if (!sys || !ctl || !opts || !out) return HJB_ERR_BAD_ARG;
+  if (!dims_ok(sys)) return HJB_ERR_UNSUPPORTED;
+  out[0] = opts->integrator;
+  out[1] = recorded != 0;
+  out[2] = cost_mode(sys, cost_spec);
+  out[3] = opts->box_enabled != 0;
+  out[4] = opts->fast_trig != 0;
+  out[5] = ctl->kind == HJB_CTL_FEEDBACK ? (ctl->clip != 0) : 1;
+  return HJB_OK;
+}
+
 int hjb_dynamics(const hjb_system* sys, int32_t integrator, int32_t fast_trig, const float* x, const float* u, int64_t B,
                  float* f, float* g, float* xdot, float* x_next, void* stream) {
   if (!sys || B < 0) return HJB_ERR_BAD_ARG;

@@ -124,8 +124,8 @@ __device__ __forceinline__ float running_cost(const DevCost& pc, const float* c0
 }
 
 // one integration step of Dynamics.simulate AFTER the clip, on the internal state: z <- wrap(step(z, u))
-template <class S, int INTEG>
-__device__ __forceinline__ void integrate(const DevSys& ps, float* x, const typename S::Trig& tr0, const float* u) {
+template <class S, int INTEG, class TC>
+__device__ __forceinline__ void integrate(const DevSys& ps, float* x, const typename S::Trig& tr0, const float* u, const TC& tc) {
   constexpr int N = S::N;
   if constexpr (INTEG == HJB_INT_DISCRETE) {
     float d[N];
@@ -144,15 +144,16 @@ __device__ __forceinline__ void integrate(const DevSys& ps, float* x, const type
     S::xdot(ps, x, tr0, u, k);
 #pragma unroll
     for (int i = 0; i < N; ++i) { acc[i] = k[i]; xt[i] = fmaf(hh, k[i], x[i]); }
-    S::trig(ps, xt, tr);
+    // (stage states are not wrapped: GUARD = true sends arguments beyond the trig table's range to the in-line path)
+    S::template trig<true>(ps, xt, tr, tc);
     S::xdot(ps, xt, tr, u, k);
 #pragma unroll
     for (int i = 0; i < N; ++i) { acc[i] = fmaf(2.f, k[i], acc[i]); xt[i] = fmaf(hh, k[i], x[i]); }
-    S::trig(ps, xt, tr);
+    S::template trig<true>(ps, xt, tr, tc);
     S::xdot(ps, xt, tr, u, k);
 #pragma unroll
     for (int i = 0; i < N; ++i) { acc[i] = fmaf(2.f, k[i], acc[i]); xt[i] = fmaf(h, k[i], x[i]); }
-    S::trig(ps, xt, tr);
+    S::template trig<true>(ps, xt, tr, tc);
     S::xdot(ps, xt, tr, u, k);
     const float h6 = ps.dt * (1.0f / 6.0f);
 #pragma unroll
@@ -206,10 +207,14 @@ __device__ __forceinline__ bool inside_box(const DevBox& b, const float* z) {
   return in;
 }
 
+// Persistent CTAs: the grid is at most kRolloutCtasPerSm x SM count and every CTA walks over blocks of 256 environments
+// (block b, b + gridDim.x, ...).  What a CTA sets up once — the trig tables in shared memory — is then paid ~1200 times
+// per launch instead of once per 256 environments.
+constexpr int kRolloutCtasPerSm = 8;
+
 template <class S, class C, int INTEG, bool REC, int COST, bool BOX>
 __global__ void __launch_bounds__(256) rollout_kernel(const __grid_constant__ RolloutArgs a) {
   constexpr int N = S::N, M = S::M;
-  const int64_t env = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   // recorded rows go through the warp's staging buffers when the whole warp is in range and every time slice starts
   // on a 16-byte boundary (a.staged: N W divisible by 4 floats, 16-byte aligned bases); otherwise per-thread stores
   // Measured on B200 (bench.py --record-stride 1, staged against direct): n = 10 / m = 3 rows 6248 against 2399 GB/s;
@@ -219,11 +224,48 @@ __global__ void __launch_bounds__(256) rollout_kernel(const __grid_constant__ Ro
   constexpr bool kStageU = REC && (M % 2 != 0) && (M > 1);
   __shared__ __align__(128) float stage_x[kStageX ? 8 * 2 * 32 * N : 1];
   __shared__ __align__(128) float stage_u[kStageU ? 8 * 2 * 32 * M : 1];
+  // fast instantiations of systems with angles: sin / cos from per-CTA tables (hjb_common.cuh::sincos_tab)
+  constexpr bool kTab = S::kFast && S::NANG > 0;
+  constexpr int NT = kTab ? trig_tables<S>() : 0;
+  __shared__ __align__(16) float2 trig_tab[kTab ? NT * kTrigSize : 1];
+  using TC = std::conditional_t<kTab, TableTrig, DirectTrig<S::kFast>>;
+  TC tc;
+  if constexpr (kTab) {
+    for (int i = threadIdx.x; i < NT * kTrigSize; i += blockDim.x) {
+      const int k = i / kTrigSize, j = i - k * kTrigSize;
+      const double off = k == 2 ? (double)a.sys.aoff[0] + (double)a.sys.aoff[1] : (double)a.sys.aoff[k];
+      double sv, cv;
+      sincos((double)(j - kTrigHalf) * (1.0 / (double)(1 << kTrigLog2)) + off, &sv, &cv);
+      trig_tab[i] = make_float2((float)sv, (float)cv);
+    }
+    __syncthreads();
+    tc.tab = trig_tab;
+  }
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+
+  // (+ a zero that only the launch knows: a plain copy of a kernel parameter is re-loaded by ptxas wherever it is used)
+  float c0r[N], r0r[M];
+  // Measured: worth it for the 13 terms of the 10-D quadcopter (112 -> 103 instructions per step, 2.91e11 -> 3.10e11
+  // env-steps/s); for the narrower systems the compiler keeps the constants in registers by itself and the detour costs
+  // ~3 % (C4), so those read the parameters directly.
+  constexpr bool kRegConsts = COST == COST_DIAG && (N + M) > 8;
+  const float opaque0 = kRegConsts && a.T < 0 ? 1.f : 0.f;
+#pragma unroll
+  for (int i = 0; i < N; ++i) c0r[i] = COST == COST_DIAG ? (kRegConsts ? a.cost.c0[i] + opaque0 : a.cost.c0[i]) : 0.f;
+#pragma unroll
+  for (int k = 0; k < M; ++k) r0r[k] = COST == COST_DIAG ? (kRegConsts ? a.cost.r0[k] + opaque0 : a.cost.r0[k]) : 0.f;
+  bool cost_wraps = false;
+  if constexpr (COST != COST_NONE) {
+#pragma unroll
+    for (int k = 0; k < S::NANG; ++k) cost_wraps = cost_wraps || (a.cost.dang[k] != 0.f);
+  }
+
+  for (int64_t blk = blockIdx.x; blk * 256 < a.N; blk += gridDim.x) {
+  const int64_t env = blk * 256 + threadIdx.x;
   const int64_t env0 = env - lane;
   bool staged = false;
   if constexpr (kStageX || kStageU) staged = a.staged != 0 && env0 + 32 <= a.N;
-  if (env >= a.N) return;
+  if (env >= a.N) break;    // the ragged tail of the last block (no block-wide barrier below this point)
 
   float z[N];  // internal state
   {
@@ -240,23 +282,12 @@ __global__ void __launch_bounds__(256) rollout_kernel(const __grid_constant__ Ro
   int64_t rec = 1;      // next trajectory slot
   int32_t phase = 0;    // steps since the last recorded state
 
-  // (+ a zero that only the launch knows: a plain copy of a kernel parameter is re-loaded by ptxas wherever it is used)
-  float c0r[N], r0r[M];
-  // Measured: worth it for the 13 terms of the 10-D quadcopter (112 -> 103 instructions per step, 2.91e11 -> 3.10e11
-  // env-steps/s); for the narrower systems the compiler keeps the constants in registers by itself and the detour costs
-  // ~3 % (C4), so those read the parameters directly.
-  constexpr bool kRegConsts = COST == COST_DIAG && (N + M) > 8;
-  const float opaque0 = kRegConsts && a.T < 0 ? 1.f : 0.f;
-#pragma unroll
-  for (int i = 0; i < N; ++i) c0r[i] = COST == COST_DIAG ? (kRegConsts ? a.cost.c0[i] + opaque0 : a.cost.c0[i]) : 0.f;
-#pragma unroll
-  for (int k = 0; k < M; ++k) r0r[k] = COST == COST_DIAG ? (kRegConsts ? a.cost.r0[k] + opaque0 : a.cost.r0[k]) : 0.f;
   auto run = [&](auto cwrap) {
   constexpr bool CWRAP = decltype(cwrap)::value;
   for (int32_t t = 0; t < a.T; ++t) {
     if constexpr (BOX) alive = alive && inside_box<S>(a.box, z);
     typename S::Trig tr;
-    S::trig(a.sys, z, tr);
+    S::template trig<false>(a.sys, z, tr, tc);
     float u[M];
     C::template control<S>(a.sys, a.ctl, z, tr, u);
     if constexpr (REC) {
@@ -272,7 +303,7 @@ __global__ void __launch_bounds__(256) rollout_kernel(const __grid_constant__ Ro
       float l = 0.f;
       if constexpr (COST != COST_NONE) l = running_cost<S, COST, CWRAP>(a.cost, c0r, r0r, z, u, 0.f);
       if constexpr (!C::kClips) clip_u<S>(a.sys, u);
-      integrate<S, INTEG>(a.sys, zn, tr, u);
+      integrate<S, INTEG>(a.sys, zn, tr, u, tc);
       if (alive) {
 #pragma unroll
         for (int i = 0; i < N; ++i) z[i] = zn[i];
@@ -283,7 +314,7 @@ __global__ void __launch_bounds__(256) rollout_kernel(const __grid_constant__ Ro
       if constexpr (COST != COST_NONE) J = running_cost<S, COST, CWRAP>(a.cost, c0r, r0r, z, u, J);
       // Dynamics.simulate's own clip (dynamics_basic.py:118); idempotent when the controller already clipped
       if constexpr (!C::kClips) clip_u<S>(a.sys, u);
-      integrate<S, INTEG>(a.sys, z, tr, u);
+      integrate<S, INTEG>(a.sys, z, tr, u, tc);
     }
     if constexpr (REC) {
       if (++phase == a.stride) {
@@ -299,11 +330,6 @@ __global__ void __launch_bounds__(256) rollout_kernel(const __grid_constant__ Ro
     }
   }
   };
-  bool cost_wraps = false;
-  if constexpr (COST != COST_NONE) {
-#pragma unroll
-    for (int k = 0; k < S::NANG; ++k) cost_wraps = cost_wraps || (a.cost.dang[k] != 0.f);
-  }
   if (COST != COST_NONE && cost_wraps) run(std::true_type{});
   else run(std::false_type{});
   if constexpr (kStageX || kStageU) {
@@ -316,11 +342,22 @@ __global__ void __launch_bounds__(256) rollout_kernel(const __grid_constant__ Ro
   }
   if (a.cost_out) a.cost_out[env] = J * a.sys.dt;
   if (a.steps_out) a.steps_out[env] = BOX ? nsteps : a.T;
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
 // launchers (one translation unit per problem instantiates these)
 // ------------------------------------------------------------------------------------------------
+inline int rollout_sm_count() {
+  static int cached = 0;
+  if (cached == 0) {
+    int dev = 0, sms = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess)
+      cached = sms;
+  }
+  return cached > 0 ? cached : 148;
+}
+
 struct RolloutVariant {
   int integrator;  // hjb_integrator
   bool rec;
@@ -331,8 +368,9 @@ struct RolloutVariant {
 template <class S, class C, int INTEG, bool REC, int COST, bool BOX>
 inline cudaError_t launch_one(const RolloutArgs& a, cudaStream_t st) {
   const int block = 256;
-  const int64_t grid = (a.N + block - 1) / block;
-  if (grid > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
+  int64_t grid = (a.N + block - 1) / block;
+  const int64_t resident = (int64_t)kRolloutCtasPerSm * rollout_sm_count();
+  if (grid > resident) grid = resident;
   rollout_kernel<S, C, INTEG, REC, COST, BOX><<<(unsigned)grid, block, 0, st>>>(a);
   return cudaGetLastError();
 }

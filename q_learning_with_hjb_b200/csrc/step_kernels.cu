@@ -36,7 +36,7 @@ __global__ void __launch_bounds__(256) dynamics_kernel(const __grid_constant__ D
   }
   if (a.x_next) {
     clip_u<S>(a.sys, u);           // simulate clips (dynamics_basic.py:118)
-    integrate<S, INTEG>(a.sys, x, tr, u);
+    integrate<S, INTEG>(a.sys, x, tr, u, DirectTrig<S::kFast>{});
     float xo[N];
     to_external<S>(a.sys, x, xo);
     store_row<N>(a.x_next, i, xo);
@@ -205,7 +205,7 @@ __global__ void __launch_bounds__(256) policy_step_kernel(const __grid_constant_
     typename S::Trig tr;
     S::trig(a.sys, x, tr);
     clip_u<S>(a.sys, u);
-    integrate<S, HJB_INT_EULER>(a.sys, x, tr, u);
+    integrate<S, HJB_INT_EULER>(a.sys, x, tr, u, DirectTrig<S::kFast>{});
     float xo[N];
     to_external<S>(a.sys, x, xo);
     store_row<N>(a.x, i, xo);

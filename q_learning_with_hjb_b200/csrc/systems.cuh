@@ -21,6 +21,36 @@
 
 namespace hjb {
 
+// How a kernel evaluates the trigonometry of a state.  angle(k, z, aoff, s, c) returns sin / cos of (z + aoff) for the
+// system's k-th angle argument (the acrobot has a third: q1 + q2 with offset aoff0 + aoff1).
+//   DirectTrig  in line: polynomial (FAST) or libdevice — the per-step kernels and the vhjb pass
+//   TableTrig   the rollout kernels' shared-memory tables (hjb_common.cuh::sincos_tab; aoff baked into the table);
+//               GUARD: arguments may leave the table's range (RK4 stage states are not wrapped) -> in-line fallback
+template <bool FAST>
+struct DirectTrig {
+  template <bool GUARD = false>
+  __device__ __forceinline__ void angle(int, float z, float aoff, float& s, float& c) const { sincos_<FAST>(z + aoff, s, c); }
+  template <bool GUARD = false>
+  __device__ __forceinline__ float tangent(int, float z, float aoff) const { return tan_<FAST>(z + aoff); }
+};
+struct TableTrig {
+  const float2* tab;   // [tables][kTrigSize], shared memory
+  template <bool GUARD = false>
+  __device__ __forceinline__ void angle(int k, float z, float aoff, float& s, float& c) const {
+    if (GUARD && !(fabsf(z) <= kTrigRange)) sincos_poly(z + aoff, s, c);
+    else sincos_tab(tab + k * kTrigSize, z, s, c);
+  }
+  template <bool GUARD = false>
+  __device__ __forceinline__ float tangent(int k, float z, float aoff) const {
+    float s, c;
+    angle<GUARD>(k, z, aoff, s, c);
+    return s * rcp_approx(c);
+  }
+};
+// number of tables a system needs
+template <class S>
+constexpr int trig_tables() { return S::KIND == HJB_SYS_ACROBOT ? 3 : S::NANG; }
+
 // states_wrap on the angle components (cartpole.py:52-64, acrobot.py:72-81, quadrotors.py:48-70,151-170)
 template <class S>
 __device__ __forceinline__ void wrap_state(float* z) {
@@ -54,7 +84,8 @@ struct LinearSys {
   static constexpr int KIND = HJB_SYS_LINEAR;
   static __device__ __forceinline__ constexpr int ang(int) { return 0; }
   struct Trig {};
-  static __device__ __forceinline__ void trig(const DevSys&, const float*, Trig&) {}
+  template <bool GUARD = false, class TC = DirectTrig<FAST>>
+  static __device__ __forceinline__ void trig(const DevSys&, const float*, Trig&, const TC& = TC{}) {}
   // A x + B u   (also the exact-ZOH update when A, B are the discretised matrices)
   static __device__ __forceinline__ void xdot(const DevSys& p, const float* x, const Trig&, const float* u, float* d) {
 #pragma unroll
@@ -92,8 +123,9 @@ struct CartpoleSys {
   static constexpr int KIND = HJB_SYS_CARTPOLE;
   static __device__ __forceinline__ constexpr int ang(int) { return 1; }
   struct Trig { float s, c; };
-  static __device__ __forceinline__ void trig(const DevSys& p, const float* z, Trig& t) {
-    sincos_<FAST>(z[1] + p.aoff[0], t.s, t.c);
+  template <bool GUARD = false, class TC = DirectTrig<FAST>>
+  static __device__ __forceinline__ void trig(const DevSys& p, const float* z, Trig& t, const TC& tc = TC{}) {
+    tc.template angle<GUARD>(0, z[1], p.aoff[0], t.s, t.c);
   }
   static __device__ __forceinline__ void xdot(const DevSys& p, const float* x, const Trig& t, const float* u, float* d) {
     const float m12 = p.c[1] * t.c;
@@ -134,11 +166,11 @@ struct AcrobotSys {
   static constexpr int KIND = HJB_SYS_ACROBOT;
   static __device__ __forceinline__ constexpr int ang(int k) { return k; }
   struct Trig { float s1, c1, s2, c2, s12, c12; };
-  static __device__ __forceinline__ void trig(const DevSys& p, const float* z, Trig& t) {
-    const float q1 = z[0] + p.aoff[0], q2 = z[1] + p.aoff[1];
-    sincos_<FAST>(q1, t.s1, t.c1);
-    sincos_<FAST>(q2, t.s2, t.c2);
-    sincos_<FAST>(q1 + q2, t.s12, t.c12);
+  template <bool GUARD = false, class TC = DirectTrig<FAST>>
+  static __device__ __forceinline__ void trig(const DevSys& p, const float* z, Trig& t, const TC& tc = TC{}) {
+    tc.template angle<GUARD>(0, z[0], p.aoff[0], t.s1, t.c1);
+    tc.template angle<GUARD>(1, z[1], p.aoff[1], t.s2, t.c2);
+    tc.template angle<GUARD>(2, z[0] + z[1], p.aoff[0] + p.aoff[1], t.s12, t.c12);
   }
   struct Terms { float m11, m12, m22, h1, h2; };  // h = C dq + G
   static __device__ __forceinline__ void terms(const DevSys& p, const float* x, const Trig& t, Terms& r) {
@@ -196,8 +228,9 @@ struct Quad2DSys {
   static constexpr int KIND = HJB_SYS_QUAD2D;
   static __device__ __forceinline__ constexpr int ang(int) { return 2; }
   struct Trig { float s, c; };
-  static __device__ __forceinline__ void trig(const DevSys& p, const float* z, Trig& t) {
-    sincos_<FAST>(z[2] + p.aoff[0], t.s, t.c);
+  template <bool GUARD = false, class TC = DirectTrig<FAST>>
+  static __device__ __forceinline__ void trig(const DevSys& p, const float* z, Trig& t, const TC& tc = TC{}) {
+    tc.template angle<GUARD>(0, z[2], p.aoff[0], t.s, t.c);
   }
   static __device__ __forceinline__ void xdot(const DevSys& p, const float* x, const Trig& t, const float* u, float* d) {
     const float sm = (u[0] + u[1]) * p.c[1];
@@ -230,9 +263,10 @@ struct Quad10DSys {
   static constexpr int KIND = HJB_SYS_QUAD10D;
   static __device__ __forceinline__ constexpr int ang(int k) { return 3 + k; }
   struct Trig { float tx, ty; };
-  static __device__ __forceinline__ void trig(const DevSys& p, const float* z, Trig& t) {
-    t.tx = tan_<FAST>(z[3] + p.aoff[0]);
-    t.ty = tan_<FAST>(z[4] + p.aoff[1]);
+  template <bool GUARD = false, class TC = DirectTrig<FAST>>
+  static __device__ __forceinline__ void trig(const DevSys& p, const float* z, Trig& t, const TC& tc = TC{}) {
+    t.tx = tc.template tangent<GUARD>(0, z[3], p.aoff[0]);
+    t.ty = tc.template tangent<GUARD>(1, z[4], p.aoff[1]);
   }
   static __device__ __forceinline__ void xdot(const DevSys& p, const float* x, const Trig& t, const float* u, float* d) {
 #pragma unroll

@@ -64,12 +64,14 @@ __global__ void __launch_bounds__(256) count_stage1(const float* __restrict__ do
     part[blockIdx.x] = t;
   }
 }
-__global__ void count_stage2(const float* __restrict__ part, int nblk, int64_t B, float eps, float* __restrict__ norm) {
+// min_time: the plain mean over the batch of the double-integrator notebook (cell 11) — no boundary term, norm[1] = 1
+__global__ void count_stage2(const float* __restrict__ part, int nblk, int64_t B, float eps, int min_time,
+                             float* __restrict__ norm) {
   if (threadIdx.x == 0 && blockIdx.x == 0) {
     double t = 0.0;
     for (int i = 0; i < nblk; ++i) t += (double)part[i];
     norm[0] = (float)((double)B - t + (double)eps);
-    norm[1] = (float)(t + (double)eps);
+    norm[1] = min_time ? 1.0f : (float)(t + (double)eps);
   }
 }
 
@@ -319,7 +321,7 @@ int hjb_vhjb_count(const float* dones, int64_t B, float eps, float* norm, void* 
   const int nblk = sm_count();
   float* part = static_cast<float*>(workspace);
   count_stage1<<<nblk, 256, 0, st>>>(dones, B, part);
-  count_stage2<<<1, 32, 0, st>>>(part, nblk, B, eps, norm);
+  count_stage2<<<1, 32, 0, st>>>(part, nblk, B, eps, 0, norm);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? HJB_OK : (int)e;
 }
@@ -384,11 +386,7 @@ int hjb_vhjb_train_step(const hjb_system* sys, const hjb_vnet* net, const hjb_ta
     const int nblk = sm_count();
     float* part = static_cast<float*>(workspace);
     count_stage1<<<nblk, 256, 0, st>>>(dones, B, part);
-    count_stage2<<<1, 32, 0, st>>>(part, nblk, B, min_time ? 0.f : task->eps, norm);
-    if (min_time) {
-      const float one = 1.0f;   // plain mean over the batch: no boundary term (double_integrator notebook, cell 11)
-      cudaMemcpyAsync(norm + 1, &one, sizeof(float), cudaMemcpyHostToDevice, st);
-    }
+    count_stage2<<<1, 32, 0, st>>>(part, nblk, B, min_time ? 0.f : task->eps, min_time, norm);
   }
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return (int)e;

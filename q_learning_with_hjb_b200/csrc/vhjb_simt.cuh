@@ -197,8 +197,10 @@ __global__ void __launch_bounds__(VTHREADS, 1) vhjb_kernel(const __grid_constant
   float hjb_sum = 0.f, term_sum = 0.f;  // warp 0 only
   float inv_norm0 = 0.f, inv_norm1 = 0.f;
   if constexpr (GRAD) {
-    inv_norm0 = 1.0f / __ldg(a.norm);
-    inv_norm1 = 1.0f / __ldg(a.norm + 1);
+    // (eps = 0 with an all-done or all-interior shard: norm = 0 -> weight 0, not 0 * inf = NaN on the masked terms)
+    const float nm0 = __ldg(a.norm), nm1 = __ldg(a.norm + 1);
+    inv_norm0 = nm0 > 0.f ? 1.0f / nm0 : 0.f;
+    inv_norm1 = nm1 > 0.f ? 1.0f / nm1 : 0.f;
   }
   __syncthreads();
 

@@ -182,14 +182,17 @@ __device__ __forceinline__ float tc_d2(float st) {
 
 // Streamed batches: block until the piece that holds `tile` has landed (flags written by the copy engine behind each
 // piece, in order, so a set flag implies the earlier ones).
-// The poll is bounded (~seconds): a caller that never sets a flag gets wrong numbers, not a hung GPU.
-__device__ __forceinline__ void wait_piece(const VhjbArgs& a, int64_t tile, int64_t& next_tile, int& piece) {
+// The poll is bounded (~seconds) so that a caller who never sets a flag cannot hang the GPU; a poll that gives up sets
+// `failed` (sticky: later pieces are not waited for), the CTA reports it in partial[P + 3], the reduction poisons the
+// loss sums with NaN and raises the workspace's failure word, and the guarded Adam update (hjb_vhjb_adam_guarded)
+// skips the step: a gradient computed from data that never arrived is never applied.
+__device__ __forceinline__ void wait_piece(const VhjbArgs& a, int64_t tile, int64_t& next_tile, int& piece, bool& failed) {
   // next_tile = first tile of the first piece not yet known to be there (LLONG_MAX when the batch is resident): the
   // common case is one 64-bit compare
   while (tile >= next_tile) {
     // ONE lane per warp polls, 2 us apart: ~1200 pollers per GPU.  (Every lane polling 100 ns apart — 38,000 threads on
     // one L2 line — starved the copy engine's own write of that line: the flag was not seen for seconds.)
-    if ((threadIdx.x & 31) == 0) {
+    if ((threadIdx.x & 31) == 0 && !failed) {
       const int* f = a.ready + piece;
       int v = 0;
       for (unsigned spins = 0; spins < (1u << 22); ++spins) {
@@ -197,10 +200,35 @@ __device__ __forceinline__ void wait_piece(const VhjbArgs& a, int64_t tile, int6
         if (v != 0) break;
         __nanosleep(2000);
       }
+      failed = v == 0;
     }
     __syncwarp();
     ++piece;
     next_tile += a.piece_tiles;
+  }
+}
+
+// A streamed batch is WRITTEN (by the copy engine) while the kernel runs: its states and costs are read with coherent
+// loads (ld.global.cg, L2) after the acquire of the piece's flag — the non-coherent read-only path (ld.global.nc, what
+// __ldg / load_row use) is only defined for data that does not change during the kernel.
+template <int W>
+__device__ __forceinline__ void load_row_cg(const float* base, int64_t row, float* v) {
+  const float* p = base + row * W;
+  if constexpr (W % 4 == 0) {
+#pragma unroll
+    for (int i = 0; i < W / 4; ++i) {
+      float4 t = __ldcg(reinterpret_cast<const float4*>(p) + i);
+      v[4 * i] = t.x; v[4 * i + 1] = t.y; v[4 * i + 2] = t.z; v[4 * i + 3] = t.w;
+    }
+  } else if constexpr (W % 2 == 0) {
+#pragma unroll
+    for (int i = 0; i < W / 2; ++i) {
+      float2 t = __ldcg(reinterpret_cast<const float2*>(p) + i);
+      v[2 * i] = t.x; v[2 * i + 1] = t.y;
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < W; ++i) v[i] = __ldcg(p + i);
   }
 }
 
@@ -262,7 +290,8 @@ __global__ void __launch_bounds__(kThreads, 1) vhjb_tc_kernel(const __grid_const
     }
   }
   if (tid == 0) {
-    *sOvf = 0;
+    sOvf[0] = 0;
+    sOvf[1] = 0;
     mbar_init(bar_pass, kComputeWarps);
     mbar_init(bar_mma, 1);
     mbar_init(bar_wg6, 1);
@@ -505,8 +534,10 @@ __global__ void __launch_bounds__(kThreads, 1) vhjb_tc_kernel(const __grid_const
     // (hjb_vhjb_saturation): nothing overflows silently.
     int expE = 0;
     if constexpr (GRAD) {
-      inv_norm0 = 1.0f / __ldg(a.norm);
-      inv_norm1 = 1.0f / __ldg(a.norm + 1);
+      // (eps = 0 with an all-done or all-interior shard: norm = 0 -> weight 0, not 0 * inf = NaN on the masked terms)
+      const float nm0 = __ldg(a.norm), nm1 = __ldg(a.norm + 1);
+      inv_norm0 = nm0 > 0.f ? 1.0f / nm0 : 0.f;
+      inv_norm1 = nm1 > 0.f ? 1.0f / nm1 : 0.f;
       const float wt = RFORM == HJB_RES_NORMALIZED ? fmaxf(inv_norm0, fabsf(a.reg) * inv_norm1) : inv_norm0;
       expE = (int)((__float_as_uint(wt) >> 23) & 0xffu) - 126;
       expE = max(-100, min(100, expE));
@@ -526,11 +557,15 @@ __global__ void __launch_bounds__(kThreads, 1) vhjb_tc_kernel(const __grid_const
     // states of a tile -> error coordinates z = wrap(x - xf) (vhjb.py:39); registers of the calling thread
     int64_t next_piece_tile = 0;
     int piece_idx = 0;
+    bool stream_failed = false;
     auto fetch_raw = [&](int64_t tile) {   // global loads issued early, consumed by to_error() later
-      if constexpr (STREAM) wait_piece(a, tile, next_piece_tile, piece_idx);
+      if constexpr (STREAM) wait_piece(a, tile, next_piece_tile, piece_idx, stream_failed);
       idx = tile * TS + sj;
       valid = sact && idx < a.B;
-      if (valid) load_row<N>(a.xs, idx, xraw);
+      if (valid) {
+        if constexpr (STREAM) load_row_cg<N>(a.xs, idx, xraw);
+        else load_row<N>(a.xs, idx, xraw);
+      }
       else {
 #pragma unroll
         for (int i = 0; i < N; ++i) xraw[i] = a.xf[i];
@@ -623,7 +658,7 @@ __global__ void __launch_bounds__(kThreads, 1) vhjb_tc_kernel(const __grid_const
         if (it == 0) {
           fetch_raw(tile);
           done = valid ? __ldg(a.dones + idx) : 0.f;
-          cost = valid ? __ldg(a.costs + idx) : 1.f;
+          cost = valid ? (STREAM ? __ldcg(a.costs + idx) : __ldg(a.costs + idx)) : 1.f;
         } else {
           idx = tile * TS + sj;
           valid = vnext;
@@ -699,16 +734,18 @@ __global__ void __launch_bounds__(kThreads, 1) vhjb_tc_kernel(const __grid_const
       wait_mma();
       tmark(it);
       if (epi_warp && more) {   // issue the next tile's loads now; they are consumed under its G1
-        if constexpr (STREAM) wait_piece(a, tile + gridDim.x, next_piece_tile, piece_idx);
+        if constexpr (STREAM) wait_piece(a, tile + gridDim.x, next_piece_tile, piece_idx, stream_failed);
         const int64_t nidx = (tile + gridDim.x) * TS + sj;
         vnext = sact && nidx < a.B;
-        if (vnext) load_row<N>(a.xs, nidx, xnext);
-        else {
+        if (vnext) {
+          if constexpr (STREAM) load_row_cg<N>(a.xs, nidx, xnext);
+          else load_row<N>(a.xs, nidx, xnext);
+        } else {
 #pragma unroll
           for (int i = 0; i < N; ++i) xnext[i] = a.xf[i];
         }
         dnext = vnext ? __ldg(a.dones + nidx) : 0.f;
-        cnext = vnext ? __ldg(a.costs + nidx) : 1.f;
+        cnext = vnext ? (STREAM ? __ldcg(a.costs + nidx) : __ldg(a.costs + nidx)) : 1.f;
       }
       if constexpr (kSmooth)
         feature_pass_k(cWk, cA1, kF1, [&](float d, float st, int k) {
@@ -892,7 +929,8 @@ __global__ void __launch_bounds__(kThreads, 1) vhjb_tc_kernel(const __grid_const
     }
     if constexpr (GRAD) {
       if (chain_max > 6.0e4f) atomicAdd(sOvf, 1);
-      asm volatile("bar.sync 1, 256;" ::: "memory");           // all pass warps: the counter is complete
+      if (STREAM && stream_failed) atomicAdd(sOvf + 1, 1);
+      asm volatile("bar.sync 1, 256;" ::: "memory");           // all pass warps: the counters are complete
     }
     if (epi_warp) {
       if (!sact) { hjb_sum = 0.f; term_sum = 0.f; sat_count = 0.f; }
@@ -912,6 +950,7 @@ __global__ void __launch_bounds__(kThreads, 1) vhjb_tc_kernel(const __grid_const
         part[vhjb_param_count(N)] = (sV[0] + sV[4]) + (sV[8] + sV[12]);
         part[vhjb_param_count(N) + 1] = (sV[1] + sV[5]) + (sV[9] + sV[13]);
         part[vhjb_param_count(N) + 2] = (sV[2] + sV[6]) + (sV[10] + sV[14]) + (float)*sOvf;
+        part[vhjb_param_count(N) + 3] = (float)sOvf[1];        // warps whose wait for a streamed piece gave up
       }
     }
   }

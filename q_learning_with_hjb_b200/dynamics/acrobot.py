@@ -29,7 +29,7 @@ class Acrobot(Dynamics):
         self.x0_std = np.full(4, 0.1, dtype=np.float32)
         self.seed = seed
         np.random.seed(seed)
-        self.fast_trig = False
+        self.fast_trig = True
 
     def get_dimension(self):
         return self.dim * 2, 1

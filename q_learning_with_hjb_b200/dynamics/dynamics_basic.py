@@ -36,8 +36,10 @@ class Dynamics:
         self.x0_std = config.x0_std
         self.seed = config.seed
         np.random.seed(config.seed)
-        #: use MUFU sin/cos/rcp in the kernels (2^-21 abs error on [-pi, pi]); False = libdevice accurate
-        self.fast_trig = False
+        #: True (default): the kernels' in-line trigonometry (quadrant reduction + minimax polynomials, <= 7e-8 absolute;
+        #: MUFU.RCP for reciprocals) — the instantiation bench.py times; False: libdevice sincosf / tanf, IEEE division.
+        #: Both meet the 1e-5 per-step / trajectory bounds (tests/test_rollout_gpu.py runs every parity test in both).
+        self.fast_trig = True
 
     # -- reference interface: host-side pieces -------------------------------------------------------
     def get_initial_state(self) -> np.ndarray:

@@ -123,6 +123,19 @@ class BatchedRollout:
                 "hjb_rollout")
         return RolloutResult(self.xs, self.us, self.x_final, self.cost, self.steps)
 
+    def kernel_variant(self) -> dict:
+        """The kernel instantiation this plan dispatches to (``hjb_rollout_variant``)."""
+        import ctypes as C
+
+        out = (C.c_int32 * 6)()
+        L.check(L.lib().hjb_rollout_variant(self.sys_spec, self.ctl_spec,
+                                            self.cost_spec if self.cost_spec is not None else C.POINTER(L.HjbCost)(),
+                                            self.opts, int(self.xs is not None or self.us is not None), out),
+                "hjb_rollout_variant")
+        return {"integrator": {v: k for k, v in L.INTEGRATORS.items()}[out[0]], "recorded": bool(out[1]),
+                "cost_mode": ("none", "diagonal", "dense", "unit")[out[2]], "box": bool(out[3]),
+                "fast_trig": bool(out[4]), "controller_clips": bool(out[5])}
+
     # -- end to end with host buffers ------------------------------------------------------------------
     def _staging(self):
         if self._pinned is None:

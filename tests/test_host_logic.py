@@ -157,27 +157,3 @@ def test_header_is_plain_c_and_a_c_caller_links():
                         f"-Wl,-rpath,{libdir}"], check=True)
         out = subprocess.run([exe], check=True, capture_output=True, text=True).stdout.strip()
         assert int(out) == len(names)
-
-
-def test_host_replay_buffer_has_deque_semantics():
-    """The NumPy ReplayBuffer (the host twin of DeviceReplayBuffer) against collections.deque(maxlen) and the DataLoader's
-    shuffle / drop_last contract (controller/vhjb.py:62-73, :153-154)."""
-    from collections import deque
-    from q_learning_with_hjb_b200.controller.vhjb import ReplayBuffer
-    rng = np.random.default_rng(0)
-    buf, ref = ReplayBuffer(3, 50), deque(maxlen=50)
-    for i in range(137):
-        x, c, d = rng.normal(size=3).astype(np.float32), float(rng.uniform()), float(i % 7 == 0)
-        buf.append(x, c, d)
-        ref.append((x, np.float32(c), np.float32(d)))
-        assert len(buf) == len(ref)
-    order = [(buf.head + k) % buf.max_size for k in range(len(buf))] if len(buf) == buf.max_size else list(range(len(buf)))
-    np.testing.assert_array_equal(buf.xs[order], np.stack([r[0] for r in ref]))
-    np.testing.assert_array_equal(buf.costs[order], np.array([r[1] for r in ref], dtype=np.float32))
-    np.testing.assert_array_equal(buf.dones[order], np.array([r[2] for r in ref], dtype=np.float32))
-    np.random.seed(1)
-    batches = list(buf.batches(8))
-    assert len(batches) == 50 // 8 and all(b[0].shape == (8, 3) and b[1].shape == (8,) and b[2].shape == (8,) for b in batches)
-    rows = {tuple(r[0].tolist()) for r in ref}
-    seen = [tuple(x.tolist()) for b in batches for x in b[0]]
-    assert len(set(seen)) == len(seen) and set(seen) <= rows
