@@ -250,9 +250,11 @@ int hjb_vhjb_loss_grad_accumulate(const hjb_system* sys, const hjb_vnet* net, co
  * piece k (piece_states states each, a multiple of 64; the last piece may be shorter) only after ready[k] != 0.  The caller
  * queues, on a copy stream, H2D(piece k of xs and costs) followed by a 4-byte H2D write of a non-zero value to ready[k],
  * for k = 0, 1, ... (pieces become ready in order); dones and norm must be complete before the launch (the normalisers
- * are sums over the whole batch).  ready must be zeroed before the copies start.  The poll is bounded: a flag that is
- * never set yields wrong numbers after a few seconds, not a hung device.  Tensor-core kernels only
- * (HJB_ERR_UNSUPPORTED otherwise: use the piecewise entry points above).
+ * are sums over the whole batch).  ready must be zeroed before the copies start.  The kernel reads the streamed buffers
+ * with coherent loads (ld.global.cg) after an acquire of the piece's flag.  The poll is bounded (seconds) so that a flag
+ * that is never set cannot hang the device; a poll that gives up is REPORTED, never silent: the loss sums of the step
+ * become NaN, the workspace's stream-failure word is raised (hjb_vhjb_stream_failures) and hjb_vhjb_adam_guarded skips
+ * the update.  Tensor-core kernels only (HJB_ERR_UNSUPPORTED otherwise: use the piecewise entry points above).
  */
 /* The copy side of a streamed batch, queued in one call (a dozen pieces x 3 cudaMemcpyAsync): piece k of xs_host / costs_host
  * (PINNED host memory) -> xs / costs, then ones_host[k] (pinned, non-zero) -> ready[k], all on copy_stream.  Call it BEFORE
@@ -263,6 +265,14 @@ int hjb_vhjb_stream_batch(const float* xs_host, const float* costs_host, float* 
 int hjb_vhjb_loss_grad_streamed(const hjb_system* sys, const hjb_vnet* net, const hjb_task* task, const float* xs,
                                 const float* dones, const float* costs, int64_t B, const float* norm, float reg, float* grad,
                                 float* sums, void* workspace, const int32_t* ready, int64_t piece_states, void* stream);
+
+/* Number of warps whose wait for a piece of a streamed batch gave up, summed over the streamed launches on this workspace
+ * since the last reset (`count`: device or pinned host float, nullable; reset != 0 zeroes the word after reading it). */
+int hjb_vhjb_stream_failures(void* workspace, int32_t n, float* count, int32_t reset, void* stream);
+/* hjb_adam on the value net's flat parameter buffer (n = state dimension), skipped — params, m, v untouched — while the
+ * workspace's stream-failure word is raised: a gradient computed from data that never arrived is never applied. */
+int hjb_vhjb_adam_guarded(float* params, float* m, float* v, const float* grad, int32_t n, float lr, float b1, float b2,
+                          float eps, int32_t step, const void* workspace, void* stream);
 
 /*
  * One whole single-GPU training step (VHJBController.params_update, controller/vhjb.py:255-288) in one call and three

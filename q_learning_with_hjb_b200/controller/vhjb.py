@@ -186,6 +186,30 @@ class VhjbKernels:
                 "hjb_vhjb_saturation_total")
         return int(out.item())
 
+    def stream_failures(self, reset: bool = True) -> int:
+        """Warps of the streamed gradient launches (``train_step_host``) whose wait for a piece of the batch gave up since
+        the last reset (``hjb_vhjb_stream_failures``).  Such a step's loss sums are NaN and its Adam update is skipped;
+        this call makes the condition an exception on the host.  Synchronises the stream."""
+        out = self.torch.zeros(1, device="cuda", dtype=self.torch.float32)
+        L.check(L.lib().hjb_vhjb_stream_failures(L.ptr(self.workspace), self.n, L.ptr(out), int(reset), L.stream_ptr()),
+                "hjb_vhjb_stream_failures")
+        return int(out.item())
+
+    def check_streams(self):
+        """Raise if a streamed batch never arrived (see ``stream_failures``)."""
+        k = self.stream_failures()
+        if k:
+            raise RuntimeError(f"hjb_vhjb_loss_grad_streamed: {k} waits for a piece of a host batch timed out — the step's "
+                               "gradient was discarded (losses NaN, Adam update skipped)")
+
+    def _poll_stream_status(self):
+        """Non-blocking: raise for a failure of an EARLIER streamed step whose status has reached the host."""
+        st = getattr(self, "_stage", None)
+        if st and st.get("status_ev") is not None and st["status_ev"].query():
+            st["status_ev"] = None
+            if float(st["status"][0]) != 0.0:
+                self.check_streams()
+
     def adam(self, params_flat, mu, nu, grad, step: int, lr: float, b1=0.9, b2=0.999, eps=1e-8):
         L.check(L.lib().hjb_adam(L.ptr(params_flat), L.ptr(mu), L.ptr(nu), L.ptr(grad), params_flat.numel(), float(lr),
                                  float(b1), float(b2), float(eps), int(step), L.stream_ptr()), "hjb_adam")
@@ -245,7 +269,12 @@ class VhjbKernels:
         from q_learning_with_hjb_b200 import parallel
         t = self.torch
         B = int(xs_h.shape[0])
+        self._poll_stream_status()
         st = self._host_staging(B)
+        # The copies below read the caller's host tensors asynchronously (pinned: straight DMA that torch's allocator does
+        # not track): they are referenced here until the next call, and `h2d_done` (st["h2d_done"]) is the event after the
+        # last copy — a caller that refills or frees its batch buffers waits for it first (VhjbKernels.host_batch_free()).
+        st["held"] = (xs_h, dones_h, costs_h)
         xs, dones, costs = st["xs"][:B], st["dones"][:B], st["costs"][:B]
         cur, cp = t.cuda.current_stream(), st["copy"]
         # pieces of whole waves of tiles (one 64-state tile per SM and wave): no CTA idles at the end of a piece
@@ -265,7 +294,7 @@ class VhjbKernels:
             bounds = [(lo, min(B, lo + step)) for lo in range(0, B, step)]
         # Streamed mode (default, tensor-core kernels): ONE gradient launch; the kernel itself waits, tile by tile, for
         # the arrival flag the copy stream writes behind each piece (hjb_vhjb_loss_grad_streamed) — no per-piece
-        # launch, reduction or host round trip.  Pieces: uniform, 8 waves of tiles (~75k states, ~3.6 MB).
+        # launch, reduction or host round trip.  Pieces: uniform, 12 waves of tiles (~114k states, ~5.4 MB).
         streamed = chunks is None and self.impl == "tensor" and os.environ.get("HJB_VHJB_IMPL", "") != "simt" and B >= 4 * wave
         if streamed:
             piece = 12 * wave
@@ -308,6 +337,8 @@ class VhjbKernels:
                         xs[sl].copy_(xs_h[sl], non_blocking=True)
                         costs[sl].copy_(costs_h[sl], non_blocking=True)
                         flags[i:i + 1].copy_(ones[i:i + 1], non_blocking=True)  # lands after the piece: same stream
+                st["h2d_done"] = t.cuda.Event()
+                st["h2d_done"].record(cp)
             normalisers()
             self._bind(params_flat)
             L.check(L.lib().hjb_vhjb_loss_grad_streamed(self.sys_spec, self.net, self.task, L.ptr(xs), L.ptr(dones),
@@ -324,14 +355,34 @@ class VhjbKernels:
                     ev = t.cuda.Event()
                     ev.record(cp)
                     ups.append((sl, ev))
+                st["h2d_done"] = ups[-1][1] if ups else None
             normalisers()
             for i, (sl, ev) in enumerate(ups):
                 cur.wait_event(ev)
                 self.loss_grad(params_flat, xs[sl], dones[sl], costs[sl], reg, accumulate=i > 0)
         parallel.sum_across_ranks(self.grad_and_sums, group)
         opt.count += 1
-        self.adam(params_flat, opt.mu, opt.nu, self.grad, opt.count, lr)
+        if streamed:
+            # guarded: a poll that gave up (the batch never arrived) raises the workspace's failure word; the update is then
+            # skipped on the device, the step's sums are NaN, and the host raises at its next look (check_streams)
+            L.check(L.lib().hjb_vhjb_adam_guarded(L.ptr(params_flat), L.ptr(opt.mu), L.ptr(opt.nu), L.ptr(self.grad), self.n,
+                                                  float(lr), 0.9, 0.999, 1e-8, int(opt.count), L.ptr(self.workspace),
+                                                  L.stream_ptr()), "hjb_vhjb_adam_guarded")
+            if "status" not in st:
+                st["status"] = t.zeros(1, dtype=t.float32).pin_memory()
+            L.check(L.lib().hjb_vhjb_stream_failures(L.ptr(self.workspace), self.n, C.c_void_p(st["status"].data_ptr()), 0,
+                                                     L.stream_ptr()), "hjb_vhjb_stream_failures")
+            st["status_ev"] = t.cuda.Event()
+            st["status_ev"].record(cur)
+        else:
+            self.adam(params_flat, opt.mu, opt.nu, self.grad, opt.count, lr)
         return self.sums, self.norm
+
+    def host_batch_free(self):
+        """Block until the host tensors handed to the last ``train_step_host`` have been read (their H2D copies are done)."""
+        st = getattr(self, "_stage", None)
+        if st and st.get("h2d_done") is not None:
+            st["h2d_done"].synchronize()
 
 
 class VHJBController(Controller):
@@ -397,12 +448,15 @@ class VHJBController(Controller):
     # ---- host-side setup ---------------------------------------------------------------------------------
     def system_additional_init(self) -> None:
         """Linearise about (xf, uf) (assumed an equilibrium) and solve the Riccati equation for the terminal cost
-        x^T P x (vhjb.py:156-160)."""
-        import scipy.linalg
+        x^T P x (vhjb.py:156-160).  As in the reference the inputs of the Riccati solve are float32 — jax.jacobian of the
+        float32 dynamics, float32 config arrays Q, R — and the solver is the repository's own ordered-Schur
+        ``utils.solve_continuous_are`` (utils/utils.py:30-80), not SciPy's: P carries single-precision rounding."""
+        from q_learning_with_hjb_b200.utils.utils import solve_continuous_are
 
         Alin, Blin = self.dynamics.linearize(np.asarray(self.xf, dtype=np.float64), np.asarray(self.uf, dtype=np.float64))
-        self.P = scipy.linalg.solve_continuous_are(Alin, Blin, np.asarray(self.Q, dtype=np.float64),
-                                                   np.asarray(self.R, dtype=np.float64))
+        self.P = np.asarray(solve_continuous_are(np.asarray(Alin, dtype=np.float32), np.asarray(Blin, dtype=np.float32),
+                                                 np.asarray(self.Q, dtype=np.float32), np.asarray(self.R, dtype=np.float32)),
+                            dtype=np.float64)
 
     def running_cost(self, x, u):
         x_diff = self.dynamics.states_wrap(np.array(x, dtype=np.float64) - self.xf)

@@ -277,6 +277,9 @@ int hjb_rollout_variant(const hjb_system* sys, const hjb_control* ctl, const hjb
   out[0] = opts->integrator;
   out[1] = recorded != 0;
   out[2] = cost_mode(sys, cost_spec);
+  // the compiled combinations (rollout_kernel.cuh::launch_cost): a box runs the dense form, recorded runs have no DIAG form
+  if (opts->box_enabled) out[2] = COST_DENSE;
+  else if (recorded && out[2] == COST_DIAG) out[2] = COST_DENSE;
   out[3] = opts->box_enabled != 0;
   out[4] = opts->fast_trig != 0;
   out[5] = ctl->kind == HJB_CTL_FEEDBACK ? (ctl->clip != 0) : 1;

@@ -207,6 +207,18 @@ __device__ __forceinline__ bool inside_box(const DevBox& b, const float* z) {
   return in;
 }
 
+// (sin, cos)(k 2^-5 + aoff) in double, rounded to fp32, for the `nt` angle arguments of a system (the third, the acrobot's
+// q1 + q2, has offset aoff0 + aoff1).  One copy per translation unit: fp64 sincos carries a large slow path.
+static __device__ __noinline__ void build_trig_tables(float2* tab, int nt, float aoff0, float aoff1) {
+  for (int i = threadIdx.x; i < nt * kTrigSize; i += blockDim.x) {
+    const int k = i / kTrigSize, j = i - k * kTrigSize;
+    const double off = k == 2 ? (double)aoff0 + (double)aoff1 : (double)(k == 1 ? aoff1 : aoff0);
+    double sv, cv;
+    sincos((double)(j - kTrigHalf) * (1.0 / (double)(1 << kTrigLog2)) + off, &sv, &cv);
+    tab[i] = make_float2((float)sv, (float)cv);
+  }
+}
+
 // Persistent CTAs: the grid is at most kRolloutCtasPerSm x SM count and every CTA walks over blocks of 256 environments
 // (block b, b + gridDim.x, ...).  What a CTA sets up once — the trig tables in shared memory — is then paid ~1200 times
 // per launch instead of once per 256 environments.
@@ -231,13 +243,7 @@ __global__ void __launch_bounds__(256) rollout_kernel(const __grid_constant__ Ro
   using TC = std::conditional_t<kTab, TableTrig, DirectTrig<S::kFast>>;
   TC tc;
   if constexpr (kTab) {
-    for (int i = threadIdx.x; i < NT * kTrigSize; i += blockDim.x) {
-      const int k = i / kTrigSize, j = i - k * kTrigSize;
-      const double off = k == 2 ? (double)a.sys.aoff[0] + (double)a.sys.aoff[1] : (double)a.sys.aoff[k];
-      double sv, cv;
-      sincos((double)(j - kTrigHalf) * (1.0 / (double)(1 << kTrigLog2)) + off, &sv, &cv);
-      trig_tab[i] = make_float2((float)sv, (float)cv);
-    }
+    build_trig_tables(trig_tab, NT, a.sys.aoff[0], a.sys.aoff[1]);
     __syncthreads();
     tc.tab = trig_tab;
   }
@@ -375,17 +381,22 @@ inline cudaError_t launch_one(const RolloutArgs& a, cudaStream_t st) {
   return cudaGetLastError();
 }
 
-template <class S, class C, int INTEG, bool REC, int COST>
-inline cudaError_t launch_box(const RolloutArgs& a, const RolloutVariant& v, cudaStream_t st) {
-  return v.box ? launch_one<S, C, INTEG, REC, COST, true>(a, st) : launch_one<S, C, INTEG, REC, COST, false>(a, st);
-}
+// Compiled combinations.  The specialised cost forms matter where the kernel is compute-bound and common: without a box,
+//   final state (+ cost):   NONE, UNIT, DIAG, DENSE
+//   recorded trajectories:  NONE, UNIT, DENSE        (diagonal costs run as DENSE)
+//   box termination:        DENSE only               (every cost form is a dense (Q, R); without a cost output the sum is
+//                                                     computed and dropped) — rollouts of this kind are short
+// — 9 instantiations per (system, controller, trig, integrator) instead of 16.
 template <class S, class C, int INTEG, bool REC>
 inline cudaError_t launch_cost(const RolloutArgs& a, const RolloutVariant& v, cudaStream_t st) {
+  if (v.box) return launch_one<S, C, INTEG, REC, COST_DENSE, true>(a, st);
   switch (v.cost) {
-    case COST_NONE: return launch_box<S, C, INTEG, REC, COST_NONE>(a, v, st);
-    case COST_DIAG: return launch_box<S, C, INTEG, REC, COST_DIAG>(a, v, st);
-    case COST_UNIT: return launch_box<S, C, INTEG, REC, COST_UNIT>(a, v, st);
-    default: return launch_box<S, C, INTEG, REC, COST_DENSE>(a, v, st);
+    case COST_NONE: return launch_one<S, C, INTEG, REC, COST_NONE, false>(a, st);
+    case COST_UNIT: return launch_one<S, C, INTEG, REC, COST_UNIT, false>(a, st);
+    case COST_DIAG:
+      if constexpr (!REC) return launch_one<S, C, INTEG, REC, COST_DIAG, false>(a, st);
+      else return launch_one<S, C, INTEG, REC, COST_DENSE, false>(a, st);
+    default: return launch_one<S, C, INTEG, REC, COST_DENSE, false>(a, st);
   }
 }
 template <class S, class C, int INTEG>

@@ -34,18 +34,46 @@ __global__ void __launch_bounds__(256) vhjb_reduce_kernel(const float* __restric
   out[j] = accumulate ? out[j] + s : s;
 }
 
-// saturation count of one launch -> tail[0] (this batch; added when the batch arrives in pieces) and tail[1] (running total)
+// saturation count of one launch -> tail[0] (this batch; added when the batch arrives in pieces) and tail[1] (running total).
+// streamed launches: the number of warps whose wait for a piece of the batch gave up -> tail[2] (sticky until
+// hjb_vhjb_stream_failures resets it); when it is non-zero the loss sums of this step are poisoned with NaN and the
+// guarded Adam update (hjb_vhjb_adam_guarded) skips the step.
 __global__ void vhjb_sat_kernel(const float* __restrict__ partial, int64_t pstride, int ncta, int at, float* __restrict__ tail,
-                                int accumulate) {
+                                int accumulate, int streamed, float* __restrict__ sums) {
   // one warp: lane l sums the CTAs l, l + 32, ... (counts are small integers: exact in any order), then a shuffle tree
-  float s = 0.f;
-  for (int c = threadIdx.x; c < ncta; c += 32) s += partial[(int64_t)c * pstride + at];
+  float s = 0.f, f = 0.f;
+  for (int c = threadIdx.x; c < ncta; c += 32) {
+    s += partial[(int64_t)c * pstride + at];
+    if (streamed) f += partial[(int64_t)c * pstride + at + 1];
+  }
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  for (int o = 16; o > 0; o >>= 1) {
+    s += __shfl_xor_sync(0xffffffffu, s, o);
+    f += __shfl_xor_sync(0xffffffffu, f, o);
+  }
   if (threadIdx.x == 0) {
     tail[0] = accumulate ? tail[0] + s : s;
     tail[1] += s;
+    if (streamed && f > 0.f) {
+      tail[2] += f;
+      if (sums) sums[0] = sums[1] = __int_as_float(0x7fc00000);
+    }
   }
+}
+
+// optax.adam, skipped (weights, mu, nu untouched) while the workspace's stream-failure word is raised
+__global__ void __launch_bounds__(256) adam_guarded_kernel(float* __restrict__ w, float* __restrict__ m, float* __restrict__ v,
+                                                           const float* __restrict__ g, int64_t len, float lr, float b1, float b2,
+                                                           float eps, float bc1, float bc2, const float* __restrict__ guard) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= len || *guard != 0.f) return;
+  const float gi = g[i];
+  const float mi = fmaf(b1, m[i], (1.f - b1) * gi);
+  const float vi = fmaf(b2, v[i], (1.f - b2) * gi * gi);
+  m[i] = mi;
+  v[i] = vi;
+  const float mhat = mi / bc1, vhat = vi / bc2;
+  w[i] = w[i] - lr * mhat / (sqrtf(vhat) + eps);
 }
 
 // ---- sum(1 - done), sum(done): two-stage, fixed order ----
@@ -207,6 +235,11 @@ static int run_vhjb(const hjb_system* sys, const hjb_vnet* net, const hjb_task* 
     if (!tensor || !want_grad || piece_states <= 0 || piece_states % tc::TS != 0) return HJB_ERR_UNSUPPORTED;
     a.ready = ready;
     a.piece_tiles = piece_states / tc::TS;
+    a.poll_limit = 1u << 22;
+    if (const char* pl = std::getenv("HJB_STREAM_POLL_LIMIT")) {
+      const long v = std::atol(pl);
+      if (v > 0) a.poll_limit = (unsigned)v;
+    }
   }
 
   static long long* dbg_buf = nullptr;
@@ -279,7 +312,8 @@ static int run_vhjb(const hjb_system* sys, const hjb_vnet* net, const hjb_task* 
     if (e != cudaSuccess) return (int)e;
   }
   if (want_grad) {  // saturation count of the fp16 range management (vhjb_tc.cuh) -> workspace tail
-    vhjb_sat_kernel<<<1, 32, 0, st>>>(a.partial, a.pstride, l.grid, P + 2, a.partial + (int64_t)kMaxCtas * a.pstride, (int)accumulate);
+    vhjb_sat_kernel<<<1, 32, 0, st>>>(a.partial, a.pstride, l.grid, P + 2, a.partial + (int64_t)kMaxCtas * a.pstride, (int)accumulate,
+                                      ready != nullptr, sums);
     e = cudaGetLastError();
     if (e != cudaSuccess) return (int)e;
   }
@@ -312,6 +346,28 @@ int hjb_vhjb_saturation_total(void* workspace, int32_t n, float* count, int32_t 
   cudaError_t e = cudaSuccess;
   if (count) e = cudaMemcpyAsync(count, tail + 1, sizeof(float), cudaMemcpyDeviceToDevice, (cudaStream_t)stream);
   if (e == cudaSuccess && reset) e = cudaMemsetAsync(tail + 1, 0, sizeof(float), (cudaStream_t)stream);
+  return e == cudaSuccess ? HJB_OK : (int)e;
+}
+
+int hjb_vhjb_stream_failures(void* workspace, int32_t n, float* count, int32_t reset, void* stream) {
+  if (!workspace || n <= 0 || n > HJB_MAX_N) return HJB_ERR_BAD_ARG;
+  float* tail = static_cast<float*>(workspace) + (int64_t)kMaxCtas * pstride_of(n);
+  cudaError_t e = cudaSuccess;
+  if (count) e = cudaMemcpyAsync(count, tail + 2, sizeof(float), cudaMemcpyDefault, (cudaStream_t)stream);
+  if (e == cudaSuccess && reset) e = cudaMemsetAsync(tail + 2, 0, sizeof(float), (cudaStream_t)stream);
+  return e == cudaSuccess ? HJB_OK : (int)e;
+}
+
+int hjb_vhjb_adam_guarded(float* params, float* m, float* v, const float* grad, int32_t n, float lr, float b1, float b2, float eps,
+                          int32_t step, const void* workspace, void* stream) {
+  if (!params || !m || !v || !grad || !workspace || n <= 0 || n > HJB_MAX_N || step < 1) return HJB_ERR_BAD_ARG;
+  const int64_t len = vhjb_param_count(n);
+  const float bc1 = (float)(1.0 - std::pow((double)b1, (double)step));
+  const float bc2 = (float)(1.0 - std::pow((double)b2, (double)step));
+  const float* guard = static_cast<const float*>(workspace) + (int64_t)kMaxCtas * pstride_of(n) + 2;
+  adam_guarded_kernel<<<(unsigned)((len + 255) / 256), 256, 0, (cudaStream_t)stream>>>(params, m, v, grad, len, lr, b1, b2, eps, bc1,
+                                                                                       bc2, guard);
+  cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? HJB_OK : (int)e;
 }
 

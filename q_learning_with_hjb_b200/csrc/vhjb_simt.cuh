@@ -49,6 +49,7 @@ struct VhjbArgs {
   // ready[t / piece_tiles] != 0 — the flags are written by the copy stream behind each piece of the batch
   const int* ready;
   int64_t piece_tiles;
+  unsigned poll_limit;  // polls (2 us apart) before a wait for a piece gives up: 2^22 (~8 s); HJB_STREAM_POLL_LIMIT overrides
 };
 
 __host__ __device__ constexpr int vhjb_param_count(int n) { return n * VH1 + VH1 * VH2 + VH2 * VH3; }

@@ -195,7 +195,7 @@ __device__ __forceinline__ void wait_piece(const VhjbArgs& a, int64_t tile, int6
     if ((threadIdx.x & 31) == 0 && !failed) {
       const int* f = a.ready + piece;
       int v = 0;
-      for (unsigned spins = 0; spins < (1u << 22); ++spins) {
+      for (unsigned spins = 0; spins < a.poll_limit; ++spins) {
         asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
         if (v != 0) break;
         __nanosleep(2000);

@@ -43,8 +43,13 @@ def _hamiltonian(A, B, Q, R):
 
 
 def solve_continuous_are(A, B, Q, R, multiple_sol: bool = False) -> Union[List[np.ndarray], np.ndarray]:
+    """Computes in the inputs' own floating-point type, as the reference does (utils/utils.py:67-80): float32 inputs — what
+    ``VHJBController.system_additional_init`` passes, controller/vhjb.py:159-160 — go through the single-precision Schur
+    form; anything else is float64."""
     import scipy.linalg
-    A, B, Q, R = (np.atleast_2d(np.asarray(v, dtype=np.float64)) for v in (A, B, Q, R))
+    arrs = [np.asarray(v) for v in (A, B, Q, R)]
+    dt = np.float32 if all(a.dtype == np.float32 for a in arrs) else np.float64
+    A, B, Q, R = (np.atleast_2d(a.astype(dt)) for a in arrs)
     n = A.shape[0]
     H = _hamiltonian(A, B, Q, R)
     if not multiple_sol:

@@ -274,3 +274,25 @@ def test_controller_gains_match_the_reference_classes():
     oac = make_controller("acrobot_es", make_dynamics("acrobot"))
     for a, b in zip(oac.get_lqr_term(), rac.get_lqr_term()):
         np.testing.assert_allclose(a, b, rtol=1e-8, atol=1e-10)
+
+
+def test_riccati_for_the_terminal_cost_matches_the_reference_solver_in_float32():
+    """controller/vhjb.py:156-160: P comes from the reference's OWN ordered-Schur solver (utils/utils.py:67-80) fed with
+    float32 Alin, Blin (jax.jacobian of the float32 dynamics), Q, R (float32 config arrays).  The product's
+    utils.solve_continuous_are computes in the inputs' type like the reference's: same P on the same float32 inputs."""
+    from q_learning_with_hjb_b200.utils import utils as U
+    rutils = R.ref_import("utils.utils")
+    rng = np.random.default_rng(0)
+    cases = [(np.array([[0, 1], [0, 0]]), np.array([[0], [1]]))]
+    for n, m in ((4, 1), (6, 2), (10, 3)):
+        cases.append((rng.normal(size=(n, n)), rng.normal(size=(n, m))))
+    for A, B in cases:
+        n, m = B.shape
+        A32, B32, Q32, R32 = (np.asarray(v, dtype=np.float32) for v in (A, B, np.eye(n), np.eye(m)))
+        ours = U.solve_continuous_are(A32, B32, Q32, R32)
+        ref = rutils.solve_continuous_are(A32, B32, Q32, R32)
+        assert ours.dtype == ref.dtype == np.float32
+        np.testing.assert_allclose(ours, ref, rtol=2e-5, atol=2e-5)     # two single-precision Schur forms
+        ours64 = U.solve_continuous_are(A, B, np.eye(n), np.eye(m))
+        np.testing.assert_allclose(ours64, rutils.solve_continuous_are(np.asarray(A, float), np.asarray(B, float),
+                                                                       np.eye(n), np.eye(m)), rtol=1e-9, atol=1e-9)

@@ -401,6 +401,59 @@ def test_host_batch_train_step_matches_device_batch(name):
     assert not torch.equal(w0, params)                  # the step really updated the weights
 
 
+def test_streamed_batch_that_never_arrives_is_reported_not_applied(monkeypatch):
+    """hjb_vhjb_loss_grad_streamed with arrival flags that are never set: the bounded poll gives up (HJB_STREAM_POLL_LIMIT
+    shortens it for the test), the step's loss sums are NaN, the workspace's failure word is raised, the guarded Adam
+    update leaves the weights and the optimiser state untouched, and the host side raises."""
+    import ctypes as C
+    from q_learning_with_hjb_b200 import _lib as L
+    monkeypatch.setenv("HJB_STREAM_POLL_LIMIT", "200")
+    B = 4 * 148 * 64
+    torch, k, p, orc, params, xs, dones, costs = _setup("quad10d", B, seed=3)
+    xd, dd, cd = _dev(torch, xs, dones, costs)
+    flags = torch.zeros(8, device="cuda", dtype=torch.int32)          # never set
+    k.counts(dd, p.eps)
+    k._bind(params)
+    L.check(L.lib().hjb_vhjb_loss_grad_streamed(k.sys_spec, k.net, k.task, L.ptr(xd), L.ptr(dd), L.ptr(cd), B, L.ptr(k.norm),
+                                                0.5, L.ptr(k.grad), L.ptr(k.sums), L.ptr(k.workspace), L.ptr(flags), 148 * 64,
+                                                L.stream_ptr()))
+    w = params.clone()
+    mu, nu = torch.zeros_like(w), torch.zeros_like(w)
+    L.check(L.lib().hjb_vhjb_adam_guarded(L.ptr(w), L.ptr(mu), L.ptr(nu), L.ptr(k.grad), k.n, 1e-3, 0.9, 0.999, 1e-8, 1,
+                                          L.ptr(k.workspace), L.stream_ptr()))
+    torch.cuda.synchronize()
+    assert torch.isnan(k.sums).all()
+    assert torch.equal(w, params) and not mu.any() and not nu.any()
+    assert k.stream_failures(reset=False) > 0
+    with pytest.raises(RuntimeError, match="timed out"):
+        k.check_streams()
+    assert k.stream_failures() == 0                                   # check_streams reset the word
+    # the same launch with the flags set computes the device-batch gradient, and the guarded update applies it
+    flags.fill_(1)
+    L.check(L.lib().hjb_vhjb_loss_grad_streamed(k.sys_spec, k.net, k.task, L.ptr(xd), L.ptr(dd), L.ptr(cd), B, L.ptr(k.norm),
+                                                0.5, L.ptr(k.grad), L.ptr(k.sums), L.ptr(k.workspace), L.ptr(flags), 148 * 64,
+                                                L.stream_ptr()))
+    g_stream = k.grad.clone()
+    L.check(L.lib().hjb_vhjb_adam_guarded(L.ptr(w), L.ptr(mu), L.ptr(nu), L.ptr(k.grad), k.n, 1e-3, 0.9, 0.999, 1e-8, 1,
+                                          L.ptr(k.workspace), L.stream_ptr()))
+    k.loss_grad(params, xd, dd, cd, 0.5)
+    assert torch.equal(g_stream, k.grad) and torch.isfinite(k.sums).all()
+    assert not torch.equal(w, params)
+
+
+def test_zero_normaliser_gives_zero_weight_not_nan():
+    """eps = 0 and a shard without boundary samples: norm[1] = 0.  The masked terms carry weight 0, not 0 * inf."""
+    torch, k, p, orc, params, xs, dones, costs = _setup("quad2d", 2048, seed=5)
+    dones[:] = 0
+    xd, dd, cd = _dev(torch, xs, dones, costs)
+    k.counts(dd, 0.0)
+    assert float(k.norm[1]) == 0.0
+    for impl in ("tensor", "simt"):
+        k.impl = impl
+        g, sums = k.loss_grad(params, xd, dd, cd, 0.5)
+        assert torch.isfinite(g).all() and torch.isfinite(sums).all(), impl
+
+
 def test_device_replay_buffer_has_deque_semantics():
     """DeviceReplayBuffer (ring in HBM, hjb_replay_append / hjb_replay_gather) against collections.deque(maxlen): plain
     extends, rollout records appended trajectory by trajectory, wrap-around, and an extend larger than the capacity."""
