@@ -157,6 +157,17 @@ int hjb_control_efforts(const hjb_system* sys, const hjb_control* ctl, int32_t f
 /* Batched Dynamics.states_wrap (cartpole.py:52-64, acrobot.py:72-81, quadrotors.py:48-70,151-170), in place. */
 int hjb_states_wrap(const hjb_system* sys, float* x, int64_t B, void* stream);
 
+/*
+ * Counter-based sampling of states on the device: x[i] = wrap(U(-std, std) + mean), the distribution of
+ * Dynamics.get_initial_state (dynamics/dynamics_basic.py:28-29) and of the seed data set of controller/vhjb.py:136-151.
+ * The reference's stream (the global NumPy RNG, one state per call) is serial; here sample i of the stream keyed by `seed`
+ * is Philox4x32-10(key = seed, counter = (first + i, component / 4)) whichever GPU or launch produces it, so a batch split
+ * over N GPUs (first = the shard's offset) is the same batch.  sys_kind selects the angle components that are wrapped.
+ *   x [count, n] device.  oracle/x0_stream.py is the bit-exact NumPy twin.
+ */
+int hjb_sample_states(int32_t sys_kind, int32_t n, const float* mean, const float* std, uint64_t seed, int64_t first,
+                      int64_t count, float* x, void* stream);
+
 /* ==== vhjb: HJB-residual pass over sampled states (controller/vhjb.py:201-288) ====================== */
 typedef enum hjb_activation {
   HJB_ACT_RELU = 0, /* controller/vhjb.py:55 */

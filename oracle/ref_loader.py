@@ -18,7 +18,15 @@ import importlib
 import os
 import sys
 
-REFERENCE_ROOT = os.environ.get("HJB_REFERENCE_ROOT", "/root/reference")
+def _default_root() -> str:
+    """/root/reference in the build container; on the GPU box the travelling copy under baseline/_ref (made by
+    tools/install_reference_baseline.py — used ONLY by bench.py's reference-literal CPU baseline)."""
+    if os.path.isdir("/root/reference/dynamics"):
+        return "/root/reference"
+    return os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "baseline", "_ref")
+
+
+REFERENCE_ROOT = os.environ.get("HJB_REFERENCE_ROOT") or _default_root()
 _STUBS = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_stubs")
 
 _REF_TOPLEVEL = ("dynamics", "controller", "configs", "utils")

@@ -24,6 +24,15 @@ import numpy as np
 PI = np.pi
 TWO_PI = 2.0 * np.pi
 
+# Working precision.  float64 (the reference's NumPy branch) is what every parity check uses; bench.py's "best-effort CPU"
+# leg switches to float32 — same arithmetic, half the memory traffic, NOT a parity oracle.
+DT = np.float64
+
+
+def set_dtype(dt):
+    global DT
+    DT = np.dtype(dt).type
+
 
 def wrap_angle(a):
     """``np.remainder(a + pi, 2*pi) - pi`` — floor-mod into [-pi, pi)
@@ -52,22 +61,22 @@ class OracleSystem:
     def wrap(self, x: np.ndarray) -> np.ndarray:
         """states_wrap, returning a copy (linear.py:17-18, cartpole.py:52-64, acrobot.py:72-81,
         quadrotors.py:48-70,151-170)."""
-        x = np.array(x, dtype=np.float64, copy=True)
+        x = np.array(x, dtype=DT, copy=True)
         for i in self.wrap_index():
             x[..., i] = wrap_angle(x[..., i])
         return x
 
     def f_g(self, x: np.ndarray) -> Tuple[np.ndarray, np.ndarray]:
         """Batched ``get_control_affine_matrix``: x[B,n] -> f[B,n], g[B,n,m]."""
-        x = np.asarray(x, dtype=np.float64)
+        x = np.asarray(x, dtype=DT)
         B = x.shape[0]
         p = self.par
         f = np.zeros((B, self.n))
         g = np.zeros((B, self.n, self.m))
         if self.kind == "linear":
             # dynamics/linear.py:20-22
-            f = x @ np.asarray(p["A"], dtype=np.float64).T
-            g[:] = np.asarray(p["B"], dtype=np.float64)[None]
+            f = x @ np.asarray(p["A"], dtype=DT).T
+            g[:] = np.asarray(p["B"], dtype=DT)[None]
         elif self.kind == "cartpole":
             # dynamics/cartpole.py:19-50 via the manipulator form dynamics_basic.py:64-94
             mc, mp, l, grav = p["mc"], p["mp"], p["l"], p["g"]
@@ -163,7 +172,7 @@ class OracleSystem:
 
     def step(self, x, u, integrator="euler"):
         """``Dynamics.simulate`` (dynamics_basic.py:107-122): clip u, integrate one dt, wrap."""
-        u = np.clip(np.asarray(u, dtype=np.float64), self.umin, self.umax)
+        u = np.clip(np.asarray(u, dtype=DT), self.umin, self.umax)
         dt = self.dt
         if integrator == "euler":
             xn = x + self.xdot(x, u) * dt
@@ -203,10 +212,10 @@ class OracleController:
     eps: float = 1000.0
 
     def control(self, sys: OracleSystem, x: np.ndarray) -> np.ndarray:
-        x = np.asarray(x, dtype=np.float64)
+        x = np.asarray(x, dtype=DT)
         if self.kind == "feedback":
             dx = sys.wrap(x - self.xf)
-            u = -dx @ np.asarray(self.K, dtype=np.float64).T + self.uf
+            u = -dx @ np.asarray(self.K, dtype=DT).T + self.uf
             return np.clip(u, sys.umin, sys.umax) if self.clip else u
         if self.kind == "cartpole_es":
             p = sys.par
@@ -216,9 +225,9 @@ class OracleController:
             Ef = 0.5 * xf[3] ** 2 - np.cos(xf[1])
             de = E - Ef                                                   # :78
             near = (np.abs(de) < self.eps_energy) & (np.sqrt(dx[:, 1] ** 2 + dx[:, 3] ** 2) < self.eps_state)  # :79
-            u_lqr = -dx @ np.asarray(self.K, dtype=np.float64).T          # :80
+            u_lqr = -dx @ np.asarray(self.K, dtype=DT).T          # :80
             u_bar = de * x[:, 3] * np.cos(x[:, 1])                        # :99
-            Ke = np.asarray(self.Ke, dtype=np.float64)
+            Ke = np.asarray(self.Ke, dtype=DT)
             ddq1 = Ke[0] * (-x[:, 0]) + Ke[1] * (-x[:, 2]) + Ke[2] * u_bar  # :100
             ddq2 = -np.cos(x[:, 1]) / p["l"] * ddq1 - p["g"] * np.sin(x[:, 1]) / p["l"]  # :101
             u_es = (p["mc"] + p["mp"]) * ddq1 + p["mp"] * p["l"] * np.cos(x[:, 1]) * ddq2 \
@@ -229,13 +238,13 @@ class OracleController:
             xf = np.array([np.pi, 0.0, 0.0, 0.0])
             d = x - xf
             dx = np.concatenate([wrap_angle(d[:, :2]), d[:, 2:]], axis=1)  # :109
-            P = np.asarray(self.P, dtype=np.float64)
+            P = np.asarray(self.P, dtype=DT)
             quad = np.einsum("bi,ij,bj->b", dx, P, dx)                    # :114
-            u_lqr = -dx @ np.asarray(self.K, dtype=np.float64).T          # :115
+            u_lqr = -dx @ np.asarray(self.K, dtype=DT).T          # :115
             M, Cdq, G = sys.acrobot_terms(x)                              # :83-86
             Ef = sys.acrobot_energy(xf[None])[0]
             ubar = (sys.acrobot_energy(x) - Ef) * x[:, 2]                 # :88
-            Ks = np.asarray(self.Ke, dtype=np.float64)
+            Ks = np.asarray(self.Ke, dtype=DT)
             ddq2 = Ks[0] * (-wrap_angle(x[:, 1])) + Ks[1] * (-x[:, 3]) + Ks[2] * ubar   # :90
             h = G + Cdq
             u_sw = (M[:, 1, 1] - M[:, 0, 1] ** 2 / M[:, 0, 0]) * ddq2 + h[:, 1] - M[:, 1, 0] / M[:, 0, 0] * h[:, 0]  # :92
@@ -248,8 +257,8 @@ def control_scale(sys: OracleSystem, ctl: OracleController, x: np.ndarray) -> np
     """Per-sample magnitude of the largest intermediate term of the control law, [B] — the scale against which
     an fp32 evaluation of the law can be expected to be accurate (cancellation between large terms is a property
     of the law, not of the implementation).  Used only to normalise errors in the parity tests."""
-    x = np.asarray(x, dtype=np.float64)
-    K = np.abs(np.asarray(ctl.K, dtype=np.float64))
+    x = np.asarray(x, dtype=DT)
+    K = np.abs(np.asarray(ctl.K, dtype=DT))
     if ctl.kind == "feedback":
         dx = np.abs(sys.wrap(x - ctl.xf))
         return (dx @ K.T + np.abs(ctl.uf)).max(axis=1)
@@ -258,7 +267,7 @@ def control_scale(sys: OracleSystem, ctl: OracleController, x: np.ndarray) -> np
         xf = np.array([0.0, np.pi, 0.0, 0.0])
         lqr = (np.abs(sys.wrap(x - xf)) @ K.T)[:, 0]
         E = 0.5 * x[:, 3] ** 2 + 1 + 1
-        Ke = np.abs(np.asarray(ctl.Ke, dtype=np.float64))
+        Ke = np.abs(np.asarray(ctl.Ke, dtype=DT))
         a1 = Ke[0] * np.abs(x[:, 0]) + Ke[1] * np.abs(x[:, 2]) + Ke[2] * E * np.abs(x[:, 3])
         a2 = a1 / p["l"] + p["g"] / p["l"]
         es = (p["mc"] + p["mp"]) * a1 + p["mp"] * p["l"] * a2 + p["mp"] * p["l"] * x[:, 3] ** 2
@@ -273,7 +282,7 @@ def control_scale(sys: OracleSystem, ctl: OracleController, x: np.ndarray) -> np
         a = pp["m2"] * pp["l1"] * pp["l2"] / 2
         Emag = 0.5 * np.abs(M[:, 0, 0]) * x[:, 2] ** 2 + 0.5 * pp["I2"] * x[:, 3] ** 2 + np.abs(M[:, 0, 1] * x[:, 2] * x[:, 3]) \
             + 200.0 + 100.0
-        Ks = np.abs(np.asarray(ctl.Ke, dtype=np.float64))
+        Ks = np.abs(np.asarray(ctl.Ke, dtype=DT))
         a2 = Ks[0] * np.pi + Ks[1] * np.abs(x[:, 3]) + Ks[2] * Emag * np.abs(x[:, 2])
         hmag = np.abs(G) + np.abs(a * x[:, 3:4] * (2 * np.abs(x[:, 2:3]) + np.abs(x[:, 3:4]))) + np.abs(a * x[:, 2:3] ** 2)
         sw = np.abs(M[:, 1, 1]) * a2 + hmag[:, 1] + hmag[:, 0]
@@ -309,10 +318,10 @@ def rollout(sys: OracleSystem, ctl: OracleController, x0: np.ndarray, steps: int
     Returns ``xs [T_rec+1, N, n]`` (time-major; x0 first, then every ``record_stride``-th state),
     ``us [T_rec, N, m]`` (the controller output at the START of each recorded interval, i.e. at steps
     0, s, 2s, ...), ``x_final [N, n]`` and ``cost [N]`` (sum of l(x,u)*dt over all steps)."""
-    x = np.array(x0, dtype=np.float64, copy=True)
+    x = np.array(x0, dtype=DT, copy=True)
     N = x.shape[0]
     xs, us = [x.copy()], []
-    J = np.zeros(N)
+    J = np.zeros(N, dtype=DT)
     for t in range(steps):
         u = ctl.control(sys, x)
         if cost is not None:

@@ -73,7 +73,11 @@ def traffic(tag):
             return None
         i = hdr.index(k)
         tot += float(vals[i].replace(",", "")) * mult.get(units[i], 1)
-    return {"dram_bytes_per_launch": tot, "kernel": vals[hdr.index("Kernel Name")][:80],
+    sys.path.insert(0, ROOT)
+    from q_learning_with_hjb_b200.build import source_hash
+    kernel = vals[hdr.index("Kernel Name")][:80]
+    return {"dram_bytes_per_launch": tot, "kernel": kernel,
+            "kernel_source_hash": source_hash("rollout" if "rollout" in kernel else "vhjb"),
             "source": f"profiles/{tag}.md (ncu --set full, one launch)"}
 
 

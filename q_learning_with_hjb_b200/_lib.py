@@ -78,6 +78,8 @@ SYMBOLS = {
     "hjb_dynamics": (C.c_int, [C.POINTER(HjbSystem), C.c_int32, C.c_int32, _P, _P, C.c_int64, _P, _P, _P, _P, _P]),
     "hjb_control_efforts": (C.c_int, [C.POINTER(HjbSystem), C.POINTER(HjbControl), C.c_int32, _P, C.c_int64, _P, _P]),
     "hjb_states_wrap": (C.c_int, [C.POINTER(HjbSystem), _P, C.c_int64, _P]),
+    "hjb_sample_states": (C.c_int, [C.c_int32, C.c_int32, C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_uint64, C.c_int64,
+                                    C.c_int64, _P, _P]),
     "hjb_fma_peak_probe": (C.c_int, [_P, C.c_int64, C.c_int32, C.POINTER(C.c_double), _P]),
     "hjb_vhjb_param_count": (C.c_int64, [C.c_int32]),
     "hjb_vhjb_workspace_bytes": (C.c_int64, [C.c_int32]),

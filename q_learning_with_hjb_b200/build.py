@@ -49,6 +49,18 @@ def _digest(paths, extra=""):
     return h.hexdigest()
 
 
+KERNEL_FAMILIES = {
+    "rollout": ("hjb_common.cuh", "systems.cuh", "rollout_kernel.cuh"),
+    "vhjb": ("hjb_common.cuh", "systems.cuh", "umma.cuh", "vhjb_epilogue.cuh", "vhjb_simt.cuh", "vhjb_tc.cuh"),
+}
+
+
+def source_hash(family: str) -> str:
+    """sha256 (16 hex digits) of the sources a kernel family is compiled from: stamps an ncu capture (profiles/traffic.json)
+    so that bench.py only quotes DRAM traffic measured on the kernel it is timing."""
+    return _digest([os.path.join(CSRC, f) for f in KERNEL_FAMILIES[family]])[:16]
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
     """Compile every .cu under csrc/ for sm_100a and link libhjb_b200.so.  Incremental: an object is rebuilt
     when its source, any header or the flags changed."""

@@ -123,10 +123,13 @@ class VhjbKernels:
         ws = int(L.lib().hjb_vhjb_workspace_bytes(self.n))
         self.workspace = torch.zeros(ws // 4, device="cuda", dtype=torch.float32)    # (zero: the saturation total starts at 0)
         self.norm = torch.empty(2, device="cuda", dtype=torch.float32)
-        # gradient and the two loss sums live back to back so that ONE all-reduce covers both
-        self.grad_and_sums = torch.zeros(self.P + 2, device="cuda", dtype=torch.float32)
+        # gradient, the two loss sums and (multi-GPU) the NEXT step's two local done-counts live back to back so that ONE
+        # all-reduce per step covers all of them
+        self.grad_and_sums = torch.zeros(self.P + 4, device="cuda", dtype=torch.float32)
         self.grad = self.grad_and_sums[: self.P]
-        self.sums = self.grad_and_sums[self.P:]
+        self.sums = self.grad_and_sums[self.P: self.P + 2]
+        self._next_counts = self.grad_and_sums[self.P + 2:]
+        self._pending = None      # (key of the dones tensor, its GLOBAL counts) carried by the previous step's all-reduce
 
     @property
     def impl(self) -> str:
@@ -215,11 +218,22 @@ class VhjbKernels:
                                  float(b1), float(b2), float(eps), int(step), L.stream_ptr()), "hjb_adam")
 
     # ---- one full training step on this rank's shard (shared by VHJBController.params_update and bench.py) ----
-    def train_step(self, params_flat, opt: AdamState, xs, dones, costs, reg: float, lr: float, group=None, loss_acc=None):
+    @staticmethod
+    def _dones_key(dones):
+        return (dones.data_ptr(), dones.numel(), dones._version)
+
+    def train_step(self, params_flat, opt: AdamState, xs, dones, costs, reg: float, lr: float, group=None, loss_acc=None,
+                   next_dones=None, local: bool = False):
         """count -> [all-reduce] -> fused loss+grad -> [all-reduce] -> Adam.  Returns the device tensor
-        [hjb_sum, term_sum] (un-normalised, global) and the norm tensor; no host synchronisation."""
+        [hjb_sum, term_sum] (un-normalised, global) and the norm tensor; no host synchronisation.
+
+        Several GPUs: the normalisers of vhjb.py:241, 253 are sums over the GLOBAL batch and depend on the done flags only.
+        A caller that already knows the next step's batch passes its ``next_dones``: their local counts ride on THIS step's
+        gradient all-reduce (two more floats in the same buffer), and the next call — with that same tensor, unmodified —
+        starts its kernel without a collective of its own: one all-reduce per step instead of two.  ``local=True`` runs the
+        single-process path even when a process group exists (what the N-GPU == 1-GPU verification compares against)."""
         from q_learning_with_hjb_b200 import parallel
-        if not parallel.is_distributed():
+        if local or not parallel.is_distributed():
             # single process: the whole step is one library call and three launches (hjb_vhjb_train_step) — what makes
             # the reference's minibatches of 256 run at ~30 us instead of ~110 us per update
             self._bind(params_flat)
@@ -230,14 +244,24 @@ class VhjbKernels:
                                                 L.ptr(self.sums), L.ptr(loss_acc), L.ptr(self.workspace), L.stream_ptr()),
                     "hjb_vhjb_train_step")
             return self.sums, self.norm
-        self.counts(dones, 0.0)
-        if self.residual_form == "min_time":           # plain mean over the global batch; no boundary term
-            parallel.global_counts(self.norm, 0.0, group)
-            self.norm[1] = 1.0
+        min_time = self.residual_form == "min_time"           # plain mean over the global batch; no boundary term
+        if self._pending is not None and self._pending[0] == self._dones_key(dones):
+            self.norm.copy_(self._pending[1])                  # global counts, delivered by the previous step's all-reduce
+            self.norm += 0.0 if min_time else self.eps
         else:
-            parallel.global_counts(self.norm, self.eps, group)
+            self.counts(dones, 0.0)
+            parallel.global_counts(self.norm, 0.0 if min_time else self.eps, group)
+        self._pending = None
+        if min_time:
+            self.norm[1] = 1.0
         self.loss_grad(params_flat, xs, dones, costs, reg)
-        parallel.sum_across_ranks(self.grad_and_sums, group)
+        if next_dones is not None:
+            L.check(L.lib().hjb_vhjb_count(L.ptr(next_dones), next_dones.numel(), 0.0, L.ptr(self._next_counts),
+                                           L.ptr(self.workspace), L.stream_ptr()), "hjb_vhjb_count")
+            parallel.sum_across_ranks(self.grad_and_sums, group)
+            self._pending = (self._dones_key(next_dones), self._next_counts.clone())
+        else:
+            parallel.sum_across_ranks(self.grad_and_sums[: self.P + 2], group)
         opt.count += 1
         self.adam(params_flat, opt.mu, opt.nu, self.grad, opt.count, lr)
         if loss_acc is not None:
@@ -360,7 +384,7 @@ class VhjbKernels:
             for i, (sl, ev) in enumerate(ups):
                 cur.wait_event(ev)
                 self.loss_grad(params_flat, xs[sl], dones[sl], costs[sl], reg, accumulate=i > 0)
-        parallel.sum_across_ranks(self.grad_and_sums, group)
+        parallel.sum_across_ranks(self.grad_and_sums[: self.P + 2], group)
         opt.count += 1
         if streamed:
             # guarded: a poll that gave up (the batch never arrived) raises the workspace's failure word; the update is then
@@ -432,18 +456,21 @@ class VHJBController(Controller):
         self.maximum_timestep = config.maximum_step
         self.num_of_trajectories_per_epoch = config.num_of_trajectories_per_epoch
 
-        # seed dataset (vhjb.py:136-151): interior points (done 0, cost 0), boundary points (done 1, clipped x^T P x)
+        # seed dataset (vhjb.py:136-151): interior points (done 0, cost 0), boundary points (done 1, clipped x^T P x).
+        # The reference draws one state per np.random.uniform call; ONE (count, n) draw yields the same numbers in the same
+        # order (the legacy generator fills the request in C order), so the RNG stream stays the reference's.
         def sample(mean, std, count):
-            return [self.dynamics.states_wrap(np.random.uniform(low=-1, high=1, size=self.state_dim) * std + mean)
-                    for _ in range(count)]
+            x = np.random.uniform(low=-1, high=1, size=(int(count), self.state_dim)) * std + mean
+            return self.dynamics.states_wrap(x) if count else x
         interior = sample(config.interior_states_mean, config.interior_states_std, config.num_of_interior_data)
         boundary = sample(config.boundary_states_mean, config.boundary_states_std, config.num_of_boundary_data)
         self.replay_buffer = DeviceReplayBuffer(self.state_dim, config.maximum_buffer_size)
-        seed_x = interior + boundary
-        seed_c = [0.0] * len(interior) + [min(self.termination_cost(x), config.boundary_cost_clip) for x in boundary]
-        seed_d = [0.0] * len(interior) + [1.0] * len(boundary)
-        if seed_x:
-            self.replay_buffer.extend(np.stack(seed_x), np.asarray(seed_c), np.asarray(seed_d))
+        if len(interior) + len(boundary):
+            dxb = self.dynamics.states_wrap(np.array(boundary, dtype=np.float64) - self.xf)
+            term = np.einsum("bi,ij,bj->b", dxb, self.P, dxb) if len(boundary) else np.zeros(0)   # termination_cost, batched
+            seed_c = np.concatenate([np.zeros(len(interior)), np.minimum(term, config.boundary_cost_clip)])
+            seed_d = np.concatenate([np.zeros(len(interior)), np.ones(len(boundary))])
+            self.replay_buffer.extend(np.concatenate([interior, boundary]), seed_c, seed_d)
 
     # ---- host-side setup ---------------------------------------------------------------------------------
     def system_additional_init(self) -> None:
@@ -603,10 +630,16 @@ class VHJBController(Controller):
             # (read once per epoch) instead of doing tensor arithmetic on scalars after every update
             plain = type(self).params_update is VHJBController.params_update and "params_update" not in self.__dict__
             acc = self.torch.zeros(3, device="cuda", dtype=self.torch.float32) if plain else None
-            for xs, costs, dones in self.replay_buffer.batches(self.batch_size):
+            # one batch of look-ahead: with several GPUs the next batch's done-counts ride on this step's gradient
+            # all-reduce (VhjbKernels.train_step: one collective per update instead of two)
+            batch_iter = iter(self.replay_buffer.batches(self.batch_size))
+            ahead = next(batch_iter, None)
+            while ahead is not None:
+                (xs, costs, dones), ahead = ahead, next(batch_iter, None)
                 if plain:
                     self.kernels.train_step(self.model_params.flat, self.optimizer_states, xs, dones, costs,
-                                            float(self.regularization), self.lr, loss_acc=acc)
+                                            float(self.regularization), self.lr, loss_acc=acc,
+                                            next_dones=None if ahead is None else ahead[2])
                 else:
                     (self.model_params, self.model_states, self.optimizer_states, total, hjb, term) = self.params_update(
                         self.model_params, self.model_states, self.optimizer_states, xs, dones, costs, self.regularization)

@@ -49,8 +49,26 @@ class Dynamics:
                                 + self.x0_mean)
 
     def get_initial_states(self, count: int) -> np.ndarray:
-        """``count`` consecutive ``get_initial_state()`` draws, stacked [count, n] (same RNG stream)."""
-        return np.stack([self.get_initial_state() for _ in range(count)])
+        """``count`` consecutive ``get_initial_state()`` draws, stacked [count, n]: ONE vectorised draw from the global NumPy
+        RNG — the legacy generator fills a (count, n) request in C order with broadcast bounds, so the numbers are those of
+        ``count`` successive calls (tests/test_host_logic.py)."""
+        x = np.random.uniform(size=(int(count), self.state_dim), low=-self.x0_std, high=self.x0_std) + self.x0_mean
+        return self.states_wrap(x) if count else x
+
+    def sample_initial_states(self, count: int, seed: int = 1234, first: int = 0, mean=None, std=None, out=None):
+        """``count`` initial states generated ON THE DEVICE by the counter-based generator (``hjb_sample_states``; fp32 CUDA
+        tensor [count, n]): the distribution of ``get_initial_state`` — wrap(U(-x0_std, x0_std) + x0_mean), or the given
+        ``mean`` / ``std`` — from a Philox stream keyed by ``seed`` and counted by ``first + i``.  What 16M-environment
+        rollouts start from instead of a host array crossing PCIe; ``first`` = a shard's offset into a global
+        batch."""
+        torch = L.require_cuda()
+        x = torch.empty((int(count), self.state_dim), device="cuda", dtype=torch.float32) if out is None else out
+        assert x.is_cuda and x.dtype == torch.float32 and x.is_contiguous() and tuple(x.shape) == (int(count), self.state_dim)
+        L.check(L.lib().hjb_sample_states(int(self.KIND), self.state_dim,
+                                          L.c_floats(self.x0_mean if mean is None else mean, self.state_dim),
+                                          L.c_floats(self.x0_std if std is None else std, self.state_dim),
+                                          int(seed), int(first), int(count), L.ptr(x), L.stream_ptr()), "hjb_sample_states")
+        return x
 
     def get_dimension(self) -> Tuple[int, int]:
         return self.state_dim, self.control_dim

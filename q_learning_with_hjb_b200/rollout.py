@@ -73,7 +73,8 @@ class BatchedRollout:
 
     def __init__(self, dynamics, controller, n_envs: int, steps: int, integrator: str = "euler",
                  record_stride: int = 0, record_controls: bool = True, cost: Optional[RunningCost] = None,
-                 box: Optional[Box] = None, fast_trig: Optional[bool] = None, want_steps: bool = False):
+                 box: Optional[Box] = None, fast_trig: Optional[bool] = None, want_steps: bool = False,
+                 want_final: bool = True):
         torch = L.require_cuda()
         self.torch = torch
         self.dyn, self.ctl = dynamics, controller
@@ -104,7 +105,9 @@ class BatchedRollout:
         self.n_rec = self.T // record_stride if record_stride > 0 else 0
         self.xs = torch.empty((self.n_rec + 1, self.N, n), **f32) if record_stride > 0 else None
         self.us = torch.empty((self.n_rec, self.N, m), **f32) if (record_stride > 0 and record_controls) else None
-        self.x_final = torch.empty((self.N, n), **f32)
+        # want_final = False: a cost-only plan (the per-environment cost is the result; no final-state write-back, and
+        # run_host brings back N floats instead of N (n + 1))
+        self.x_final = torch.empty((self.N, n), **f32) if want_final else None
         self.cost = torch.empty((self.N,), **f32) if cost is not None else None
         self.steps = torch.empty((self.N,), device="cuda", dtype=torch.int32) if (want_steps or box is not None) else None
         self._x0_dev = None
@@ -143,7 +146,7 @@ class BatchedRollout:
             self._x0_dev = t.empty((self.N, self.n), device="cuda", dtype=t.float32)
             self._pinned = {
                 "x0": t.empty((self.N, self.n), dtype=t.float32, pin_memory=True),
-                "x_final": t.empty((self.N, self.n), dtype=t.float32, pin_memory=True),
+                "x_final": t.empty((self.N, self.n), dtype=t.float32, pin_memory=True) if self.x_final is not None else None,
                 "cost": t.empty((self.N,), dtype=t.float32, pin_memory=True) if self.cost is not None else None,
             }
         return self._pinned
@@ -152,7 +155,7 @@ class BatchedRollout:
         return self.N * self.n * 4
 
     def d2h_bytes(self) -> int:
-        return self.N * self.n * 4 + (self.N * 4 if self.cost is not None else 0)
+        return (self.N * self.n * 4 if self.x_final is not None else 0) + (self.N * 4 if self.cost is not None else 0)
 
     def _launch_range(self, x0_dev, lo: int, hi: int):
         """Envs [lo, hi) of a final-state(+cost) plan on the current stream (the outputs are env-major: a range of
@@ -163,7 +166,8 @@ class BatchedRollout:
         L.check(L.lib().hjb_rollout(self.sys_spec, self.ctl_spec,
                                     self.cost_spec if self.cost_spec is not None else C.POINTER(L.HjbCost)(),
                                     self.opts, L.ptr(x0_dev[sl]), hi - lo, self.T, None, None,
-                                    L.ptr(self.x_final[sl]), L.ptr(self.cost[sl]) if self.cost is not None else None,
+                                    L.ptr(self.x_final[sl]) if self.x_final is not None else None,
+                                    L.ptr(self.cost[sl]) if self.cost is not None else None,
                                     L.ptr(self.steps[sl]) if self.steps is not None else None, L.stream_ptr()),
                 "hjb_rollout")
 
@@ -193,7 +197,8 @@ class BatchedRollout:
         if chunks <= 1:
             self._x0_dev.copy_(pin["x0"], non_blocking=True)
             res = self.launch(self._x0_dev)
-            pin["x_final"].copy_(res.x_final, non_blocking=True)
+            if res.x_final is not None:
+                pin["x_final"].copy_(res.x_final, non_blocking=True)
             if res.cost is not None:
                 pin["cost"].copy_(res.cost, non_blocking=True)
             t.cuda.current_stream().synchronize()
@@ -221,10 +226,55 @@ class BatchedRollout:
                 done.record(run)
             with t.cuda.stream(pipe["d2h"]):
                 pipe["d2h"].wait_event(done)
-                pin["x_final"][sl].copy_(self.x_final[sl], non_blocking=True)
+                if self.x_final is not None:
+                    pin["x_final"][sl].copy_(self.x_final[sl], non_blocking=True)
                 if self.cost is not None:
                     pin["cost"][sl].copy_(self.cost[sl], non_blocking=True)
         pipe["d2h"].synchronize()                            # the last D2H copy follows every launch and every H2D copy
+        return pin["x_final"], pin["cost"]
+
+    def run_seeded(self, seed: int, first: int = 0, chunks: int = 32):
+        """The end-to-end call whose INPUT is a seed: the initial states (the dynamics' own x0 distribution) are generated
+        on the device by the counter-based generator (``hjb_sample_states``: environment i is sample ``first + i`` of the
+        stream keyed by ``seed``), range by range ahead of each range's kernel; the per-environment results come back to
+        pinned host memory.  Nothing crosses PCIe on the way in — what a many-GPU box needs, where eight 400 MB host
+        arrays per step share one root complex."""
+        t = self.torch
+        pin = self._staging()
+        chunks = max(1, min(int(chunks), self.N // 65536)) if self.xs is None else 1
+        if chunks <= 1:
+            self.dyn.sample_initial_states(self.N, seed, first, out=self._x0_dev)
+            res = self.launch(self._x0_dev)
+            if res.x_final is not None:
+                pin["x_final"].copy_(res.x_final, non_blocking=True)
+            if res.cost is not None:
+                pin["cost"].copy_(res.cost, non_blocking=True)
+            t.cuda.current_stream().synchronize()
+            return pin["x_final"], pin["cost"]
+        pipe = self._pipeline()
+        cur = t.cuda.current_stream()
+        start = t.cuda.Event()
+        start.record(cur)
+        for s_ in (pipe["d2h"], *pipe["run"]):
+            s_.wait_event(start)
+        step = -(-self.N // chunks)
+        step = -(-step // 256) * 256
+        for c, lo in enumerate(range(0, self.N, step)):
+            hi = min(self.N, lo + step)
+            sl = slice(lo, hi)
+            run = pipe["run"][c & 1]
+            with t.cuda.stream(run):
+                self.dyn.sample_initial_states(hi - lo, seed, first + lo, out=self._x0_dev[sl])
+                self._launch_range(self._x0_dev, lo, hi)
+                done = t.cuda.Event()
+                done.record(run)
+            with t.cuda.stream(pipe["d2h"]):
+                pipe["d2h"].wait_event(done)
+                if self.x_final is not None:
+                    pin["x_final"][sl].copy_(self.x_final[sl], non_blocking=True)
+                if self.cost is not None:
+                    pin["cost"][sl].copy_(self.cost[sl], non_blocking=True)
+        pipe["d2h"].synchronize()
         return pin["x_final"], pin["cost"]
 
     def pinned_x0(self):

@@ -157,3 +157,40 @@ def test_header_is_plain_c_and_a_c_caller_links():
                         f"-Wl,-rpath,{libdir}"], check=True)
         out = subprocess.run([exe], check=True, capture_output=True, text=True).stdout.strip()
         assert int(out) == len(names)
+
+
+def test_vectorised_initial_states_are_the_reference_stream():
+    """Dynamics.get_initial_states(count) is ONE NumPy draw; it must produce the numbers of `count` successive
+    get_initial_state() calls (dynamics_basic.py:28-29) — the notebook known-answer tests depend on the draw offsets."""
+    from tests.helpers import make_dynamics
+    for kind in ("cartpole", "quad2d", "quad10d", "linear"):
+        dyn = make_dynamics(kind)
+        np.random.seed(3)
+        loop = np.stack([dyn.get_initial_state() for _ in range(257)])
+        np.random.seed(3)
+        batch = dyn.get_initial_states(257)
+        np.testing.assert_array_equal(loop, batch)
+        assert np.random.uniform() == np.random.RandomState(3).uniform(size=257 * dyn.state_dim + 1)[-1]   # same stream position
+    assert make_dynamics("quad2d").get_initial_states(0).shape == (0, 6)
+
+
+def test_counter_based_state_stream_twin():
+    """oracle/x0_stream.py (the NumPy twin of hjb_sample_states): Philox4x32-10 against the published Random123 known
+    answers; sample i does not depend on how the batch is split; distribution = wrap(U(-std, std) + mean)."""
+    from oracle import x0_stream as X
+    kat = [((0, 0), (0, 0, 0, 0), (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)),
+           ((0xffffffff, 0xffffffff), (0xffffffff,) * 4, (0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd)),
+           ((0xa4093822, 0x299f31d0), (0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344),
+            (0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1))]
+    for key, ctr, want in kat:
+        got = X.philox4x32_10(key[0], key[1], *[np.array([c]) for c in ctr])
+        assert tuple(int(v[0]) for v in got) == want
+    mean, std = np.float32([0, 3.14, 0, 0]), np.float32([2.4, 0.05, 1, 0.05])
+    whole = X.sample_states("cartpole", mean, std, 1234, 0, 5000)
+    parts = np.concatenate([X.sample_states("cartpole", mean, std, 1234, lo, 1250) for lo in range(0, 5000, 1250)])
+    np.testing.assert_array_equal(whole, parts)
+    assert whole.dtype == np.float32 and not np.array_equal(whole, X.sample_states("cartpole", mean, std, 1235, 0, 5000))
+    assert (np.abs(whole[:, 0]) <= 2.4).all() and (whole[:, 1] >= -np.pi).all() and (whole[:, 1] < np.pi).all()
+    raw = np.where(whole[:, 1] < 0, whole[:, 1] + 2 * np.pi, whole[:, 1])          # un-wrap: 3.14 +- 0.05
+    assert abs(raw.mean() - 3.14) < 2e-3 and raw.min() >= 3.09 - 1e-6 and raw.max() <= 3.19 + 1e-6
+    assert abs(whole[:, 2].std() - 1 / np.sqrt(3)) < 0.02

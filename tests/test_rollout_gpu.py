@@ -527,3 +527,23 @@ def test_energy_shaping_branch_methods_and_demo_loops():
     t, xs, us, e = AE.test_acrobot(ac, make_controller("acrobot_es", ac), tf=5.0, plot=False)
     assert xs.shape == (len(t), 4) and e.shape == (len(t),) and np.isfinite(e).all()
     np.testing.assert_allclose(xs[0], [0.001, 0, 0, 0], atol=1e-7)
+
+
+@pytest.mark.parametrize("skind", ["linear", "cartpole", "acrobot", "quad2d", "quad10d"])
+def test_device_state_generator_equals_its_numpy_twin(skind):
+    """hjb_sample_states (Philox4x32-10, counted by the global sample index) against oracle/x0_stream.py: bit-exact, and
+    a batch generated in shards (first = the shard's offset) is the same batch."""
+    torch = _cuda()
+    from oracle import x0_stream as X
+    dyn = make_dynamics(skind)
+    N = 100_003
+    x = dyn.sample_initial_states(N, seed=1234)
+    ref = X.sample_states(skind, dyn.x0_mean, dyn.x0_std, 1234, 0, N)
+    assert x.shape == (N, dyn.state_dim) and x.dtype == torch.float32
+    np.testing.assert_array_equal(x.cpu().numpy(), ref)
+    a = dyn.sample_initial_states(40_000, seed=1234)
+    b = dyn.sample_initial_states(N - 40_000, seed=1234, first=40_000)
+    assert torch.equal(torch.cat([a, b]), x)
+    big = dyn.sample_initial_states(7, seed=2**40 + 5, first=2**33)                # 64-bit seed and counter
+    np.testing.assert_array_equal(big.cpu().numpy(), X.sample_states(skind, dyn.x0_mean, dyn.x0_std, 2**40 + 5, 2**33, 7))
+    assert dyn.sample_initial_states(0).shape == (0, dyn.state_dim)
