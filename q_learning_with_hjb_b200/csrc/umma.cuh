@@ -138,6 +138,28 @@ __device__ __forceinline__ void mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_
       "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(0u)
       : "memory");
 }
+// A operand in TENSOR MEMORY (row m of the M = 128 tile in lane m; 32-bit column c holds k = 2c in the low half and
+// k = 2c + 1 in the high half; one K = 16 step = 8 columns), B from shared memory; every field but the two bases an
+// immediate (see mma_imm).  tests/cuda/ts_probe.cu checks the layout against a CPU GEMM and measures the issue rate.
+template <uint32_t ACOL, uint32_t B_LO, uint32_t B_HI, uint32_t IDESC, uint32_t DCOL>
+__device__ __forceinline__ void mma_ts_imm(uint32_t tmem_base, uint32_t sbd, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      ".reg .b32 bl, bh, dd, aa, id;\n\t"
+      ".reg .b64 db;\n\t"
+      "add.u32 bl, %1, %4;\n\t"
+      "mov.u32 bh, %5;\n\t"
+      "add.u32 dd, %0, %7;\n\t"
+      "add.u32 aa, %0, %3;\n\t"
+      "mov.u32 id, %6;\n\t"
+      "mov.b64 db, {bl, bh};\n\t"
+      "setp.ne.b32 p, %2, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [dd], [aa], db, id, p;\n\t"
+      "}\n" ::"r"(tmem_base),
+      "r"(sbd), "r"(accumulate), "n"(ACOL), "n"(B_LO), "n"(B_HI), "n"(IDESC), "n"(DCOL)
+      : "memory");
+}
 // all previously issued MMAs of this thread arrive on `bar` when complete (implies fence::before_thread_sync)
 __device__ __forceinline__ void mma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -189,6 +211,12 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16
       "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),
       "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
       : "memory");
+}
+
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&v)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(v[0]), "r"(v[1]),
+               "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+               : "memory");
 }
 
 // ---- BF16x3 split ----------------------------------------------------------------------------------------

@@ -28,6 +28,7 @@
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 
+#include <cstdlib>
 #include <type_traits>
 #include <utility>
 
@@ -1317,6 +1318,14 @@ __global__ void __launch_bounds__(kResThreads, 1) vhjb_tc_residual_kernel(const 
   if (warp == 0) tmem_dealloc(tm, 512);
 }
 
+}  // namespace tc
+}  // namespace hjb
+
+#include "vhjb_tc_res.cuh"   // the states-on-lanes residual kernel (relu nets)
+
+namespace hjb {
+namespace tc {
+
 template <class S, int ACT, int UFORM, int RFORM>
 inline cudaError_t launch_vhjb_tc_variant(const VhjbArgs& a, const VhjbLaunch& l, cudaStream_t st) {
   cudaError_t e;
@@ -1330,6 +1339,21 @@ inline cudaError_t launch_vhjb_tc_variant(const VhjbArgs& a, const VhjbLaunch& l
     e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
     if (e != cudaSuccess) return e;
     k<<<l.grid, kThreads, kSmemBytes, st>>>(a);
+  } else if constexpr (ACT == HJB_ACT_RELU) {
+    // states on the TMEM lanes, activations fed from tensor memory (vhjb_tc_res.cuh); HJB_VHJB_RESIDUAL=v1: the round-1
+    // kernel (features on the lanes), kept for A/B measurements
+    static const bool v1 = [] { const char* e = std::getenv("HJB_VHJB_RESIDUAL"); return e && e[0] == 'v' && e[1] == '1'; }();
+    if (v1) {
+      auto k = vhjb_tc_residual_kernel<S, ACT, UFORM, RFORM, kF16>;
+      e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kResSmemBytes);
+      if (e != cudaSuccess) return e;
+      k<<<l.grid, kResThreads, kResSmemBytes, st>>>(a);
+    } else {
+      auto k = vhjb_tc_residual2_kernel<S, UFORM, RFORM, kF16>;
+      e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRes2SmemBytes);
+      if (e != cudaSuccess) return e;
+      k<<<l.grid, kRes2Threads, kRes2SmemBytes, st>>>(a);
+    }
   } else {
     auto k = vhjb_tc_residual_kernel<S, ACT, UFORM, RFORM, kF16>;
     e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kResSmemBytes);
