@@ -302,18 +302,26 @@ int hjb_vhjb_train_step(const hjb_system* sys, const hjb_vnet* net, const hjb_ta
                         void* stream);
 
 /*
- * Range check of the last hjb_vhjb_loss_grad on this workspace (device float `count`, stream-ordered).  The
- * tensor-core gradient pass carries per-state adjoints in fp16 with per-state power-of-two scaling (vhjb_tc.cuh);
- * a state whose adjoint seed exceeds 2^12 times the batch-typical weight (|x - xf| and |u - uf| ~ 1e-2 and below reach
- * that with the reference's eps = 1e-10), or whose adjoint chain grows past fp16's 65504 (a gain above ~1000 between the
- * seeds and the first layer: conversions saturate, nothing becomes inf / NaN), is clipped and counted here.  0 for every
- * other batch; callers that need those states exactly set hjb_vnet.impl = 1 (the fp32 CUDA-core kernels).
+ * Range management of the tensor-core gradient pass, and what is left of it for the caller to check.  The pass carries
+ * per-state adjoints in fp16 with per-state power-of-two scaling (vhjb_tc.cuh).  A state whose adjoint seeds exceed 2^6
+ * times the batch-typical weight (|x - xf|, |u - uf| of order 0.1 and below with the reference's eps = 1e-10; a terminal
+ * sample stored with cost ~ 0) does NOT go through that chain: the kernel records its index and the fp32 CUDA-core kernel,
+ * launched behind it by the same entry point, computes exactly those states; their weight gradients are summed after the
+ * tensor kernel's partials in a fixed order (hjb_vhjb_deferred: how many states of the last launch took that pass).
+ * What remains countable: a deferred list that is full (2048 states per epilogue warp of the tensor kernel: the state
+ * then stays on the tensor path with clipped seeds), or an adjoint chain that grows past fp16's 65504 between the seeds
+ * and the first layer (a gain above ~1000: conversions saturate, nothing becomes inf / NaN).  hjb_vhjb_saturation returns
+ * that count for the last hjb_vhjb_loss_grad on this workspace (device float `count`, stream-ordered): 0 for every batch
+ * met in the reference's configurations; callers that see non-zero set hjb_vnet.impl = 1 (fp32 CUDA-core kernels).
  */
 int hjb_vhjb_saturation(const void* workspace, int32_t n, float* count, void* stream);
 /* The same count summed over every gradient launch on this workspace since the last reset (count nullable; reset != 0
  * zeroes the total after reading it; zero it once — or zero-fill the workspace — before the first use): what a training
  * loop polls once per epoch instead of once per update. */
 int hjb_vhjb_saturation_total(void* workspace, int32_t n, float* count, int32_t reset, void* stream);
+/* States of the last gradient launch that were computed by the fp32 pass instead of the tensor chain (see above);
+ * `count`: device or pinned host float. */
+int hjb_vhjb_deferred(const void* workspace, int32_t n, float* count, void* stream);
 
 /*
  * One step of the learned-policy rollout for N trajectories at once (VHJBController.rollout_trajectory,

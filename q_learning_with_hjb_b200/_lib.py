@@ -100,6 +100,7 @@ SYMBOLS = {
     "hjb_vhjb_adam_guarded": (C.c_int, [_P, _P, _P, _P, C.c_int32, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int32,
                                         _P, _P]),
     "hjb_vhjb_saturation": (C.c_int, [_P, C.c_int32, _P, _P]),
+    "hjb_vhjb_deferred": (C.c_int, [_P, C.c_int32, _P, _P]),
     "hjb_vhjb_saturation_total": (C.c_int, [_P, C.c_int32, _P, C.c_int32, _P]),
     "hjb_policy_step": (C.c_int, [C.POINTER(HjbSystem), C.POINTER(HjbTask), C.POINTER(C.c_float), C.POINTER(C.c_float),
                                   C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_int32, _P, _P, _P, _P, _P, _P, _P,

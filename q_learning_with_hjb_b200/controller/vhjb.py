@@ -174,11 +174,20 @@ class VhjbKernels:
         return self.grad, self.sums
 
     def saturated(self) -> int:
-        """Number of states of the last ``loss_grad`` whose adjoint seed left the tensor-core kernel's fp16 range
-        management (include/hjb_b200.h ``hjb_vhjb_saturation``); 0 except for states within ~1e-4 of the goal.
+        """Number of states of the last ``loss_grad`` that the tensor-core kernel had to clip (include/hjb_b200.h
+        ``hjb_vhjb_saturation``): out-of-range seeds are deferred to the fp32 pass (``deferred()``), so what is counted
+        here is a full deferred list or an adjoint chain beyond fp16's range — 0 in every reference configuration.
         Synchronises the stream."""
         out = self.torch.zeros(1, device="cuda", dtype=self.torch.float32)
         L.check(L.lib().hjb_vhjb_saturation(L.ptr(self.workspace), self.n, L.ptr(out), L.stream_ptr()), "hjb_vhjb_saturation")
+        return int(out.item())
+
+    def deferred(self) -> int:
+        """States of the last ``loss_grad`` / ``train_step`` that the tensor-core kernel handed to the fp32 pass (their
+        adjoint seeds lie beyond its fp16 range management: near-goal states, terminal samples with cost ~ 0).
+        Synchronises the stream."""
+        out = self.torch.zeros(1, device="cuda", dtype=self.torch.float32)
+        L.check(L.lib().hjb_vhjb_deferred(L.ptr(self.workspace), self.n, L.ptr(out), L.stream_ptr()), "hjb_vhjb_deferred")
         return int(out.item())
 
     def saturated_total(self, reset: bool = True) -> int:
@@ -657,10 +666,11 @@ class VHJBController(Controller):
                 avg_total.append(float(totals) / n_batches)
                 avg_hjb.append(float(hjbs) / n_batches)
                 avg_term.append(float(terms) / n_batches)
-            # Range check of the tensor-core gradient pass, once per epoch (one host read): a state whose adjoint seeds
-            # or chain gain left the fp16 range management was clipped and counted, never silently — from here on the
-            # fp32 CUDA-core kernels take over (they are exact for any range; ~10x slower on large batches, no
-            # difference at the reference's batch size of 256).
+            # Range check of the tensor-core gradient pass, once per epoch (one host read).  States whose adjoint seeds lie
+            # beyond the fp16 range management take the fp32 pass behind the tensor kernel in every update (exact, no
+            # switch of kernels); what can still be counted here is an adjoint CHAIN that outgrew fp16 (a backward gain
+            # above ~1000 — not met in any reference configuration): clipped and counted, never silent, and from then on the
+            # fp32 CUDA-core kernels take over.
             if n_batches and self.kernels.impl == "tensor" and self.kernels.saturated_total() > 0:
                 self.kernels.impl = "simt"
                 print(f"epoch:{epoch + 1}, adjoint range check tripped: continuing with the fp32 CUDA-core kernels")

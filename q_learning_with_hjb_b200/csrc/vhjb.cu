@@ -11,7 +11,11 @@
 
 namespace hjb {
 
-constexpr int kMaxCtas = 160;  // >= SM count (148 on B200)
+constexpr int kMaxCtas = 160;  // >= SM count (148 on B200): per-CTA partial slots of the main launch
+// Workspace: [kMaxCtas slots: main launch][kMaxCtas slots: fp32 pass over the deferred states][4 tail words]
+//            (tail: 8 floats)  [int defer_count[4 kMaxCtas]][int defer_index[4 kMaxCtas][kDeferCap]]
+constexpr int kSlots = 2 * kMaxCtas;
+constexpr int kDeferLists = 4 * kMaxCtas;
 
 // Kernel selection: the tcgen05 kernel (vhjb_tc.cuh) for every compiled combination (relu / tanh / sin value nets);
 // the CUDA-core kernel (vhjb_simt.cuh) is the fp32 reference implementation on the device.  HJB_VHJB_IMPL=simt forces the CUDA-core kernel (A/B measurements, parity).
@@ -25,12 +29,19 @@ static int64_t pstride_of(int n) { return ((int64_t)vhjb_param_count(n) + 2 + 3)
 
 // grad[j] = sum over CTAs (fixed order) of partial[cta][j]; j in [first, first + count)
 // (accumulate: out[j] += the sum — a batch processed as several launches, in launch order)
+// dtail != null: the fp32 pass over the deferred states ran behind the main launch; its CTAs 0 .. dtail[3] - 1 wrote
+// partials into the slots kMaxCtas onwards, summed after the main launch's (same fixed order in every run)
 __global__ void __launch_bounds__(256) vhjb_reduce_kernel(const float* __restrict__ partial, int64_t pstride, int ncta,
-                                                          int first, int count, float* __restrict__ out, int accumulate) {
+                                                          int first, int count, float* __restrict__ out, int accumulate,
+                                                          const float* __restrict__ dtail) {
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= count) return;
   float s = 0.f;
   for (int c = 0; c < ncta; ++c) s += partial[(int64_t)c * pstride + first + j];
+  if (dtail != nullptr) {
+    const int nd = (int)dtail[3];
+    for (int c = 0; c < nd; ++c) s += partial[(int64_t)(kMaxCtas + c) * pstride + first + j];
+  }
   out[j] = accumulate ? out[j] + s : s;
 }
 
@@ -130,11 +141,15 @@ __global__ void __launch_bounds__(256) vhjb_reduce_adam_kernel(const float* __re
                                                                float* __restrict__ m, float* __restrict__ v, float lr, float b1,
                                                                float b2, float eps, float bc1, float bc2,
                                                                const float* __restrict__ norm, float reg,
-                                                               float* __restrict__ loss_acc) {
+                                                               float* __restrict__ loss_acc, const float* __restrict__ dtail) {
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j < P) {
     float g = 0.f;
     for (int c = 0; c < ncta; ++c) g += partial[(int64_t)c * pstride + j];
+    if (dtail != nullptr) {   // the fp32 pass over the deferred states (see vhjb_reduce_kernel)
+      const int nd = (int)dtail[3];
+      for (int c = 0; c < nd; ++c) g += partial[(int64_t)(kMaxCtas + c) * pstride + j];
+    }
     grad[j] = g;
     const float mi = fmaf(b1, m[j], (1.f - b1) * g);
     const float vi = fmaf(b2, v[j], (1.f - b2) * g * g);
@@ -228,6 +243,9 @@ static int run_vhjb(const hjb_system* sys, const hjb_vnet* net, const hjb_task* 
   a.V = V; a.p = p; a.u = u; a.r = r;
   a.partial = static_cast<float*>(workspace);
   a.pstride = pstride_of(n);
+  a.tail = a.partial + (int64_t)kSlots * a.pstride;
+  a.defer_count = reinterpret_cast<int*>(a.tail + 8);
+  a.defer_index = a.defer_count + kDeferLists;
   const bool tensor = use_tensor_path(net, B);
   const int tile = tensor ? tc::TS : VBM;
   a.n_tiles = (B + tile - 1) / tile;
@@ -257,6 +275,7 @@ static int run_vhjb(const hjb_system* sys, const hjb_vnet* net, const hjb_task* 
   int64_t grid = cta_tiles < sm_count() ? cta_tiles : sm_count();
   if (grid < 1) grid = 1;
   l.grid = (int)grid;
+  a.defer_lists = 4 * l.grid;
 
   cudaError_t e = cudaErrorNotSupported;
   if (tensor) {
@@ -281,6 +300,34 @@ static int run_vhjb(const hjb_system* sys, const hjb_vnet* net, const hjb_task* 
   }
   if (e == cudaErrorNotSupported) return HJB_ERR_UNSUPPORTED;
   if (e != cudaSuccess) return (int)e;
+  // The tensor-core gradient kernel leaves the states whose adjoint seeds lie beyond its fp16 range management to this
+  // launch: the CUDA-core kernel over exactly those states (fp32), partials into the second half of the slots.  CTAs
+  // without work return before touching their weights: an empty pass costs one launch.
+  const bool deferred = tensor && want_grad;
+  if (deferred) {
+    VhjbArgs d = a;
+    d.defer_gather = 1;
+    d.part_slot0 = kMaxCtas;
+    d.ready = nullptr;
+    d.dbg = nullptr;
+    VhjbLaunch ld;
+    ld.grad = true;
+    const int64_t dt = (B + VBM - 1) / VBM;
+    ld.grid = (int)(dt < sm_count() ? dt : sm_count());
+    cudaError_t de = cudaErrorNotSupported;
+    switch (sys->kind) {
+      case HJB_SYS_LINEAR:
+        if (n == 2 && m == 1) de = vhjb_launch_linear21(d, ld, net->act, task->control_form, task->residual_form, st);
+        break;
+      case HJB_SYS_CARTPOLE: de = vhjb_launch_cartpole(d, ld, net->act, task->control_form, task->residual_form, st); break;
+      case HJB_SYS_QUAD2D: de = vhjb_launch_quad2d(d, ld, net->act, task->control_form, task->residual_form, st); break;
+      case HJB_SYS_QUAD10D: de = vhjb_launch_quad10d(d, ld, net->act, task->control_form, task->residual_form, st); break;
+      default: break;
+    }
+    if (de == cudaErrorNotSupported) return HJB_ERR_UNSUPPORTED;
+    if (de != cudaSuccess) return (int)de;
+  }
+  const float* dtail = deferred ? a.tail : nullptr;
   if (dbg) {  // developer probe: clock64 at (after wait_mma, end of pass) of every step of CTA 0's third tile
     long long h[64];
     cudaStreamSynchronize(st);
@@ -294,26 +341,24 @@ static int run_vhjb(const hjb_system* sys, const hjb_vnet* net, const hjb_task* 
   }
   const int P = vhjb_param_count(n);
   if (tail) {
-    vhjb_reduce_adam_kernel<<<(P + 255) / 256, 256, 0, st>>>(a.partial, a.pstride, l.grid, P, grad, sums,
-                                                             a.partial + (int64_t)kMaxCtas * a.pstride, tail->w, tail->m, tail->v,
-                                                             tail->lr, tail->b1, tail->b2, tail->eps, tail->bc1, tail->bc2, norm, reg,
-                                                             tail->loss_acc);
+    vhjb_reduce_adam_kernel<<<(P + 255) / 256, 256, 0, st>>>(a.partial, a.pstride, l.grid, P, grad, sums, a.tail, tail->w, tail->m,
+                                                             tail->v, tail->lr, tail->b1, tail->b2, tail->eps, tail->bc1, tail->bc2,
+                                                             norm, reg, tail->loss_acc, dtail);
     e = cudaGetLastError();
     return e == cudaSuccess ? HJB_OK : (int)e;
   }
   if (want_grad) {
-    vhjb_reduce_kernel<<<(P + 255) / 256, 256, 0, st>>>(a.partial, a.pstride, l.grid, 0, P, grad, (int)accumulate);
+    vhjb_reduce_kernel<<<(P + 255) / 256, 256, 0, st>>>(a.partial, a.pstride, l.grid, 0, P, grad, (int)accumulate, dtail);
     e = cudaGetLastError();
     if (e != cudaSuccess) return (int)e;
   }
   if (sums) {
-    vhjb_reduce_kernel<<<1, 256, 0, st>>>(a.partial, a.pstride, l.grid, P, 2, sums, (int)accumulate);
+    vhjb_reduce_kernel<<<1, 256, 0, st>>>(a.partial, a.pstride, l.grid, P, 2, sums, (int)accumulate, nullptr);
     e = cudaGetLastError();
     if (e != cudaSuccess) return (int)e;
   }
   if (want_grad) {  // saturation count of the fp16 range management (vhjb_tc.cuh) -> workspace tail
-    vhjb_sat_kernel<<<1, 32, 0, st>>>(a.partial, a.pstride, l.grid, P + 2, a.partial + (int64_t)kMaxCtas * a.pstride, (int)accumulate,
-                                      ready != nullptr, sums);
+    vhjb_sat_kernel<<<1, 32, 0, st>>>(a.partial, a.pstride, l.grid, P + 2, a.tail, (int)accumulate, ready != nullptr, sums);
     e = cudaGetLastError();
     if (e != cudaSuccess) return (int)e;
   }
@@ -330,28 +375,36 @@ int64_t hjb_vhjb_param_count(int32_t n) { return n > 0 && n <= HJB_MAX_N ? vhjb_
 
 int64_t hjb_vhjb_workspace_bytes(int32_t n) {
   if (n <= 0 || n > HJB_MAX_N) return -1;
-  return ((int64_t)kMaxCtas * pstride_of(n) + 4) * (int64_t)sizeof(float);
+  return ((int64_t)kSlots * pstride_of(n) + 8) * (int64_t)sizeof(float) +
+         ((int64_t)kDeferLists + (int64_t)kDeferLists * kDeferCap) * (int64_t)sizeof(int);
 }
 
 int hjb_vhjb_saturation(const void* workspace, int32_t n, float* count, void* stream) {
   if (!workspace || !count || n <= 0 || n > HJB_MAX_N) return HJB_ERR_BAD_ARG;
-  const float* tail = static_cast<const float*>(workspace) + (int64_t)kMaxCtas * pstride_of(n);
+  const float* tail = static_cast<const float*>(workspace) + (int64_t)kSlots * pstride_of(n);
   cudaError_t e = cudaMemcpyAsync(count, tail, sizeof(float), cudaMemcpyDeviceToDevice, (cudaStream_t)stream);
   return e == cudaSuccess ? HJB_OK : (int)e;
 }
 
 int hjb_vhjb_saturation_total(void* workspace, int32_t n, float* count, int32_t reset, void* stream) {
   if (!workspace || n <= 0 || n > HJB_MAX_N) return HJB_ERR_BAD_ARG;
-  float* tail = static_cast<float*>(workspace) + (int64_t)kMaxCtas * pstride_of(n);
+  float* tail = static_cast<float*>(workspace) + (int64_t)kSlots * pstride_of(n);
   cudaError_t e = cudaSuccess;
   if (count) e = cudaMemcpyAsync(count, tail + 1, sizeof(float), cudaMemcpyDeviceToDevice, (cudaStream_t)stream);
   if (e == cudaSuccess && reset) e = cudaMemsetAsync(tail + 1, 0, sizeof(float), (cudaStream_t)stream);
   return e == cudaSuccess ? HJB_OK : (int)e;
 }
 
+int hjb_vhjb_deferred(const void* workspace, int32_t n, float* count, void* stream) {
+  if (!workspace || !count || n <= 0 || n > HJB_MAX_N) return HJB_ERR_BAD_ARG;
+  const float* tail = static_cast<const float*>(workspace) + (int64_t)kSlots * pstride_of(n);
+  cudaError_t e = cudaMemcpyAsync(count, tail + 4, sizeof(float), cudaMemcpyDefault, (cudaStream_t)stream);
+  return e == cudaSuccess ? HJB_OK : (int)e;
+}
+
 int hjb_vhjb_stream_failures(void* workspace, int32_t n, float* count, int32_t reset, void* stream) {
   if (!workspace || n <= 0 || n > HJB_MAX_N) return HJB_ERR_BAD_ARG;
-  float* tail = static_cast<float*>(workspace) + (int64_t)kMaxCtas * pstride_of(n);
+  float* tail = static_cast<float*>(workspace) + (int64_t)kSlots * pstride_of(n);
   cudaError_t e = cudaSuccess;
   if (count) e = cudaMemcpyAsync(count, tail + 2, sizeof(float), cudaMemcpyDefault, (cudaStream_t)stream);
   if (e == cudaSuccess && reset) e = cudaMemsetAsync(tail + 2, 0, sizeof(float), (cudaStream_t)stream);
@@ -364,7 +417,7 @@ int hjb_vhjb_adam_guarded(float* params, float* m, float* v, const float* grad, 
   const int64_t len = vhjb_param_count(n);
   const float bc1 = (float)(1.0 - std::pow((double)b1, (double)step));
   const float bc2 = (float)(1.0 - std::pow((double)b2, (double)step));
-  const float* guard = static_cast<const float*>(workspace) + (int64_t)kMaxCtas * pstride_of(n) + 2;
+  const float* guard = static_cast<const float*>(workspace) + (int64_t)kSlots * pstride_of(n) + 2;
   adam_guarded_kernel<<<(unsigned)((len + 255) / 256), 256, 0, (cudaStream_t)stream>>>(params, m, v, grad, len, lr, b1, b2, eps, bc1,
                                                                                        bc2, guard);
   cudaError_t e = cudaGetLastError();

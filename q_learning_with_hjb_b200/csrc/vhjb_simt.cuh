@@ -50,11 +50,24 @@ struct VhjbArgs {
   const int* ready;
   int64_t piece_tiles;
   unsigned poll_limit;  // polls (2 us apart) before a wait for a piece gives up: 2^22 (~8 s); HJB_STREAM_POLL_LIMIT overrides
+  // Deferred states (tensor-core gradient kernel -> fp32 pass): a state whose adjoint seeds lie beyond the fp16 range
+  // management of vhjb_tc.cuh contributes NOTHING on the tensor path; its index is appended to the list of the (CTA,
+  // epilogue warp) that met it — defer_index[list][0 .. defer_count[list]) in tile order, so the lists are the same in
+  // every run — and the CUDA-core kernel, launched behind the tensor kernel with defer_gather = 1, runs exactly those
+  // states in fp32 and adds their weight gradients through its own per-CTA partial slots (part_slot0 onwards).
+  int* defer_count;     // [defer_lists]
+  int* defer_index;     // [defer_lists][kDeferCap]
+  int defer_lists;      // lists in use = 4 x (CTAs of the tensor launch)
+  int defer_gather;     // CUDA-core kernel: 1 = the batch is the concatenation of the deferred lists
+  int part_slot0;       // first per-CTA partial slot of this launch
+  float* tail;          // workspace tail words: [0] saturation (launch), [1] saturation (total), [2] stream failures,
+                        // [3] CTAs of the deferred pass that wrote partials, [4] deferred states of the last launch
 };
+constexpr int kDeferCap = 2048;   // entries per list; a list that is full counts further states as saturated (not deferred)
 
 __host__ __device__ constexpr int vhjb_param_count(int n) { return n * VH1 + VH1 * VH2 + VH2 * VH3; }
 __host__ __device__ constexpr int vhjb_smem_floats(int n) {
-  return vhjb_param_count(n) + 6 * VH1 * VLD + 2 * VH3 * VLD + 3 * n * VLD + VBM;
+  return vhjb_param_count(n) + 6 * VH1 * VLD + 2 * VH3 * VLD + 3 * n * VLD + VBM + 640;   // + prefix sums of the deferred lists
 }
 
 template <int ACT>
@@ -174,6 +187,38 @@ __global__ void __launch_bounds__(VTHREADS, 1) vhjb_kernel(const __grid_constant
   const int ti = tid >> 4, to = tid & 15;        // 16 x 16 thread grid of the weight-gradient blocks
   const int o1 = tid & 127, ih1 = tid >> 7;      // W1-bar: column o1, rows ih1 + 2a
 
+  // ---- deferred-state mode: the batch is the concatenation of the tensor kernel's deferred lists ----
+  int* sPre = reinterpret_cast<int*>(sVb + VBM);     // [defer_lists + 1] exclusive prefix sums of the list lengths
+  int64_t n_tiles = a.n_tiles;
+  int64_t n_states = a.B;
+  if constexpr (GRAD) {
+    if (a.defer_gather) {
+      if (warp == 0) {
+        int run = 0;
+        for (int base = 0; base < a.defer_lists; base += 32) {
+          const int l = base + lane;
+          const int c = l < a.defer_lists ? min(__ldcg(a.defer_count + l), kDeferCap) : 0;
+          int inc = c;
+#pragma unroll
+          for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += t;
+          }
+          if (l < a.defer_lists) sPre[l] = run + inc - c;
+          run += __shfl_sync(0xffffffffu, inc, 31);
+        }
+        if (lane == 0) sPre[a.defer_lists] = run;
+      }
+      __syncthreads();
+      n_states = sPre[a.defer_lists];
+      n_tiles = (n_states + VBM - 1) / VBM;
+      if (blockIdx.x == 0 && tid == 0) {
+        a.tail[3] = (float)min((int64_t)gridDim.x, n_tiles);
+        a.tail[4] = (float)n_states;                      // hjb_vhjb_deferred: states of this launch that took the fp32 pass
+      }
+      if ((int64_t)blockIdx.x >= n_tiles) return;      // (whole CTA: nothing to do, no partial written, none read)
+    }
+  }
   {  // weights -> shared memory, once per CTA
     constexpr int P4 = vhjb_param_count(N) / 4;
     const float4* src = reinterpret_cast<const float4*>(a.params);
@@ -205,9 +250,20 @@ __global__ void __launch_bounds__(VTHREADS, 1) vhjb_kernel(const __grid_constant
   }
   __syncthreads();
 
-  for (int64_t tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
-    const int64_t idx = tile * VBM + lane;   // the state this lane owns
-    const bool valid = idx < a.B;
+  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    int64_t idx = tile * VBM + lane;   // the state this lane owns
+    const bool valid = idx < n_states;
+    if constexpr (GRAD) {
+      if (a.defer_gather && warp == 0) {   // entry idx of the concatenated lists: binary search over the prefix sums
+        int lo = 0, hi = a.defer_lists;
+        const int j = (int)idx;
+        while (hi - lo > 1) {
+          const int mid = (lo + hi) >> 1;
+          if (sPre[mid] <= j) lo = mid; else hi = mid;
+        }
+        idx = valid ? (int64_t)__ldcg(a.defer_index + (int64_t)lo * kDeferCap + (j - sPre[lo])) : 0;
+      }
+    }
     // ---- phase 0: load states, error coordinates, normalised input (vhjb.py:39, :45) ----
     float xraw[N];
     if (warp == 0) {
@@ -440,8 +496,9 @@ __global__ void __launch_bounds__(VTHREADS, 1) vhjb_kernel(const __grid_constant
   }
 
   // ---- per-CTA partials ----
-  float* part = a.partial + (int64_t)blockIdx.x * a.pstride;
+  float* part = a.partial + (int64_t)(blockIdx.x + a.part_slot0) * a.pstride;
   if constexpr (GRAD) {
+    if (a.defer_gather) { hjb_sum = 0.f; term_sum = 0.f; }   // the tensor kernel's epilogue already counted these states
 #pragma unroll
     for (int q = 0; q < NA1; ++q) {
       const int i = ih1 + 2 * q;

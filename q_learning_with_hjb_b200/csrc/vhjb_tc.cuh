@@ -523,6 +523,7 @@ __global__ void __launch_bounds__(kThreads, 1) vhjb_tc_kernel(const __grid_const
     bool vnext = false;
     float Vsum = 0.f, Vbar = 0.f, gymax = 0.f, fscale = 0.f;
     float hjb_sum = 0.f, term_sum = 0.f, sat_count = 0.f;
+    int dcount = 0;                          // entries of this epilogue warp's deferred list
     float inv_norm0 = 0.f, inv_norm1 = 0.f;
     // Gradient pass, fp16 range management.  The reverse pass of one state is linear in its adjoint seeds
     // (g0bar, Vbar), whose size varies by many decades over a batch (1 / (l + eps), 1 / (cost + eps), 1 / batch).
@@ -779,14 +780,26 @@ __global__ void __launch_bounds__(kThreads, 1) vhjb_tc_kernel(const __grid_const
             ms = fmaxf(ms, fabsf(gb[i]));
           }
           const int eb = (int)((__float_as_uint(ms) >> 23) & 0xffu);       // ms = f 2^(eb - 126), f in [1/2, 1)
+          // Seeds more than 2^kSeedCap above the batch-typical weight (states within ~0.1 of the goal: 1 / (l + eps) is
+          // large there, and dV/dx is the small remainder of a ~100-fold cancellation that the MMA's truncating
+          // accumulation resolves to ~2.5e-4 only) leave the tensor path: the state's adjoint seeds are zeroed here and
+          // its index goes to this warp's deferred list — the fp32 CUDA-core pass behind this kernel computes exactly
+          // those states (VhjbArgs::defer_*).  A full list (kDeferCap entries) keeps the state here, clipped and counted.
+          const bool in_range = eb > 8 && eb < 226;
+          const int ks = eb - 126, ts = ks - expE;
+          bool defer = in_range && sact && valid && ts > kSeedCap;
+          const unsigned dm = __ballot_sync(0xffffffffu, defer);
+          const int pos = dcount + __popc(dm & ((1u << lane) - 1u));
+          dcount += __popc(dm);
+          if (defer) {
+            if (pos < kDeferCap) a.defer_index[(int64_t)(blockIdx.x * 4 + q) * kDeferCap + pos] = (int)idx;
+            else { defer = false; sat_count += 1.f; }
+          }
           float lam = 0.f, fs = 0.f;
-          if (eb > 8 && eb < 226) {
-            const int ks = eb - 126, ts = ks - expE;
+          if (in_range) {
             const int as = max(-24, min(kSeedCap, ts));
-            const int fe = min(kFwdCap, ts - as);                            // >= 0; 0 for all but near-goal states
-            if (sact && ts - as > kFwdCap) sat_count += 1.f;                 // seed beyond 2^(12+E): under-weighted
-            lam = __uint_as_float((uint32_t)(as - ks + 127) << 23);          // 2^(a_s - k_s), exponent in [19, 252]
-            fs = __uint_as_float((uint32_t)(fe + 127) << 23);                // 2^fe, fe in [0, 6]
+            lam = defer ? 0.f : __uint_as_float((uint32_t)(as - ks + 127) << 23);   // 2^(a_s - k_s), exponent in [19, 252]
+            fs = 1.f;
           }
 #pragma unroll
           for (int i = 0; i < N; ++i) gb[i] *= lam;
@@ -795,27 +808,6 @@ __global__ void __launch_bounds__(kThreads, 1) vhjb_tc_kernel(const __grid_const
             store8<FMT>(smem, kG0, kHPiece, kRbH, sj, 8, gb + 8);
             sVb[sj] = Vbar * lam;
             sF[sj] = fs;
-          }
-          if (sact && fs != 1.f && fs != 0.f) {   // rare: rescale this state's column of g1 (F1), g2 (F0) and row of gy (Y0)
-            const __half m = __float2half_rn(fs);
-            for (int r = 0; r < 128; ++r) {
-              const uint32_t off = (uint32_t)(r >> 3) * kRbF + ((uint32_t)(sj >> 3) << 7) + ((uint32_t)(r & 7) << 4) + ((uint32_t)(sj & 7) << 1);
-#pragma unroll
-              for (int pc = 0; pc < 2; ++pc) {
-                __half* e1 = reinterpret_cast<__half*>(smem + kF1 + off + pc * kFPiece);
-                __half* e0 = reinterpret_cast<__half*>(smem + kF0 + off + pc * kFPiece);
-                *e1 = __hmul(*e1, m);
-                *e0 = __hmul(*e0, m);
-              }
-            }
-            for (int c = 0; c < VH3; ++c) {
-              const uint32_t off = kY0 + (uint32_t)(sj >> 3) * kRbY + ((uint32_t)(c >> 3) << 7) + ((uint32_t)(sj & 7) << 4) + ((uint32_t)(c & 7) << 1);
-#pragma unroll
-              for (int pc = 0; pc < 2; ++pc) {
-                __half* e = reinterpret_cast<__half*>(smem + off + pc * kYPiece);
-                *e = __hmul(*e, m);
-              }
-            }
           }
           fscale = fs;
         }
@@ -945,6 +937,7 @@ __global__ void __launch_bounds__(kThreads, 1) vhjb_tc_kernel(const __grid_const
         sV[4 * q] = hjb_sum;
         sV[4 * q + 1] = term_sum;
         sV[4 * q + 2] = sat_count;
+        if constexpr (GRAD) a.defer_count[blockIdx.x * 4 + q] = min(dcount, kDeferCap);
       }
       asm volatile("bar.sync 2, 128;" ::: "memory");
       if (tid == 0) {

@@ -279,10 +279,10 @@ def test_near_goal_states_keep_their_weight():
         assert np.abs(g[sl] - gi.reshape(-1)).max() <= TOL * np.abs(gi).max()
 
 
-def test_saturation_counter_reports_out_of_range_seeds():
+def test_out_of_range_seeds_take_the_fp32_pass():
     """A terminal sample whose stored cost is 0 has the weight 1/(0 + eps) = 1e10: beyond the fp16 range management of
-    the tensor-core kernel, which must COUNT it (hjb_vhjb_saturation) instead of overflowing; the CUDA-core kernel
-    (HJB_VHJB_IMPL=simt) handles the same batch exactly."""
+    the tensor-core kernel.  Its index goes to the deferred list and the fp32 CUDA-core pass behind the tensor kernel
+    computes it: the gradient of the batch is exact (round 1 clipped and counted such a state), nothing is saturated."""
     B = 2048
     torch, k, p, orc, params, xs, dones, costs = _setup("quad10d", B, seed=13, wseed=3)
     dones[:] = 0
@@ -292,12 +292,46 @@ def test_saturation_counter_reports_out_of_range_seeds():
     k.counts(dd, p.eps)
     g_tc = _with_impl(None, lambda: k.loss_grad(params, xd, dd, cd, 0.5)[0].clone())
     assert torch.isfinite(g_tc).all()
-    assert _with_impl(None, k.saturated) >= 1
+    assert _with_impl(None, k.saturated) == 0 and _with_impl(None, k.deferred) >= 1
     g_cc = _with_impl("simt", lambda: k.loss_grad(params, xd, dd, cd, 0.5)[0].clone())
     assert _with_impl("simt", k.saturated) == 0
     _, _, _, grads, _ = orc.loss_and_grad(xs, dones, costs, 0.5)
     go = np.concatenate([x.reshape(-1) for x in grads])
     assert np.abs(g_cc.cpu().numpy() - go).max() <= TOL * np.abs(go).max()
+    assert np.abs(g_tc.cpu().numpy() - go).max() <= TOL * np.abs(go).max()
+
+
+@pytest.mark.parametrize("name,B,frac", [("linear", 256, 0.3), ("quad10d", 20000, 0.9), ("linear_sin", 4099, 0.1)])
+def test_deferred_states_are_exact_deterministic_and_counted(name, B, frac):
+    """A third of the batch within 3e-5 of the goal (with random weights V ~ 30 |z|^2: the seeds pass 2^6 x typical below |z| ~ 1e-4): those
+    states leave the tensor path (their seeds are > 2^6 x typical) for the fp32 pass.  Loss sums and gradient against the
+    oracle at the usual tolerance; two runs give the same bits (the deferred lists are filled in tile order per epilogue
+    warp, and their partials are summed in a fixed order); the count says how many states went that way."""
+    torch, k, p, orc, params, xs, dones, costs = _setup(name, B, seed=21, wseed=4)
+    rng = np.random.default_rng(5)
+    near = rng.choice(B, size=B // 3, replace=False)
+    xs[near] = (p.xf + 3e-5 * rng.uniform(-1, 1, size=(len(near), p.sys.n))).astype(np.float32)
+    dones[near] = 0
+    xd, dd, cd = _dev(torch, xs, dones, costs)
+    k.counts(dd, p.eps)
+    g1, s1 = (t.clone() for t in k.loss_grad(params, xd, dd, cd, 0.3))
+    nd = k.deferred()
+    # (how many of the near states pass the 2^6 threshold depends on the problem: in the double integrator the two terms
+    # of p-bar largely cancel near the goal — an fp64 emulation of the seed exponents gives 66 % / 100 % / 19 % here)
+    assert frac * len(near) <= nd <= B and k.saturated() == 0
+    g2, s2 = (t.clone() for t in k.loss_grad(params, xd, dd, cd, 0.3))
+    assert torch.equal(g1, g2) and torch.equal(s1, s2)
+    total, hjb, term, grads, _ = orc.loss_and_grad(xs, dones, costs, 0.3)
+    go = np.concatenate([x.reshape(-1) for x in grads])
+    assert np.abs(g1.cpu().numpy() - go).max() <= TOL * np.abs(go).max()
+    assert abs(float(s1[0] / k.norm[0]) - hjb) <= TOL * abs(hjb)
+    # a batch without such states defers nothing
+    xs2, dones2, costs2 = sample_batch(name, B, seed=22)
+    far = np.linalg.norm(xs2 - p.xf, axis=1) > 0.5
+    x2, d2, c2 = _dev(torch, xs2[far], dones2[far] * 0, costs2[far])
+    k.counts(d2, p.eps)
+    k.loss_grad(params, x2, d2, c2, 0.0)
+    assert k.deferred() == 0
 
 
 # ---- SURVEY.md 8f row 1: learned-policy rollouts, all trajectories at once on device ----
@@ -601,11 +635,10 @@ def test_adjoint_chain_overflow_is_clipped_and_counted_not_nan():
 def test_wild_batch_that_overflowed_the_first_range_management():
     """tests/golden/vhjb_linear_overflow_batch.npz: weights and minibatch of update 13,606 of the reference's
     linear_vhjb_controller.gin run, where a state 1.6e-3 from the goal (seeds 2^8 x typical) met a backward gain of 267:
-    68,398 in fp16.  With the seed cap at 2^6 it is inside the range again: finite and not saturated.  Tolerance 3e-4
-    here instead of 1e-4: a third of this minibatch lies within 0.02 of the goal, where the trained net's dV/dx is what is
-    left after a ~100-fold cancellation in g1 W1^T, and tcgen05.mma accumulates with truncation (a -2.5e-6 relative bias
-    on the uncancelled terms): the seeds of such a state are good to ~2.5e-4 (tools/wild_batch_check.py: 5e-6 ... 3.6e-4
-    per state against the fp32 kernel, which itself is at 2.7e-7 on this batch) and they carry most of the gradient."""
+    68,398 in fp16.  A third of this minibatch lies within 0.02 of the goal, where the trained net's dV/dx is what is left
+    after a ~100-fold cancellation in g1 W1^T; tcgen05.mma accumulates with truncation, so on the tensor chain the seeds
+    of such a state are good to ~2.5e-4 only (round 1 asserted 3e-4 here).  Those states now take the fp32 pass (their seeds
+    are > 2^6 x the batch-typical weight): the reference's own minibatch meets the north star's 1e-4, nothing saturates."""
     import os
     torch = _cuda()
     d = np.load(os.path.join(os.path.dirname(__file__), "golden", "vhjb_linear_overflow_batch.npz"))
@@ -623,7 +656,8 @@ def test_wild_batch_that_overflowed_the_first_range_management():
     off = 0
     for gi in grads:
         sl = slice(off, off + gi.size); off += gi.size
-        assert np.abs(g[sl] - gi.reshape(-1)).max() <= 3e-4 * np.abs(gi).max()
+        assert np.abs(g[sl] - gi.reshape(-1)).max() <= TOL * np.abs(gi).max()
+    assert k.deferred() > 0
     k.impl = "simt"
     try:
         g32 = k.loss_grad(params, xd, dd, cd, reg)[0].cpu().numpy().astype(np.float64)
