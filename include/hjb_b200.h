@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define HJB_ABI_VERSION 1
+#define HJB_ABI_VERSION 2
 #define HJB_MAX_N 10 /* largest state dimension (NearHoverQuadcopter) */
 #define HJB_MAX_M 3  /* largest control dimension */
 
@@ -75,7 +75,13 @@ typedef enum hjb_control_kind {
   HJB_CTL_CARTPOLE_ES = 1,
   /* controller/acrobot_energy_shaping.py:74-121; K, P = LQR gain / cost-to-go about xf = [pi, 0, 0, 0],
    * aux = {Ks0, Ks1, Ks2, eps}                                                                          */
-  HJB_CTL_ACROBOT_ES = 2
+  HJB_CTL_ACROBOT_ES = 2,
+  /* Tracking of a TIME-VARYING reference: u_t = clip(u_ref[t] - K wrap(x - x_ref[t]), umin, umax) — the feedback law of
+   * controller/quadrotors_model_based_controller.py:36-38 about the state / feed-forward input that
+   * Quadrotors2DWaypointsPlanner.update(t) returns (:77-233; minimum snap + differential flatness).  The reference is a
+   * device table ref[ref_steps][n + m] (row t: x_ref, then u_ref, at time t * dt; rows past the end repeat the last:
+   * hover at the final way-point), the same for every environment — planned once per horizon, not once per step.      */
+  HJB_CTL_TRACK = 3
 } hjb_control_kind;
 
 typedef struct hjb_control {
@@ -85,6 +91,9 @@ typedef struct hjb_control {
   float P[16];                    /* ACROBOT_ES: 4 x 4 row-major */
   float xf[HJB_MAX_N], uf[HJB_MAX_M];
   float aux[8];
+  const float* ref;   /* TRACK: device pointer, [ref_steps][n + m] row-major; else unused (null)        */
+  int32_t ref_steps;  /* TRACK: rows of ref                                                              */
+  int32_t ref_offset; /* TRACK: step 0 of the call is row ref_offset (per-step calls at a given time)   */
 } hjb_control;
 
 /* ---- running cost l(x,u) = dx^T Q dx + (u-uf)^T R (u-uf), dx = wrap(x - xf) -----------------------

@@ -199,6 +199,9 @@ class OracleController:
                   [no clip]; controller/quadrotors_model_based_controller.py:36-38,73-75 [clip])
       cartpole_es controller/cartpole_energy_shaping.py:65-110
       acrobot_es  controller/acrobot_energy_shaping.py:74-121
+      track       u_t = clip(u_ref(t) - K wrap(x - x_ref(t))): the feedback law of
+                  controller/quadrotors_model_based_controller.py:36-38 about what Quadrotors2DWaypointsPlanner.update(t)
+                  returns (:77-233); ``planner`` is an OraclePlanner, ``dt`` the step of the time grid
     """
     kind: str
     K: Optional[np.ndarray] = None        # (m, n) LQR gain
@@ -210,9 +213,15 @@ class OracleController:
     eps_energy: float = 1.0
     eps_state: float = 1.0
     eps: float = 1000.0
+    planner: Optional["OraclePlanner"] = None
 
-    def control(self, sys: OracleSystem, x: np.ndarray) -> np.ndarray:
+    def control(self, sys: OracleSystem, x: np.ndarray, t: float = 0.0) -> np.ndarray:
         x = np.asarray(x, dtype=DT)
+        if self.kind == "track":
+            x_ref, u_ref = self.planner.update(t)
+            dx = sys.wrap(x - x_ref)
+            u = -dx @ np.asarray(self.K, dtype=DT).T + u_ref
+            return np.clip(u, sys.umin, sys.umax)
         if self.kind == "feedback":
             dx = sys.wrap(x - self.xf)
             u = -dx @ np.asarray(self.K, dtype=DT).T + self.uf
@@ -251,6 +260,71 @@ class OracleController:
             u = np.where((quad < self.eps)[:, None], u_lqr, u_sw[:, None])
             return np.clip(u, sys.umin, sys.umax)                         # :119
         raise ValueError(self.kind)
+
+
+class OraclePlanner:
+    """Minimum-snap way-point planner and its differential-flatness lift for the planar quadrotor, restated from
+    controller/quadrotors_model_based_controller.py:77-233 formula by formula (including the reference's hand-derived
+    theta_ddot, :201-202, whose last term reads 2 x_ddot y_dddot / b^3).  ``update(t)`` -> (x_ref [6], u_ref [2])."""
+
+    def __init__(self, waypoints, par, avg_speed=0.25):
+        self.points = np.asarray(waypoints, dtype=np.float64)
+        self.g, self.m, self.r, self.I = (float(par[k]) for k in ("g", "m", "r", "I"))
+        n = self.points.shape[0]
+        self.interval_t = np.sqrt(((self.points[1:] - self.points[:-1]) ** 2).sum(1)) / avg_speed      # :90-93
+        self.cumulated_t = np.zeros(n)
+        self.cumulated_t[1:] = np.cumsum(self.interval_t)                                                 # :94-95
+        S = n - 1
+        A = np.zeros((8 * S, 8 * S)); b = np.zeros((2, 8 * S))                                            # :107-109
+        term = self.term
+        A[0, :8] = term(0, 0); A[1, -8:] = term(self.interval_t[-1], 0)                                   # :113-117
+        b[:, 0] = self.points[0]; b[:, 1] = self.points[-1]
+        for k, nd in enumerate((1, 2, 3)):                                                                # :119-124
+            A[2 + 2 * k, :8] = term(0, nd); A[3 + 2 * k, -8:] = term(self.interval_t[-1], nd)
+        for i in range(S - 1):                                                                            # :127-132
+            A[8 + 2 * i, 8 * i:8 * (i + 1)] = term(self.interval_t[i], 0)
+            A[9 + 2 * i, 8 * (i + 1):8 * (i + 2)] = term(0, 0)
+            b[:, 8 + 2 * i] = self.points[i + 1]; b[:, 9 + 2 * i] = self.points[i + 1]
+        for i in range(S - 1):                                                                            # :135-153
+            for k in range(6):
+                row = 8 + (S - 1) * 2 + i * 6 + k
+                A[row, 8 * i:8 * (i + 1)] = term(self.interval_t[i], k + 1)
+                A[row, 8 * (i + 1):8 * (i + 2)] = -term(0, k + 1)
+        self.coeff = np.stack([np.linalg.solve(A, b[d]).reshape(S, 8) for d in range(2)])                # :155-156
+
+    @staticmethod
+    def term(t, n, order=7):                                                                              # :160-176
+        z = np.zeros(order + 1)
+        for i in range(order + 1):
+            if i - n >= 0:
+                z[i] = t ** (i - n) * np.prod(np.arange(i, i - n, -1))
+        return z
+
+    def flat(self, t, coeff):                                                                             # :178-214
+        o = coeff.shape[1] - 1
+        d = [[float(np.dot(coeff[c], self.term(t, n, o))) for c in range(2)] for n in range(5)]
+        (x, y), (xd, yd), (xdd, ydd), (x3, y3), (x4, y4) = d
+        b = ydd + self.g
+        theta = -np.arctan2(xdd, b)
+        q = 1 + (xdd / b) ** 2
+        w = x3 / b - xdd * y3 / b ** 2
+        theta_d = -1 / q * w
+        theta_dd = 2 * xdd / b / q ** 2 * w ** 2 - 1 / q * (x4 / b - x3 * y3 / b ** 2 - x3 * y3 / b ** 2 - xdd * y4 / b ** 2
+                                                             + 2 * xdd * y3 / b ** 3)
+        if not np.sin(theta) == 0:                                                                        # :207-212
+            u1 = (self.I / self.r * theta_dd - self.m / np.sin(theta) * xdd) / 2
+            u2 = (-self.I / self.r * theta_dd - self.m / np.sin(theta) * xdd) / 2
+        else:
+            u1 = (self.I / self.r * theta_dd + self.m / np.cos(theta) * b) / 2
+            u2 = (-self.I / self.r * theta_dd + self.m / np.cos(theta) * b) / 2
+        return np.array([x, y, theta, xd, yd, theta_d]), np.array([u1, u2])
+
+    def update(self, t):                                                                                  # :216-231
+        index = np.argwhere(t >= self.cumulated_t)[-1, 0]
+        if index == self.cumulated_t.shape[0] - 1:
+            coeff = np.zeros((2, 8)); coeff[:, 0] = self.points[-1]
+            return self.flat(0.0, coeff)
+        return self.flat(t - self.cumulated_t[index], self.coeff[:, index, :])
 
 
 def control_scale(sys: OracleSystem, ctl: OracleController, x: np.ndarray) -> np.ndarray:
@@ -323,7 +397,7 @@ def rollout(sys: OracleSystem, ctl: OracleController, x0: np.ndarray, steps: int
     xs, us = [x.copy()], []
     J = np.zeros(N, dtype=DT)
     for t in range(steps):
-        u = ctl.control(sys, x)
+        u = ctl.control(sys, x, t * sys.dt) if ctl.kind == "track" else ctl.control(sys, x)
         if cost is not None:
             J += cost.running(sys, x, u) * sys.dt
         if record_stride and t % record_stride == 0 and t // record_stride < steps // record_stride:
@@ -421,6 +495,11 @@ def std_system(kind: str) -> OracleSystem:
     raise ValueError(kind)
 
 
+# the way-points of the tracking tests / bench extras (a slalom; ~7.6 s at 0.5 m/s: 152 steps of dt = 0.05)
+TRACK_WAYPOINTS = np.array([[0.0, 0.0], [1.0, 0.5], [2.0, -0.3], [2.5, 1.0]])
+TRACK_SPEED = 0.5
+
+
 def std_controller(kind: str, sys: OracleSystem) -> OracleController:
     """The model-based controller each BASELINE config pairs with ``sys``."""
     if kind == "lqr":             # A6 on linear.gin, Q=I,R=I
@@ -443,6 +522,10 @@ def std_controller(kind: str, sys: OracleSystem) -> OracleController:
         K, P = lqr_gain(A, B, np.eye(6), np.eye(2))
         uf = sys.par["m"] * sys.par["g"] / 2 * np.ones(2)
         return OracleController("feedback", K=K, P=P, xf=np.zeros(6), uf=uf, clip=True)
+    if kind == "quad2d_track":    # hover gain about the planner's time-varying reference
+        A, B = quad2d_hover_AB(sys.par)
+        K, P = lqr_gain(A, B, np.eye(6), np.eye(2))
+        return OracleController("track", K=K, P=P, planner=OraclePlanner(TRACK_WAYPOINTS, sys.par, avg_speed=TRACK_SPEED))
     if kind == "quad10d_hover":   # A10
         A, B = quad10d_hover_AB(sys.par)
         K, P = lqr_gain(A, B, np.eye(10), np.eye(3))

@@ -16,7 +16,7 @@ HJB_MAX_M = 3
 # hjb_system_kind
 SYS_LINEAR, SYS_CARTPOLE, SYS_ACROBOT, SYS_QUAD2D, SYS_QUAD10D = range(5)
 # hjb_control_kind
-CTL_FEEDBACK, CTL_CARTPOLE_ES, CTL_ACROBOT_ES = range(3)
+CTL_FEEDBACK, CTL_CARTPOLE_ES, CTL_ACROBOT_ES, CTL_TRACK = range(4)
 # hjb_integrator
 INT_EULER, INT_RK4, INT_DISCRETE = range(3)
 INTEGRATORS = {"euler": INT_EULER, "rk4": INT_RK4, "discrete": INT_DISCRETE}
@@ -34,7 +34,8 @@ class HjbSystem(C.Structure):
 class HjbControl(C.Structure):
     _fields_ = [("kind", C.c_int32), ("clip", C.c_int32),
                 ("K", C.c_float * (HJB_MAX_M * HJB_MAX_N)), ("P", C.c_float * 16),
-                ("xf", C.c_float * HJB_MAX_N), ("uf", C.c_float * HJB_MAX_M), ("aux", C.c_float * 8)]
+                ("xf", C.c_float * HJB_MAX_N), ("uf", C.c_float * HJB_MAX_M), ("aux", C.c_float * 8),
+                ("ref", C.c_void_p), ("ref_steps", C.c_int32), ("ref_offset", C.c_int32)]
 
 
 class HjbCost(C.Structure):

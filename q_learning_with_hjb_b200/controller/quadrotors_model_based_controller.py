@@ -1,9 +1,9 @@
 """Hover LQR controllers for the planar quadrotor and the 10-D near-hover quadcopter:
 u = clip(-K wrap(x - xf) + uf, umin, umax)  (reference: controller/quadrotors_model_based_controller.py:7-75).
 
-``Quadrotors2DWaypointsPlanner`` (the reference's minimum-snap planner, :77-233) is a host-side linear solve that no
-rollout uses yet; it is provided with the reference's interface plus a batched
-``plan(ts)`` — the time-varying reference a tracking rollout would consume."""
+``Quadrotors2DWaypointsPlanner`` (the reference's minimum-snap planner, :77-233) is a host-side linear solve, provided with
+the reference's interface plus a batched ``plan(ts)``; ``Quadrotors2DTrackingController`` feeds that time-varying reference
+to the rollout kernel: u_t = clip(u_ref(t) - K wrap(x - x_ref(t)))."""
 import numpy as np
 
 from q_learning_with_hjb_b200 import _lib as L
@@ -176,3 +176,53 @@ class Quadrotors2DWaypointsPlanner:
                 vals = np.where(ts >= self.cumulated_t[-1], 0.0, vals)                               # at rest when hovering
             d.append((vals[0], vals[1]))
         return self._flat_to_state_input(self.dynamics, d)
+
+
+class Quadrotors2DTrackingController(DeviceController):
+    """Way-point tracking for the planar quadrotor: the hover LQR's feedback (reference :36-38) about the state and
+    feed-forward input the minimum-snap planner returns for the current time (:77-233),
+
+        x_ref, u_ref = planner.update(t);   u = clip(u_ref - K wrap(x - x_ref), umin, umax)
+
+    (the reference ships the planner and the hover controller; this is the loop that joins them).  ``K`` is the hover gain
+    for (Q, R).  The whole reference — ``planner.plan(i dt)``, i = 0 .. — is computed ONCE on the host in float64 and lives
+    on the device as a table [steps][n + m]; the rollout kernel reads row t in step t (the same row for every
+    environment), so N environments x T steps cost one planning pass, not N T planner calls.
+    """
+
+    def __init__(self, dynamics: Quadrotors2D, planner: "Quadrotors2DWaypointsPlanner", Q, R, settle_steps: int = 2) -> None:
+        super().__init__()
+        self.dynamics, self.planner = dynamics, planner
+        hover = Quadrotors2DHoveringController(dynamics, np.zeros(6), Q, R)
+        self.K, self.P, self.Q, self.R = hover.K, hover.P, hover.Q, hover.R
+        self.umin, self.umax = dynamics.get_control_limit()
+        dt = float(dynamics.dt)
+        # rows 0 .. : t = i dt up to the end of the last segment, then `settle_steps` rows of hovering at the last
+        # way-point (the kernel repeats the last row for later steps)
+        self.steps = int(np.ceil(planner.cumulated_t[-1] / dt)) + 1 + int(settle_steps)
+        self.ts = dt * np.arange(self.steps)
+        self.x_ref, self.u_ref = planner.plan(self.ts)
+        self.xf, self.uf = self.x_ref[-1], self.u_ref[-1]
+        self._table = None
+
+    def reference_table(self):
+        """float32 CUDA tensor [steps, 8]: x_ref (6), u_ref (2) per step."""
+        if self._table is None:
+            torch = L.require_cuda()
+            self._table = torch.as_tensor(np.concatenate([self.x_ref, self.u_ref], axis=1).astype(np.float32)).cuda().contiguous()
+        return self._table
+
+    def control_spec(self, offset: int = 0):
+        c = L.HjbControl()
+        c.kind, c.clip = L.CTL_TRACK, 1
+        L.fill(c.K, self.K)
+        L.fill(c.xf, self.xf)
+        L.fill(c.uf, self.uf)
+        tab = self.reference_table()
+        c.ref, c.ref_steps, c.ref_offset = tab.data_ptr(), int(tab.shape[0]), int(offset)
+        return c
+
+    def get_control_efforts(self, x, t: float = 0.0):
+        """u for state(s) ``x`` at time ``t`` (rounded to the step grid of the dynamics, like the per-step loop)."""
+        step = int(round(float(t) / float(self.dynamics.dt)))
+        return self._efforts(self.dynamics.system_spec(), self.control_spec(offset=max(step, 0)), x)

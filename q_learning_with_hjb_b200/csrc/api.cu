@@ -121,6 +121,9 @@ static void make_dev_ctl(const hjb_system* s, const hjb_control* c, DevSys& ds, 
   std::memcpy(d.xf, c->xf, sizeof(d.xf));
   std::memcpy(d.uf, c->uf, sizeof(d.uf));
   std::memcpy(d.aux, c->aux, sizeof(d.aux));
+  d.ref = c->kind == HJB_CTL_TRACK ? c->ref : nullptr;
+  d.ref_steps = c->ref_steps;
+  d.ref_offset = c->ref_offset;
   if (c->kind == HJB_CTL_CARTPOLE_ES) {
     // aux in = {Ke0, Ke1, Ke2, eps_energy, eps_state}; E(xf) = 0.5 dth_f^2 - cos(th_f)
     d.aux[4] = c->aux[4] * c->aux[4];
@@ -213,6 +216,7 @@ int hjb_rollout(const hjb_system* sys, const hjb_control* ctl, const hjb_cost* c
                 int32_t* steps, void* stream) {
   if (!sys || !ctl || !opts || N < 0 || T < 0) return HJB_ERR_BAD_ARG;
   if (!dims_ok(sys)) return HJB_ERR_UNSUPPORTED;
+  if (ctl->kind == HJB_CTL_TRACK && (!ctl->ref || ctl->ref_steps <= 0 || ctl->ref_offset < 0)) return HJB_ERR_BAD_ARG;
   if (N == 0) return HJB_OK;
   if (!x0) return HJB_ERR_BAD_ARG;
   if (cost && !cost_spec) return HJB_ERR_BAD_ARG;
@@ -262,6 +266,7 @@ int hjb_rollout(const hjb_system* sys, const hjb_control* ctl, const hjb_cost* c
       break;
     case HJB_SYS_QUAD2D:
       if (ctl->kind == HJB_CTL_FEEDBACK) e = rollout_quad2d_fb(a, v, fast, st);
+      else if (ctl->kind == HJB_CTL_TRACK) e = rollout_quad2d_track(a, v, fast, st);
       break;
     case HJB_SYS_QUAD10D:
       if (ctl->kind == HJB_CTL_FEEDBACK) e = rollout_quad10d_fb(a, v, fast, st);
@@ -304,6 +309,7 @@ int hjb_control_efforts(const hjb_system* sys, const hjb_control* ctl, int32_t f
   if (!dims_ok(sys)) return HJB_ERR_UNSUPPORTED;
   if (B == 0) return HJB_OK;
   if (!x || !u) return HJB_ERR_BAD_ARG;
+  if (ctl->kind == HJB_CTL_TRACK && (!ctl->ref || ctl->ref_steps <= 0 || ctl->ref_offset < 0)) return HJB_ERR_BAD_ARG;
   CtlArgs a;
   make_dev_sys(sys, a.sys);
   make_dev_ctl(sys, ctl, a.sys, a.ctl);

@@ -44,6 +44,9 @@ struct DevCtl {
   // CARTPOLE_ES aux = {Ke0, Ke1, Ke2, eps_energy, eps_state^2, E(xf)}
   // ACROBOT_ES  aux = {Ks0, Ks1, Ks2, eps, E(xf)}
   float aux[8];
+  // TRACK: the time-varying reference, ref[t] = {x_ref (n), u_ref (m)} for step t (rows past the end repeat the last)
+  const float* ref;
+  int ref_steps, ref_offset;
 };
 
 struct DevCost {

@@ -295,7 +295,7 @@ __global__ void __launch_bounds__(256) rollout_kernel(const __grid_constant__ Ro
     typename S::Trig tr;
     S::template trig<false>(a.sys, z, tr, tc);
     float u[M];
-    C::template control<S>(a.sys, a.ctl, z, tr, u);
+    C::template control<S>(a.sys, a.ctl, z, tr, u, t);
     if constexpr (REC) {
       if (phase == 0 && a.us && rec <= a.n_rec) {
         if (kStageU && staged) staged_store<M>(stage_u + (wib * 2 + (int)(rec & 1)) * 32 * M, lane, a.us + ((rec - 1) * a.N + env0) * M, u);
@@ -428,6 +428,7 @@ HJB_DECLARE_PROBLEM(cartpole_es);
 HJB_DECLARE_PROBLEM(acrobot_fb);
 HJB_DECLARE_PROBLEM(acrobot_es);
 HJB_DECLARE_PROBLEM(quad2d_fb);
+HJB_DECLARE_PROBLEM(quad2d_track);
 HJB_DECLARE_PROBLEM(quad10d_fb);
 
 #define HJB_DEFINE_PROBLEM(name, SYS_T, CTL, ALLOW_DISCRETE)                                              \

@@ -126,6 +126,7 @@ cudaError_t step_control(int sys_kind, int ctl_kind, const CtlArgs& a, bool fast
     return launch_ctl_fast<CartpoleSys, CartpoleESCtl>(a, fast, st);
   if (ctl_kind == HJB_CTL_ACROBOT_ES && sys_kind == HJB_SYS_ACROBOT)
     return launch_ctl_fast<AcrobotSys, AcrobotESCtl>(a, fast, st);
+  if (ctl_kind == HJB_CTL_TRACK && sys_kind == HJB_SYS_QUAD2D) return launch_ctl_fast<Quad2DSys, TrackCtl>(a, fast, st);
   return cudaErrorNotSupported;
 }
 

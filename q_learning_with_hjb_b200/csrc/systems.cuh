@@ -313,7 +313,7 @@ struct FeedbackCtl {
   static constexpr bool kClips = CLIP;  // output already inside [umin, umax]: simulate's clip is then a no-op
   template <class S>
   static __device__ __forceinline__ void control(const DevSys& ps, const DevCtl& pc, const float* z,
-                                                 const typename S::Trig&, float* u) {
+                                                 const typename S::Trig&, float* u, int = 0) {
 #pragma unroll
     for (int k = 0; k < S::M; ++k) {
       float acc = pc.u0[k];
@@ -325,6 +325,36 @@ struct FeedbackCtl {
   }
 };
 
+// Tracking of a time-varying reference (HJB_CTL_TRACK): u_t = clip(u_ref[t] - K wrap(z - x_ref[t])) with (x_ref, u_ref)(t)
+// what Quadrotors2DWaypointsPlanner.update(t dt) returns (controller/quadrotors_model_based_controller.py:77-233) and K
+// the hover gain of :36-38.  aoff = 0: z is the raw (wrapped) state.  The reference row is the same for every thread of
+// the launch: two uniform 16-byte loads per step, served by L1.
+struct TrackCtl {
+  static constexpr int KIND = HJB_CTL_TRACK;
+  static constexpr bool kClips = true;
+  template <class S>
+  static __device__ __forceinline__ void control(const DevSys& ps, const DevCtl& pc, const float* z,
+                                                 const typename S::Trig&, float* u, int t = 0) {
+    constexpr int W = S::N + S::M;
+    const int row = min(t + pc.ref_offset, pc.ref_steps - 1);
+    float r[W];
+    load_row<W>(pc.ref, row, r);
+    float d[S::N];
+#pragma unroll
+    for (int i = 0; i < S::N; ++i) d[i] = z[i] - r[i];
+#pragma unroll
+    for (int k = 0; k < S::NANG; ++k) d[S::ang(k)] = wrap_pi_<S::kFast>(d[S::ang(k)]);
+#pragma unroll
+    for (int k = 0; k < S::M; ++k) {
+      float acc = r[S::N + k];
+#pragma unroll
+      for (int i = 0; i < S::N; ++i) acc = fmaf(-pc.K[k * S::N + i], d[i], acc);
+      u[k] = acc;
+    }
+    clip_u<S>(ps, u);
+  }
+};
+
 // controller/cartpole_energy_shaping.py:65-110 (aoff = 0: z is the raw state).  Both branches are evaluated
 // and selected (no divergence).  aux = {Ke0, Ke1, Ke2, eps_energy, eps_state^2, E(xf)}; ps.c[5] = 1/l, ps.c[6] = g/l
 struct CartpoleESCtl {
@@ -332,7 +362,7 @@ struct CartpoleESCtl {
   static constexpr bool kClips = true;
   template <class S>
   static __device__ __forceinline__ void control(const DevSys& ps, const DevCtl& pc, const float* x,
-                                                 const typename S::Trig& t, float* u) {
+                                                 const typename S::Trig& t, float* u, int = 0) {
     static_assert(S::KIND == HJB_SYS_CARTPOLE, "cartpole energy shaping needs the cartpole");
     float dx[4];
 #pragma unroll
@@ -359,7 +389,7 @@ struct AcrobotESCtl {
   static constexpr bool kClips = true;
   template <class S>
   static __device__ __forceinline__ void control(const DevSys& ps, const DevCtl& pc, const float* x,
-                                                 const typename S::Trig& t, float* u) {
+                                                 const typename S::Trig& t, float* u, int = 0) {
     static_assert(S::KIND == HJB_SYS_ACROBOT, "acrobot energy shaping needs the acrobot");
     float dx[4];
     // (the internal state is wrapped: z in [-pi, pi); a goal angle of 0 — q2 in the reference, :131 — needs no second wrap)

@@ -161,6 +161,10 @@ __global__ void __launch_bounds__(256) vhjb_reduce_adam_kernel(const float* __re
   if (j < 3) {
     float t = 0.f;
     for (int c = 0; c < ncta; ++c) t += partial[(int64_t)c * pstride + P + j];
+    if (dtail != nullptr && j < 2) {   // loss terms of the deferred states
+      const int nd = (int)dtail[3];
+      for (int c = 0; c < nd; ++c) t += partial[(int64_t)(kMaxCtas + c) * pstride + P + j];
+    }
     if (j < 2) sums[j] = t;
     else { sat[0] = t; sat[1] += t; }   // [0]: this launch, [1]: running total (hjb_vhjb_saturation_total)
   }
@@ -169,6 +173,13 @@ __global__ void __launch_bounds__(256) vhjb_reduce_adam_kernel(const float* __re
     // reads them once per epoch instead of doing tensor arithmetic on two scalars after every update
     float s0 = 0.f, s1 = 0.f;
     for (int c = 0; c < ncta; ++c) { s0 += partial[(int64_t)c * pstride + P]; s1 += partial[(int64_t)c * pstride + P + 1]; }
+    if (dtail != nullptr) {
+      const int nd = (int)dtail[3];
+      for (int c = 0; c < nd; ++c) {
+        s0 += partial[(int64_t)(kMaxCtas + c) * pstride + P];
+        s1 += partial[(int64_t)(kMaxCtas + c) * pstride + P + 1];
+      }
+    }
     const float hjb = s0 / norm[0], term = s1 / norm[1];
     loss_acc[0] += hjb + reg * term;
     loss_acc[1] += hjb;
@@ -353,7 +364,7 @@ static int run_vhjb(const hjb_system* sys, const hjb_vnet* net, const hjb_task* 
     if (e != cudaSuccess) return (int)e;
   }
   if (sums) {
-    vhjb_reduce_kernel<<<1, 256, 0, st>>>(a.partial, a.pstride, l.grid, P, 2, sums, (int)accumulate, nullptr);
+    vhjb_reduce_kernel<<<1, 256, 0, st>>>(a.partial, a.pstride, l.grid, P, 2, sums, (int)accumulate, dtail);
     e = cudaGetLastError();
     if (e != cudaSuccess) return (int)e;
   }

@@ -498,7 +498,7 @@ __global__ void __launch_bounds__(VTHREADS, 1) vhjb_kernel(const __grid_constant
   // ---- per-CTA partials ----
   float* part = a.partial + (int64_t)(blockIdx.x + a.part_slot0) * a.pstride;
   if constexpr (GRAD) {
-    if (a.defer_gather) { hjb_sum = 0.f; term_sum = 0.f; }   // the tensor kernel's epilogue already counted these states
+    // (deferred-state mode: hjb_sum / term_sum are the loss terms of the deferred states — the tensor kernel left them out)
 #pragma unroll
     for (int q = 0; q < NA1; ++q) {
       const int i = ih1 + 2 * q;

@@ -67,6 +67,9 @@ def make_controller(kind, dyn):
         return QC.Quadrotors2DHoveringController(dyn, np.zeros(6), np.eye(6), np.eye(2))
     if kind == "quad10d_hover":
         return QC.NearHoverQuadcopterHoveringController(dyn, np.zeros(10), np.eye(10), np.eye(3))
+    if kind == "quad2d_track":
+        planner = QC.Quadrotors2DWaypointsPlanner(O.TRACK_WAYPOINTS, dyn, avg_speed=O.TRACK_SPEED)
+        return QC.Quadrotors2DTrackingController(dyn, planner, np.eye(6), np.eye(2))
     raise ValueError(kind)
 
 

@@ -21,14 +21,15 @@ def test_library_exports_every_declared_symbol():
     handle = ctypes.CDLL(L.lib_path())
     for name in declared:
         assert hasattr(handle, name), f"{name} not exported by libhjb_b200.so"
-    assert L.lib().hjb_abi_version() == 1
+    assert L.lib().hjb_abi_version() == 2
     assert L.lib().hjb_status_string(-2).startswith(b"hjb: unsupported")
 
 
 def test_struct_sizes_match_header_layout():
     from q_learning_with_hjb_b200 import _lib as L
     assert ctypes.sizeof(L.HjbSystem) == 4 * (4 + 3 + 3 + 8 + 16 + 8)
-    assert ctypes.sizeof(L.HjbControl) == 4 * (2 + 30 + 16 + 10 + 3 + 8)
+    # (69 four-byte fields, padding to the pointer's alignment, the reference-table pointer, two int32)
+    assert ctypes.sizeof(L.HjbControl) == 280 + 8 + 2 * 4 and L.HjbControl.ref.offset == 280
     assert ctypes.sizeof(L.HjbCost) == 4 * (100 + 9 + 10 + 3)
     assert ctypes.sizeof(L.HjbRolloutOpts) == 4 * (4 + 30)
 
@@ -150,7 +151,7 @@ def test_header_is_plain_c_and_a_c_caller_links():
         with open(src, "w") as fh:
             fh.write('#include "hjb_b200.h"\n#include <stdio.h>\nint main(void) {\n  const void* table[] = {\n')
             fh.write("".join(f"    (const void*)&{n},\n" for n in names))
-            fh.write('  };\n  printf("%d\\n", (int)(sizeof(table) / sizeof(table[0])));\n  return hjb_abi_version() == 1 ? 0 : 1;\n}\n')
+            fh.write('  };\n  printf("%d\\n", (int)(sizeof(table) / sizeof(table[0])));\n  return hjb_abi_version() == 2 ? 0 : 1;\n}\n')
         exe = os.path.join(tmp, "caller")
         libdir = os.path.dirname(L.lib_path())
         subprocess.run([gcc, "-std=c99", "-I", os.path.join(ROOT, "include"), src, "-o", exe, "-L", libdir, "-lhjb_b200",

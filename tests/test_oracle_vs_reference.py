@@ -296,3 +296,45 @@ def test_riccati_for_the_terminal_cost_matches_the_reference_solver_in_float32()
         ours64 = U.solve_continuous_are(A, B, np.eye(n), np.eye(m))
         np.testing.assert_allclose(ours64, rutils.solve_continuous_are(np.asarray(A, float), np.asarray(B, float),
                                                                        np.eye(n), np.eye(m)), rtol=1e-9, atol=1e-9)
+
+
+def test_tracking_loop_matches_the_reference_classes():
+    """the reference ships the minimum-snap planner (quadrotors_model_based_controller.py:77-233) and the
+    hover LQR (:7-38); the tracking loop joins them — x_ref, u_ref = planner.update(t); u = clip(u_ref - K wrap(x - x_ref));
+    x = dynamics.simulate(x, u).  Oracle planner vs the reference's planner (bit for bit: same formulas), product planner
+    vs both (1e-9), and the oracle's tracking rollout vs the loop run with the reference's own classes."""
+    from q_learning_with_hjb_b200.controller import quadrotors_model_based_controller as QC
+    from tests.helpers import make_dynamics
+    rdyn = R.make_quad2d()
+    rmod = R.ref_import("controller.quadrotors_model_based_controller")
+    rplan = rmod.Quadrotors2DWaypointsPlanner(O.TRACK_WAYPOINTS, rdyn, avg_speed=O.TRACK_SPEED)
+    rhover = rmod.Quadrotors2DHoveringController(rdyn, np.zeros(6), np.eye(6), np.eye(2))
+    osys = O.std_system("quad2d")
+    octl = O.std_controller("quad2d_track", osys)
+    pplan = QC.Quadrotors2DWaypointsPlanner(O.TRACK_WAYPOINTS, make_dynamics("quad2d"), avg_speed=O.TRACK_SPEED)
+    np.testing.assert_allclose(octl.K, rhover.K, rtol=1e-12)
+    ts = np.arange(0, rplan.cumulated_t[-1] + 0.3, 0.05)
+    px, pu = pplan.plan(ts)
+    for i, t in enumerate(ts):
+        xr, ur = rplan.update(t)
+        xo, uo = octl.planner.update(t)
+        np.testing.assert_array_equal(xo, xr)
+        np.testing.assert_array_equal(uo, ur)
+        np.testing.assert_allclose(px[i], xr, rtol=0, atol=1e-9)
+        np.testing.assert_allclose(pu[i], ur, rtol=0, atol=1e-8)
+    # the loop with the reference's own classes, three starts, against the oracle's batched rollout
+    rng = np.random.default_rng(0)
+    x0 = rng.uniform(-0.3, 0.3, size=(3, 6))
+    T = len(ts) - 1
+    xs, us, xf, _ = O.rollout(osys, octl, x0, T, "euler", record_stride=1)
+    umin, umax = rdyn.get_control_limit()
+    for e in range(3):
+        x = x0[e].copy()
+        for i in range(T):
+            xr, ur = rplan.update(ts[i])
+            u = np.clip(-rhover.K @ rdyn.states_wrap(x - xr) + ur, umin, umax)
+            np.testing.assert_allclose(us[i, e], u, rtol=0, atol=1e-9)
+            x = rdyn.simulate(x, u)
+            np.testing.assert_allclose(xs[i + 1, e], x, rtol=0, atol=1e-9)
+    # ... and it tracks: the end of the slalom is reached
+    assert np.abs(xf[:, :2] - O.TRACK_WAYPOINTS[-1]).max() < 0.05

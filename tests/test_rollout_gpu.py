@@ -547,3 +547,40 @@ def test_device_state_generator_equals_its_numpy_twin(skind):
     big = dyn.sample_initial_states(7, seed=2**40 + 5, first=2**33)                # 64-bit seed and counter
     np.testing.assert_array_equal(big.cpu().numpy(), X.sample_states(skind, dyn.x0_mean, dyn.x0_std, 2**40 + 5, 2**33, 7))
     assert dyn.sample_initial_states(0).shape == (0, dyn.state_dim)
+
+
+@FAST
+def test_waypoint_tracking_rollout(fast):
+    """the planar quadrotor tracking the minimum-snap reference of Quadrotors2DWaypointsPlanner
+    (controller/quadrotors_model_based_controller.py:77-233) with the hover gain (:36-38), the time-varying reference as a
+    device table.  Against the loop run with the reference's OWN classes (tests/golden/tracking_reference.npz), against the
+    oracle on 256 starts, per-step through get_control_efforts(x, t) — and the slalom is flown."""
+    torch = _cuda()
+    G = np.load(os.path.join(GOLDEN, "tracking_reference.npz"))
+    dyn = make_dynamics("quad2d")
+    dyn.fast_trig = fast
+    ctl = make_controller("quad2d_track", dyn)
+    T = G["traj_u"].shape[0]
+    np.testing.assert_allclose(ctl.K, G["K"], rtol=1e-10)
+    assert rel_err(ctl.x_ref[:T + 1], G["x_ref"][:ctl.steps][:T + 1], (2,)) < 1e-8     # the host plan vs planner.update(t)
+    res = dyn.rollout(ctl, G["traj_x"][0], T, record_stride=1)
+    assert rel_err(res.xs, G["traj_x"], (2,)) < 1e-5
+    assert rel_err(res.us, G["traj_u"]) < 1e-4                   # (u amplifies the state error by |K|)
+    osys, octl = oracle_pair("quad2d", "quad2d_track")
+    x0 = np.random.default_rng(2).uniform(-0.5, 0.5, size=(256, 6)).astype(np.float32)
+    res = dyn.rollout(ctl, x0, T, record_stride=1)
+    xs, us, xf, _ = O.rollout(osys, octl, x0.astype(np.float64), T, "euler", record_stride=1)
+    assert rel_err(res.xs, xs, (2,)) < 1e-5 and rel_err(res.x_final, xf, (2,)) < 1e-5
+    assert np.abs(res.x_final[:, :2] - O.TRACK_WAYPOINTS[-1]).max() < 0.05     # arrived at the last way-point
+    mid = T // 2
+    assert np.abs(res.xs[mid, :, :2] - G["x_ref"][mid, :2]).max() < 0.1       # ... along the planned path
+    # per-step interface at a given time
+    u = ctl.get_control_efforts(res.xs[mid], t=mid * float(dyn.dt))
+    assert rel_err(u, us[mid]) < 1e-4
+    # the reference table is the same for every environment: a rollout of shards equals the rollout of the batch
+    a = dyn.rollout(ctl, x0[:100], T, record_stride=0).x_final
+    np.testing.assert_array_equal(a, res.x_final[:100])
+    # RK4 variant against the oracle's RK4 (u held over the step)
+    res4 = dyn.rollout(ctl, x0, T, integrator="rk4", record_stride=0)
+    _, _, xf4, _ = O.rollout(osys, octl, x0.astype(np.float64), T, "rk4", record_stride=0)
+    assert rel_err(res4.x_final, xf4, (2,)) < 1e-5

@@ -301,10 +301,12 @@ def test_out_of_range_seeds_take_the_fp32_pass():
     assert np.abs(g_tc.cpu().numpy() - go).max() <= TOL * np.abs(go).max()
 
 
-@pytest.mark.parametrize("name,B,frac", [("linear", 256, 0.3), ("quad10d", 20000, 0.9), ("linear_sin", 4099, 0.1)])
-def test_deferred_states_are_exact_deterministic_and_counted(name, B, frac):
-    """A third of the batch within 3e-5 of the goal (with random weights V ~ 30 |z|^2: the seeds pass 2^6 x typical below |z| ~ 1e-4): those
-    states leave the tensor path (their seeds are > 2^6 x typical) for the fp32 pass.  Loss sums and gradient against the
+@pytest.mark.parametrize("name,B", [("linear", 256), ("quad10d", 20000), ("linear_sin", 4099)])
+def test_deferred_states_are_exact_deterministic_and_counted(name, B):
+    """A third of the batch within 3e-5 of the goal: those states leave the tensor path for the fp32 pass — their adjoint
+    seeds are > 2^6 x typical (an fp64 emulation of the seed exponents: 66 % / 100 % / 19 % of them in the three cases;
+    in the double integrator the two terms of p-bar largely cancel), and their inputs are below 2^-10, where the fp16
+    split of the activations is good to 3e-5 relative at best.  Loss sums and gradient against the
     oracle at the usual tolerance; two runs give the same bits (the deferred lists are filled in tile order per epilogue
     warp, and their partials are summed in a fixed order); the count says how many states went that way."""
     torch, k, p, orc, params, xs, dones, costs = _setup(name, B, seed=21, wseed=4)
@@ -316,9 +318,7 @@ def test_deferred_states_are_exact_deterministic_and_counted(name, B, frac):
     k.counts(dd, p.eps)
     g1, s1 = (t.clone() for t in k.loss_grad(params, xd, dd, cd, 0.3))
     nd = k.deferred()
-    # (how many of the near states pass the 2^6 threshold depends on the problem: in the double integrator the two terms
-    # of p-bar largely cancel near the goal — an fp64 emulation of the seed exponents gives 66 % / 100 % / 19 % here)
-    assert frac * len(near) <= nd <= B and k.saturated() == 0
+    assert len(near) <= nd <= B and k.saturated() == 0
     g2, s2 = (t.clone() for t in k.loss_grad(params, xd, dd, cd, 0.3))
     assert torch.equal(g1, g2) and torch.equal(s1, s2)
     total, hjb, term, grads, _ = orc.loss_and_grad(xs, dones, costs, 0.3)
