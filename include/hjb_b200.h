@@ -332,6 +332,35 @@ int hjb_vhjb_saturation_total(void* workspace, int32_t n, float* count, int32_t 
  * `count`: device or pinned host float. */
 int hjb_vhjb_deferred(const void* workspace, int32_t n, float* count, void* stream);
 
+/* ==== the notebooks' soft-PD baseline ===========================================
+ * SoftPDValueApproximator (examples/cartpole_balancing.ipynb cell 6, examples/drone_hovering.ipynb cell 6): an unconstrained
+ * value net  z = wrap(x - xf) -> Dense(128) -> s -> Dense(128) -> s -> Dense(64) -> s -> Dense(1), every Dense WITH bias,
+ * s = tanh (cart-pole notebook) or relu (drone notebook); no input normalisation.  params: one flat fp32 device buffer
+ * [W1 (n x 128) | b1 | W2 (128 x 128) | b2 | W3 (128 x 64) | b3 | w4 (64) | b4], Flax (in, out) kernels.               */
+typedef struct hjb_softpd {
+  int32_t n;
+  int32_t act;                 /* HJB_ACT_TANH or HJB_ACT_RELU */
+  int32_t normalized_residual; /* 0: |vdot + l| (cart-pole nb cell 11); 1: |vdot / (l + eps) + 1| (drone nb cell 11) */
+  const float* params;
+  float xf[HJB_MAX_N], uf[HJB_MAX_M];
+  float Q[HJB_MAX_N * HJB_MAX_N], R[HJB_MAX_M * HJB_MAX_M], Rinv[HJB_MAX_M * HJB_MAX_M];
+  float K[HJB_MAX_M * HJB_MAX_N]; /* LQR gain, loss form 2 */
+  float P[HJB_MAX_N * HJB_MAX_N]; /* Riccati solution, loss form 1 */
+  float eps;
+} hjb_softpd;
+int64_t hjb_softpd_param_count(int32_t n);     /* 128 n + 128 + 128*128 + 128 + 128*64 + 64 + 64 + 1 */
+int64_t hjb_softpd_workspace_bytes(int32_t n); /* caller-owned scratch for the two calls below */
+/* V [B], p = dV/dx [B, n], u = clip(-R^-1 g^T p / 2 + uf) [B, m] (each nullable) — get_soft_pd_control_with_additional_term */
+int hjb_softpd_policy(const hjb_system* sys, const hjb_softpd* net, const float* xs, int64_t B, float* V, float* p, float* u,
+                      void* workspace, void* stream);
+/* Loss and its parameter gradient (mean over the batch, as jax.value_and_grad of the notebooks' losses returns them):
+ *   loss_form 0  soft_pd_hjb_loss:         mean_i [ res_i + reg max(0, V(xf) - V(x_i)) ],  u from the net
+ *   loss_form 1  soft_pd_warmup_hjb_loss of the cart-pole notebook:  mean_i |V(x_i) - z_i^T P z_i|
+ *   loss_form 2  soft_pd_warmup_hjb_loss of the drone notebook: form 0 with u = clip(-K z + uf)
+ * grad [param_count]; sums [3] = {sum_i res_i (form 1: sum_i |V - z^T P z|), sum_i hinge_i, #{i: V(x_i) < V(xf)}}.      */
+int hjb_softpd_loss_grad(const hjb_system* sys, const hjb_softpd* net, const float* xs, int64_t B, int32_t loss_form, float reg,
+                         float* grad, float* sums, void* workspace, void* stream);
+
 /*
  * One step of the learned-policy rollout for N trajectories at once (VHJBController.rollout_trajectory,
  * controller/vhjb.py:171-193; the first widening row of SURVEY.md 8f).  `u` [N, m] is the value-net policy's control at

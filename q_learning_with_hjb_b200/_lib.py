@@ -67,6 +67,14 @@ class HjbTask(C.Structure):
                 ("eps", C.c_float), ("control_form", C.c_int32), ("residual_form", C.c_int32)]
 
 
+class HjbSoftPD(C.Structure):
+    _fields_ = [("n", C.c_int32), ("act", C.c_int32), ("normalized_residual", C.c_int32), ("params", C.c_void_p),
+                ("xf", C.c_float * HJB_MAX_N), ("uf", C.c_float * HJB_MAX_M),
+                ("Q", C.c_float * (HJB_MAX_N * HJB_MAX_N)), ("R", C.c_float * (HJB_MAX_M * HJB_MAX_M)),
+                ("Rinv", C.c_float * (HJB_MAX_M * HJB_MAX_M)), ("K", C.c_float * (HJB_MAX_M * HJB_MAX_N)),
+                ("P", C.c_float * (HJB_MAX_N * HJB_MAX_N)), ("eps", C.c_float)]
+
+
 # every symbol include/hjb_b200.h declares: name -> (restype, argtypes)
 _P = C.c_void_p
 SYMBOLS = {
@@ -112,6 +120,11 @@ SYMBOLS = {
     "hjb_replay_append": (C.c_int, [_P, _P, _P, _P, C.c_int64, C.c_int64, C.c_int32, C.c_int64, C.c_int64, C.c_int64, _P, _P,
                                     _P, _P]),
     "hjb_replay_gather": (C.c_int, [_P, _P, _P, _P, C.c_int64, C.c_int32, _P, _P, _P, _P]),
+    "hjb_softpd_param_count": (C.c_int64, [C.c_int32]),
+    "hjb_softpd_workspace_bytes": (C.c_int64, [C.c_int32]),
+    "hjb_softpd_policy": (C.c_int, [C.POINTER(HjbSystem), C.POINTER(HjbSoftPD), _P, C.c_int64, _P, _P, _P, _P, _P]),
+    "hjb_softpd_loss_grad": (C.c_int, [C.POINTER(HjbSystem), C.POINTER(HjbSoftPD), _P, C.c_int64, C.c_int32, C.c_float, _P, _P,
+                                       _P, _P]),
     "hjb_adam": (C.c_int, [_P, _P, _P, _P, C.c_int64, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int32, _P]),
 }
 
