@@ -427,8 +427,19 @@ def measure_rollout(wname, integ, envs, T, record_stride, steps, warmup, rank, w
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+    # warm-up: at least 3 launches AND ~50 ms of GPU work (the previous configuration's oracle check ran on the CPU for
+    # seconds: the clocks of an idle GPU ramp up again over the first milliseconds — visible on the 50 us launches of C1)
+    w0, w1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    w0.record()
     for _ in range(max(warmup, 3)):
         plan.launch(x0)
+    w1.record()
+    torch.cuda.synchronize()
+    per = max(w0.elapsed_time(w1) / max(warmup, 3), 1e-3)
+    for _ in range(int(min(2000, 50.0 / per))):
+        plan.launch(x0)
+    if envs <= (1 << 16):
+        steps = max(steps, 20)
     barrier()
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

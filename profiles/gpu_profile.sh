@@ -4,7 +4,7 @@
 # profiles/summarize_ncu.py turns them into the committed summaries.
 set -u
 export HJB_BENCH_NO_CLOCK_LOOP=1   # the 1 s clock-sampling loop would put hundreds of launches under ncu
-CMD="python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-vhjb ${BENCH_ARGS:-}"
+CMD="python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-vhjb --no-extra --no-parity --no-verify ${BENCH_ARGS:-}"
 TAG=${TAG:-rollout}
 KERNEL=${KERNEL:-rollout_kernel}
 $CMD > gpurun_out/${TAG}_plain.log 2>&1 &&

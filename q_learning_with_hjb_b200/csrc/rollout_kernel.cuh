@@ -207,8 +207,8 @@ __device__ __forceinline__ bool inside_box(const DevBox& b, const float* z) {
   return in;
 }
 
-// (sin, cos)(k 2^-5 + aoff) in double, rounded to fp32, for the `nt` angle arguments of a system (the third, the acrobot's
-// q1 + q2, has offset aoff0 + aoff1).  One copy per translation unit: fp64 sincos carries a large slow path.
+// (sin, cos)(k 2^-5 + aoff) in double, rounded to fp32, for the `nt` angle arguments of a system.  One copy per translation
+// unit: fp64 sincos carries a large slow path.
 static __device__ __noinline__ void build_trig_tables(float2* tab, int nt, float aoff0, float aoff1) {
   for (int i = threadIdx.x; i < nt * kTrigSize; i += blockDim.x) {
     const int k = i / kTrigSize, j = i - k * kTrigSize;
