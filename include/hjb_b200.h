@@ -311,6 +311,28 @@ int hjb_vhjb_train_step(const hjb_system* sys, const hjb_vnet* net, const hjb_ta
                         void* stream);
 
 /*
+ * The same step on SEVERAL GPUs (one process per GPU, this rank's shard of the batch): the tail — reduction of the per-CTA
+ * partials, exchange of [grad | loss sums | done-counts of the next batch] between the ranks, Adam — is ONE kernel that
+ * writes its elements into every rank's exchange buffer over NVLink peer memory, publishes a flag with release semantics,
+ * waits (bounded) for the peers' flags, sums the ranks' slots in rank order (identical bits on every rank) and updates the
+ * weights: no NCCL call, no separate reduction / Adam launches.  `norm` = the GLOBAL normalisers of this batch (device, 2
+ * floats: from counts_out of the previous call, or an all-reduce of hjb_vhjb_count); next_counts (nullable) = this rank's
+ * [sum(1 - done), sum(done)] of the NEXT batch, whose global normalisers (sums + eps; {B, 1} for MIN_TIME) are returned in
+ * counts_out — pass that buffer as `norm` of the next call (alternate two buffers).  peer_bufs / peer_flags:
+ * device arrays [world] of pointers to every rank's exchange buffer (hjb_vhjb_peer_exchange_floats floats) and flag array
+ * (hjb_vhjb_peer_exchange_flags uint32, zeroed once before the first step) in peer-accessible memory (e.g. torch symmetric
+ * memory); step = 1, 2, ... identical on all ranks.  A wait that gives up (~2 s) raises hjb_vhjb_stream_failures' word,
+ * turns the loss sums into NaN and skips the update.
+ */
+int64_t hjb_vhjb_peer_exchange_floats(int32_t n, int32_t world);
+int64_t hjb_vhjb_peer_exchange_flags(int32_t n, int32_t world);
+int hjb_vhjb_train_step_peer(const hjb_system* sys, const hjb_vnet* net, const hjb_task* task, const float* xs, const float* dones,
+                             const float* costs, int64_t B, float reg, float lr, float b1, float b2, float adam_eps, int32_t step,
+                             float* m, float* v, const float* norm, float* grad, float* sums, float* loss_acc,
+                             const float* next_counts, float* counts_out, void* const* peer_bufs, void* const* peer_flags,
+                             int32_t rank, int32_t world, void* workspace, void* stream);
+
+/*
  * Range management of the tensor-core gradient pass, and what is left of it for the caller to check.  The pass carries
  * per-state adjoints in fp16 with per-state power-of-two scaling (vhjb_tc.cuh).  A state whose adjoint seeds exceed 2^6
  * times the batch-typical weight (|x - xf|, |u - uf| of order 0.1 and below with the reference's eps = 1e-10; a terminal

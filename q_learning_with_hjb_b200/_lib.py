@@ -108,6 +108,11 @@ SYMBOLS = {
     "hjb_vhjb_stream_failures": (C.c_int, [_P, C.c_int32, _P, C.c_int32, _P]),
     "hjb_vhjb_adam_guarded": (C.c_int, [_P, _P, _P, _P, C.c_int32, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int32,
                                         _P, _P]),
+    "hjb_vhjb_peer_exchange_floats": (C.c_int64, [C.c_int32, C.c_int32]),
+    "hjb_vhjb_peer_exchange_flags": (C.c_int64, [C.c_int32, C.c_int32]),
+    "hjb_vhjb_train_step_peer": (C.c_int, [C.POINTER(HjbSystem), C.POINTER(HjbVnet), C.POINTER(HjbTask), _P, _P, _P, C.c_int64,
+                                           C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int32, _P, _P, _P, _P, _P,
+                                           _P, _P, _P, _P, _P, C.c_int32, C.c_int32, _P, _P]),
     "hjb_vhjb_saturation": (C.c_int, [_P, C.c_int32, _P, _P]),
     "hjb_vhjb_deferred": (C.c_int, [_P, C.c_int32, _P, _P]),
     "hjb_vhjb_saturation_total": (C.c_int, [_P, C.c_int32, _P, C.c_int32, _P]),

@@ -254,6 +254,45 @@ class VhjbKernels:
                     "hjb_vhjb_train_step")
             return self.sums, self.norm
         min_time = self.residual_form == "min_time"           # plain mean over the global batch; no boundary term
+        if not hasattr(self, "_peer"):
+            self._peer = parallel.peer_buffers(self.n, group)
+        if self._peer is not None:
+            # reduce + exchange over NVLink peer memory + Adam: ONE kernel behind the gradient kernel, no NCCL call.  The
+            # exchange also carries this rank's done-counts of the next batch and leaves the next step's global
+            # normalisers in a device buffer (two buffers alternate): a steady-state step launches nothing else.
+            px, t = self._peer, self.torch
+            if not hasattr(self, "_peer_local"):
+                self._peer_local = t.zeros(2, device="cuda", dtype=t.float32)
+                self._peer_norm = [t.ones(2, device="cuda", dtype=t.float32), t.ones(2, device="cuda", dtype=t.float32)]
+                self._peer_flip = 0
+            if self._pending is not None and self._pending[0] == self._dones_key(dones):
+                norm = self._pending[1]                          # delivered by the previous step's exchange
+            else:
+                self.counts(dones, 0.0)
+                parallel.global_counts(self.norm, 0.0 if min_time else self.eps, group)
+                if min_time:
+                    self.norm[1] = 1.0
+                norm = self.norm
+            self._pending = None
+            out = self._peer_norm[self._peer_flip]
+            if out is norm:
+                self._peer_flip ^= 1
+                out = self._peer_norm[self._peer_flip]
+            if next_dones is not None:
+                L.check(L.lib().hjb_vhjb_count(L.ptr(next_dones), next_dones.numel(), 0.0, L.ptr(self._peer_local),
+                                               L.ptr(self.workspace), L.stream_ptr()), "hjb_vhjb_count")
+            self._bind(params_flat)
+            opt.count += 1
+            L.check(L.lib().hjb_vhjb_train_step_peer(
+                self.sys_spec, self.net, self.task, L.ptr(xs), L.ptr(dones), L.ptr(costs), xs.shape[0], float(reg), float(lr),
+                0.9, 0.999, 1e-8, int(opt.count), L.ptr(opt.mu), L.ptr(opt.nu), L.ptr(norm), L.ptr(self.grad),
+                L.ptr(self.sums), L.ptr(loss_acc), L.ptr(self._peer_local) if next_dones is not None else None,
+                L.ptr(out), L.ptr(px.bufs), L.ptr(px.flags), px.rank, px.world, L.ptr(self.workspace),
+                L.stream_ptr()), "hjb_vhjb_train_step_peer")
+            if next_dones is not None:
+                self._pending = (self._dones_key(next_dones), out)
+                self._peer_flip ^= 1
+            return self.sums, norm
         if self._pending is not None and self._pending[0] == self._dones_key(dones):
             self.norm.copy_(self._pending[1])                  # global counts, delivered by the previous step's all-reduce
             self.norm += 0.0 if min_time else self.eps

@@ -187,6 +187,120 @@ __global__ void __launch_bounds__(256) vhjb_reduce_adam_kernel(const float* __re
   }
 }
 
+
+// ---- several GPUs: reduce -> exchange over NVLink peer memory -> Adam, in ONE kernel -------------------------------------
+// The multi-GPU train step used to end with three reduction launches, an NCCL all-reduce of [grad | loss sums] (~101 KB:
+// pure latency on NVLink / NVSwitch) and an Adam launch.  Here CTA b owns elements [256 b, 256 b + 256) of the exchanged
+// vector q = [grad (P) | hjb sum, term sum | this rank's done-counts of the NEXT batch (2)]:
+//   1. it sums ITS elements over the per-CTA partial slots (same fixed order as vhjb_reduce_kernel),
+//   2. stores them into slot `rank` of EVERY rank's exchange buffer (plain stores to peer memory: NVLink writes),
+//   3. publishes: __threadfence_system, then st.release.sys of the step number to flag (rank, b) on every rank,
+//   4. waits (bounded) until the flags (r, b) of all ranks r on ITS OWN GPU carry the step number,
+//   5. sums the W slots in rank order — the same order on every rank, so every rank holds the same bits — and
+//   6. applies the optax.adam update to its elements of the weights.
+// No CTA waits for another CTA of its own GPU (no co-residency requirement), only for the same CTA of the peers.  Buffers
+// are double-buffered by the parity of the step: a rank can only write step k + 2 after it saw every peer's step k + 1,
+// which a peer publishes after its own step-k kernel completed.  A wait that gives up raises the workspace's failure word,
+// poisons the loss sums with NaN and skips the update (never a hung device, never a silent garbage step).
+struct PeerExchange {
+  float* const* bufs;        // device array [world]: rank r's exchange buffer, [2][world][qpad] floats
+  uint32_t* const* flags;    // device array [world]: rank r's flags, [world][nblk]
+  int rank, world;
+  uint32_t seq;              // step number (> 0, increasing)
+  int qpad;
+  const float* next_counts;  // this rank's [sum(1 - done), sum(done)] of the next batch (or zeros)
+  float* counts_out;         // the next batch's GLOBAL normalisers: counts + eps ([1] = 1 for the min-time form)
+  float norm_eps;
+  int min_time;
+  unsigned poll_limit;
+};
+
+__global__ void __launch_bounds__(256) vhjb_reduce_exchange_adam_kernel(const float* __restrict__ partial, int64_t pstride, int ncta,
+                                                                        int P, const float* __restrict__ dtail, PeerExchange x,
+                                                                        float* __restrict__ grad, float* __restrict__ sums,
+                                                                        float* __restrict__ tail, float* __restrict__ w,
+                                                                        float* __restrict__ m, float* __restrict__ v, float lr,
+                                                                        float b1, float b2, float eps, float bc1, float bc2,
+                                                                        const float* __restrict__ norm, float reg,
+                                                                        float* __restrict__ loss_acc) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  const int Q = P + 4, nblk = gridDim.x;
+  const int parity = (int)(x.seq & 1u);
+  float mine = 0.f;
+  if (j < P + 2) {
+    for (int c = 0; c < ncta; ++c) mine += partial[(int64_t)c * pstride + j];
+    if (dtail != nullptr) {
+      const int nd = (int)dtail[3];
+      for (int c = 0; c < nd; ++c) mine += partial[(int64_t)(kMaxCtas + c) * pstride + j];
+    }
+  } else if (j < Q) {
+    mine = x.next_counts ? x.next_counts[j - (P + 2)] : 0.f;
+  }
+  if (j < Q) {
+    const size_t off = ((size_t)parity * x.world + x.rank) * x.qpad + j;
+    for (int r = 0; r < x.world; ++r) x.bufs[r][off] = mine;
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 32) {   // saturation count of this rank's launch (local, like vhjb_sat_kernel)
+    float t = 0.f;
+    for (int c = 0; c < ncta; ++c) t += partial[(int64_t)c * pstride + P + 2];
+    tail[0] = t;
+    tail[1] += t;
+  }
+  __threadfence_system();
+  __syncthreads();
+  __shared__ int failed;
+  if (threadIdx.x == 0) failed = 0;
+  if (threadIdx.x < x.world) {
+    uint32_t* f = x.flags[threadIdx.x] + (size_t)x.rank * nblk + blockIdx.x;
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(f), "r"(x.seq) : "memory");
+  }
+  __syncthreads();
+  if (threadIdx.x < x.world) {
+    const uint32_t* f = x.flags[x.rank] + (size_t)threadIdx.x * nblk + blockIdx.x;
+    uint32_t got = 0;
+    unsigned spins = 0;
+    for (; spins < x.poll_limit; ++spins) {
+      asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(got) : "l"(f) : "memory");
+      if (got == x.seq) break;
+      __nanosleep(200);
+    }
+    if (got != x.seq) atomicAdd(&failed, 1);
+  }
+  __syncthreads();
+  const bool bad = failed != 0;
+  if (bad && threadIdx.x == 0) atomicAdd(tail + 2, 1.0f);
+  float g = 0.f;
+  if (j < Q) {
+    const float* mybuf = x.bufs[x.rank] + (size_t)parity * x.world * x.qpad;
+    for (int r = 0; r < x.world; ++r) g += __ldcg(mybuf + (size_t)r * x.qpad + j);
+  }
+  const float nanv = __int_as_float(0x7fc00000);
+  if (j < P) {
+    grad[j] = g;
+    if (!bad) {
+      const float mi = fmaf(b1, m[j], (1.f - b1) * g);
+      const float vi = fmaf(b2, v[j], (1.f - b2) * g * g);
+      m[j] = mi;
+      v[j] = vi;
+      const float mhat = mi / bc1, vhat = vi / bc2;
+      w[j] = w[j] - lr * mhat / (sqrtf(vhat) + eps);
+    }
+  } else if (j < P + 2) {
+    sums[j - P] = bad ? nanv : g;
+  } else if (j < Q) {
+    if (x.counts_out) x.counts_out[j - (P + 2)] = (x.min_time && j == P + 3) ? 1.0f : g + x.norm_eps;
+  }
+  if (loss_acc != nullptr && j == P) {          // the thread that owns the hjb sum also reads the term sum's slots
+    const float* mybuf = x.bufs[x.rank] + (size_t)parity * x.world * x.qpad;
+    float s1 = 0.f;
+    for (int r = 0; r < x.world; ++r) s1 += __ldcg(mybuf + (size_t)r * x.qpad + P + 1);
+    const float hjb = g / norm[0], term = s1 / norm[1];
+    loss_acc[0] += hjb + reg * term;
+    loss_acc[1] += hjb;
+    loss_acc[2] += term;
+  }
+}
+
 // ---- optax.adam ----
 __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ w, float* __restrict__ m, float* __restrict__ v,
                                                    const float* __restrict__ g, int64_t len, float lr, float b1, float b2,
@@ -216,6 +330,7 @@ struct AdamTail {   // when set, run_vhjb ends with vhjb_reduce_adam_kernel inst
   float *w, *m, *v;
   float lr, b1, b2, eps, bc1, bc2;
   float* loss_acc;
+  const PeerExchange* peer = nullptr;   // several GPUs: reduce + exchange over peer memory + Adam in one kernel
 };
 
 static int run_vhjb(const hjb_system* sys, const hjb_vnet* net, const hjb_task* task, const float* xs, const float* dones,
@@ -351,6 +466,14 @@ static int run_vhjb(const hjb_system* sys, const hjb_vnet* net, const hjb_task* 
     std::fprintf(stderr, "\n");
   }
   const int P = vhjb_param_count(n);
+  if (tail && tail->peer) {
+    vhjb_reduce_exchange_adam_kernel<<<(P + 4 + 255) / 256, 256, 0, st>>>(a.partial, a.pstride, l.grid, P, dtail, *tail->peer, grad, sums,
+                                                                          a.tail, tail->w, tail->m, tail->v, tail->lr, tail->b1,
+                                                                          tail->b2, tail->eps, tail->bc1, tail->bc2, norm, reg,
+                                                                          tail->loss_acc);
+    e = cudaGetLastError();
+    return e == cudaSuccess ? HJB_OK : (int)e;
+  }
   if (tail) {
     vhjb_reduce_adam_kernel<<<(P + 255) / 256, 256, 0, st>>>(a.partial, a.pstride, l.grid, P, grad, sums, a.tail, tail->w, tail->m,
                                                              tail->v, tail->lr, tail->b1, tail->b2, tail->eps, tail->bc1, tail->bc2,
@@ -520,6 +643,53 @@ int hjb_vhjb_train_step(const hjb_system* sys, const hjb_vnet* net, const hjb_ta
   tail.loss_acc = loss_acc;
   return run_vhjb(sys, net, task, xs, dones, costs, B, norm, reg, nullptr, nullptr, nullptr, nullptr, grad, sums, workspace, true,
                   false, st, &tail);
+}
+
+int64_t hjb_vhjb_peer_exchange_floats(int32_t n, int32_t world) {
+  if (n <= 0 || n > HJB_MAX_N || world < 1) return -1;
+  const int64_t qpad = (vhjb_param_count(n) + 4 + 63) / 64 * 64;
+  return 2 * (int64_t)world * qpad;
+}
+int64_t hjb_vhjb_peer_exchange_flags(int32_t n, int32_t world) {
+  if (n <= 0 || n > HJB_MAX_N || world < 1) return -1;
+  return (int64_t)world * ((vhjb_param_count(n) + 4 + 255) / 256);
+}
+
+int hjb_vhjb_train_step_peer(const hjb_system* sys, const hjb_vnet* net, const hjb_task* task, const float* xs, const float* dones,
+                             const float* costs, int64_t B, float reg, float lr, float b1, float b2, float adam_eps, int32_t step,
+                             float* m, float* v, const float* norm, float* grad, float* sums, float* loss_acc,
+                             const float* next_counts, float* counts_out, void* const* peer_bufs, void* const* peer_flags,
+                             int32_t rank, int32_t world, void* workspace, void* stream) {
+  if (!sys || !net || !task || !net->params || !m || !v || !norm || !grad || !sums || !workspace || B < 0 || step < 1)
+    return HJB_ERR_BAD_ARG;
+  if (!peer_bufs || !peer_flags || world < 2 || world > 64 || rank < 0 || rank >= world) return HJB_ERR_BAD_ARG;
+  if (B > 0 && (!xs || !dones || !costs)) return HJB_ERR_BAD_ARG;
+  PeerExchange x;
+  x.bufs = reinterpret_cast<float* const*>(peer_bufs);
+  x.flags = reinterpret_cast<uint32_t* const*>(peer_flags);
+  x.rank = rank; x.world = world;
+  x.seq = (uint32_t)step;
+  x.qpad = (int)((vhjb_param_count(sys->n) + 4 + 63) / 64 * 64);
+  x.next_counts = next_counts;
+  x.counts_out = counts_out;
+  x.min_time = task->residual_form == HJB_RES_MIN_TIME;
+  x.norm_eps = x.min_time ? 0.f : task->eps;
+  x.poll_limit = 1u << 23;   // x 200 ns: ~2 s
+  if (const char* pl = std::getenv("HJB_PEER_POLL_LIMIT")) {
+    const long pv = std::atol(pl);
+    if (pv > 0) x.poll_limit = (unsigned)pv;
+  }
+  AdamTail tail;
+  tail.w = const_cast<float*>(net->params);
+  tail.m = m;
+  tail.v = v;
+  tail.lr = lr; tail.b1 = b1; tail.b2 = b2; tail.eps = adam_eps;
+  tail.bc1 = (float)(1.0 - std::pow((double)b1, (double)step));
+  tail.bc2 = (float)(1.0 - std::pow((double)b2, (double)step));
+  tail.loss_acc = loss_acc;
+  tail.peer = &x;
+  return run_vhjb(sys, net, task, xs, dones, costs, B, norm, reg, nullptr, nullptr, nullptr, nullptr, grad, sums, workspace, true,
+                  false, (cudaStream_t)stream, &tail);
 }
 
 int hjb_adam(float* params, float* m, float* v, const float* grad, int64_t len, float lr, float b1, float b2, float eps,

@@ -1,8 +1,10 @@
 """Multi-GPU plumbing: one process per GPU, ``torch.distributed`` (NCCL over NVLink on the GPU box, gloo in the CPU
 tests).  The hot path shards by initial state / sampled state; the ONLY data-path collectives are the two in
-``VhjbKernels.train_step``: an all-reduce of the two done-counts (so that every rank normalises by the GLOBAL batch,
-controller/vhjb.py:241, 253) and an all-reduce of the flat value-net gradient with the two loss sums appended
-(~101 KB).  Rollouts need no collective at all.
+``VhjbKernels.train_step``: the two done-counts (so that every rank normalises by the GLOBAL batch,
+controller/vhjb.py:241, 253) and the flat value-net gradient with the two loss sums appended (~101 KB).  Rollouts need no
+collective at all.  On NVLink-connected GPUs the exchange is done by the library's own kernel over peer memory
+(``PeerBuffers`` + ``hjb_vhjb_train_step_peer``: reduce, exchange and Adam in one launch); NCCL all-reduces are the fallback
+(``HJB_VHJB_EXCHANGE=nccl``, or when symmetric memory cannot be set up).
 """
 from __future__ import annotations
 
@@ -49,3 +51,47 @@ def sum_across_ranks(flat, group=None):
     if dist.is_available() and dist.is_initialized():
         dist.all_reduce(flat, group=group)
     return flat
+
+
+class PeerBuffers:
+    """Exchange buffers and flags of ``hjb_vhjb_train_step_peer`` in torch symmetric memory (peer-mapped over NVLink):
+    every rank can store into every rank's buffer.  ``bufs`` / ``flags`` are device arrays [world] of the peers' pointers."""
+
+    def __init__(self, n: int, group=None):
+        import torch
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm
+        from q_learning_with_hjb_b200 import _lib as L
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        nf = int(L.lib().hjb_vhjb_peer_exchange_floats(n, self.world))
+        ng = int(L.lib().hjb_vhjb_peer_exchange_flags(n, self.world))
+        self.mem = symm.empty(nf + ng, dtype=torch.float32, device=torch.device("cuda", torch.cuda.current_device()))
+        self.mem.zero_()
+        self.handle = symm.rendezvous(self.mem, group if group is not None else dist.group.WORLD)
+        ptrs = [int(p) for p in self.handle.buffer_ptrs]
+        self.bufs = torch.tensor(ptrs, dtype=torch.int64, device="cuda")
+        self.flags = torch.tensor([p + 4 * nf for p in ptrs], dtype=torch.int64, device="cuda")
+        torch.cuda.synchronize()
+        dist.barrier(group)          # every rank's flags are zero before anyone's first step
+
+
+def peer_buffers(n: int, group=None):
+    """``PeerBuffers`` for a value net of state dimension n, or None (NCCL fallback: HJB_VHJB_EXCHANGE=nccl, a non-NCCL
+    process group as in the CPU tests, or symmetric memory unavailable)."""
+    import os
+    import torch.distributed as dist
+    if os.environ.get("HJB_VHJB_EXCHANGE", "") == "nccl" or not is_distributed():
+        return None
+    import torch
+    if dist.get_backend(group) != "nccl":
+        return None
+    px = None
+    try:
+        px = PeerBuffers(n, group)
+    except Exception as exc:   # noqa: BLE001 — any set-up failure means: use NCCL
+        import warnings
+        warnings.warn(f"peer-memory exchange unavailable ({exc!r}); falling back to NCCL all-reduces")
+    # every rank must take the same path: peer exchange only if it was set up everywhere
+    ok = torch.tensor([1.0 if px is not None else 0.0], device="cuda")
+    dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+    return px if float(ok.item()) > 0 else None
