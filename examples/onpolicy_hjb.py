@@ -135,6 +135,44 @@ def train(p: Problem, k, epochs, seed=0, log=print, log_every=10):
     return params, history
 
 
+def soft_pd_policy(ctl):
+    """u(x) of a SoftPDController, batched on the device."""
+    return lambda x: ctl.get_control_efforts_with_additional_term(x)[0]
+
+
+def train_soft_pd(p: Problem, ctl, epochs, warmup_epochs=20, warmup_form="value_match", regularization=1.0, seed=0,
+                  log=print, log_every=10):
+    """The notebooks' soft-PD runs (examples/cartpole_balancing.ipynb cell 11, examples/drone_hovering.ipynb cell 11; cell 12
+    of both is the same with ``warmup_epochs=0``): the SAME on-policy loop as :func:`train` around the unconstrained value net
+    of ``SoftPDController`` — ``warmup_epochs`` epochs on the warm-up loss (``"value_match"``: |V - z^T P z|, cart-pole;
+    ``"hjb_lqr"``: the HJB residual under the LQR's control, drone), then the HJB residual + regularization * hinge.
+    -> [(mean loss, mean rollout cost, mean collected length)] per epoch."""
+    import torch
+    from q_learning_with_hjb_b200.controller.vhjb import DeviceReplayBuffer
+    torch.manual_seed(seed)
+    n = p.dyn.get_dimension()[0]
+    policy = soft_pd_policy(ctl)
+    data = DeviceReplayBuffer(n, p.batch + epochs * p.trajectories_per_epoch * p.rollout_steps)
+    data.extend(np.tile(np.asarray(p.xf, dtype=np.float32), (p.batch, 1)), np.ones(p.batch), np.zeros(p.batch))  # [xf] * 256
+    history = []
+    for epoch in range(epochs):
+        x0 = np.stack([p.dyn.get_initial_state() for _ in range(p.trajectories_per_epoch)])
+        states, costs, lengths = rollout(p, policy, x0)
+        if states.shape[0]:
+            data.extend(states, torch.ones(states.shape[0], device="cuda"), torch.zeros(states.shape[0], device="cuda"))
+        form = warmup_form if epoch < warmup_epochs else "hjb"
+        total, nb = torch.zeros((), device="cuda"), 0
+        for xs, _, _ in data.batches(p.batch):
+            loss, _, _ = ctl.params_update(xs, form, regularization)
+            total += loss
+            nb += 1
+        history.append((float(total) / nb, float(costs.mean()), float(lengths.float().mean())))
+        if log and (epoch + 1) % log_every == 0:
+            log(f"{'warmup ' if epoch < warmup_epochs else ''}epoch:{epoch + 1} loss:{history[-1][0]:.5f}, "
+                f"cumulated cost:{history[-1][1]:.3f}, avg trajectory length: {history[-1][2]:.2f}")
+    return history
+
+
 def lqr_policy(p: Problem, K, clip=False):
     """u = -K wrap(x - xf) + uf (optionally clipped; Dynamics.simulate clips anyway)."""
     import torch
