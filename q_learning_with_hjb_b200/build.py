@@ -44,7 +44,7 @@ def _digest(paths, extra=""):
     h = hashlib.sha256(extra.encode())
     for p in paths:
         with open(p, "rb") as fh:
-            h.update(p.encode())
+            h.update(os.path.basename(p).encode())     # NOT the path: the GPU box builds from another directory
             h.update(fh.read())
     return h.hexdigest()
 

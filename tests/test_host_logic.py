@@ -195,3 +195,20 @@ def test_counter_based_state_stream_twin():
     raw = np.where(whole[:, 1] < 0, whole[:, 1] + 2 * np.pi, whole[:, 1])          # un-wrap: 3.14 +- 0.05
     assert abs(raw.mean() - 3.14) < 2e-3 and raw.min() >= 3.09 - 1e-6 and raw.max() <= 3.19 + 1e-6
     assert abs(whole[:, 2].std() - 1 / np.sqrt(3)) < 0.02
+
+
+def test_kernel_source_hash_is_independent_of_the_checkout_directory(tmp_path):
+    """profiles/traffic.json stamps each ncu capture with the hash of the kernel sources; bench.py quotes the measured DRAM
+    traffic only when that hash equals the hash of the sources it runs on — on the GPU box the repository lives under another
+    path, so the hash must cover file names and contents only."""
+    import shutil
+    from q_learning_with_hjb_b200 import build
+    a, b = tmp_path / "a", tmp_path / "some" / "where" / "else"
+    a.mkdir()
+    b.mkdir(parents=True)
+    names = build.KERNEL_FAMILIES["rollout"]
+    for d in (a, b):
+        for f in names:
+            shutil.copy(os.path.join(build.CSRC, f), d / f)
+    assert build._digest([str(a / f) for f in names]) == build._digest([str(b / f) for f in names])
+    assert build._digest([str(a / f) for f in names])[:16] == build.source_hash("rollout")
