@@ -852,21 +852,29 @@ def measure_vhjb(w, steps, warmup, rank, world, local, want_cpu, extras=False, v
     e2e_rate = B * world * steps / (e2e_ms * 1e-3)
     kern_rate = B * steps / (grad_ms * 1e-3)          # per GPU, the fused loss+gradient kernel (+ its 3 tiny reduces)
     logical_tflops = kern_rate * VHJB_FLOPS_FULL(n) / 1e12
+    peer = world > 1 and getattr(k, "_peer", None) is not None
+    exchange = ("none (single GPU)" if world == 1 else
+                "peer memory over NVLink inside the reduce kernel (hjb_vhjb_train_step_peer): reduce + exchange + Adam in one "
+                "launch, no NCCL call in the step" if peer else
+                "NCCL: one all-reduce of gradient + loss sums + next normalisers per step")
     d = {
         "metric": "HJB-residual states/s (residual + loss-gradient + Adam train step)", "value": train_rate,
         "unit": "states/s", "n_gpus": world, "steps": steps, "warmup": max(warmup, 3), "ms_per_step": train_ms / steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": w["label"], "states_per_gpu": B, "value_net": [n, 128, 128, 64],
                    "activation": p.act, "parallelism": f"state-shard x{world}, grad all-reduce" if world > 1 else "single GPU",
+                   "exchange": exchange,
                    "l2": "states (>= 40 MB) streamed once per step; weights resident in shared memory", "seed": "1234 + rank",
                    "kernel": "tcgen05 fp16x3 (vhjb_tc.cuh)" if tensor_path else "CUDA-core fp32 (vhjb_simt.cuh)"},
         "residual_only_states_per_s": res_rate,
         "e2e": {"value": e2e_rate, "unit": "states/s", "h2d_bytes_per_step": h2d_bytes,
                 "d2h_bytes_per_step": 16, "ms_per_step": e2e_ms / steps},
-        # single process: count, fused pass, reduce-and-Adam (hjb_vhjb_train_step); multi-GPU: fused pass, reduce x3,
-        # count x2 of the next batch, Adam (the NCCL all-reduce — ONE per step — is not counted)
-        "gpu_launches": steps * (3 if world == 1 else 7),
-        "collectives_per_step": 0 if world == 1 else 1,
+        # kernels of this library per step (profiles/r02_vhjb_quad10d_tc.md lists them).  Single process: count x2, fused
+        # tensor pass, deferred fp32 pass, reduce-and-Adam (hjb_vhjb_train_step); multi-GPU over peer memory: count x2 of the
+        # next batch, the two passes, reduce-exchange-Adam; multi-GPU over NCCL: the two passes, reduce x3, count x2 of the
+        # next batch, Adam (the NCCL all-reduce — ONE per step — is not counted)
+        "gpu_launches": steps * (5 if world == 1 or peer else 8),
+        "collectives_per_step": 0 if world == 1 or peer else 1,
         "verify": ver, "extra": sub,
         "kernel_ms": grad_ms / steps,
         "clocks": clk,
