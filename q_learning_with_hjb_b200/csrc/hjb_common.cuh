@@ -119,28 +119,29 @@ __device__ __forceinline__ void sincos_poly(float x, float& s, float& c) {
   c = __int_as_float(__float_as_int(cv) ^ (((q + 1) & 2) << 30));
 }
 
-// Rollout kernels (whole horizon in one launch): sin / cos by table + short Taylor step.  Each CTA builds, once, a
-// shared-memory table of (sin, cos)(k 2^-5 + aoff) for |k 2^-5| <= 8 rad, evaluated in DOUBLE and rounded to fp32 (the
-// internal-coordinate offset aoff is baked in, so the per-step "z + aoff" add disappears).  Per evaluation:
-//   k = rint(32 x) (1.5 * 2^23 trick), r = x - k / 32 (exact, one FMA, |r| <= 1/64), one LDS.64,
-//   sin r = r - r^3 / 6 (next term 8e-12), cos r - 1 = -r^2 / 2 (next term 2.5e-9), and the rotation
-//   s = S + (C sin r + S (cos r - 1)),  c = C + (-S sin r + C (cos r - 1))            — 14 instructions against 21.
+// Rollout kernels (whole horizon in one launch): sin / cos by table + second-order Taylor step.  Each CTA builds, once, a
+// shared-memory table of (sin, cos)(k 2^-7 + aoff) for |k 2^-7| <= 3.5 rad (wrapped angles live in [-pi, pi]; 897 entries,
+// 7 KB), evaluated in DOUBLE and rounded to fp32 (the internal-coordinate offset aoff is baked in, so the per-step
+// "z + aoff" add disappears).  Per evaluation:
+//   k = rint(128 x) (1.5 * 2^23 trick), r = x - k / 128 (exact, one FMA, |r| <= 2^-8), one LDS.64, and
+//   s = S + r (C - S r / 2),  c = C - r (S + C r / 2)        (next term r^3 / 6 <= 1e-8)
+// — 8 FMA-pipe instructions + 3 for index and load (the 2^-5 table of the first version needed the third-order term:
+// 11 + 3; an in-line quadrant reduction + minimax polynomials 21).  The FMA pipe is what bounds the step loop
+// (tests/cuda/rollout_x2_probe.cu), so these three instructions are 5 % of a quad-2D Euler step.
 // The index is clamped (unsigned min): a NaN state reads a valid entry and still yields NaN through r.
-constexpr int kTrigLog2 = 5;
-constexpr int kTrigHalf = 8 << kTrigLog2;
+constexpr int kTrigLog2 = 7;
+constexpr float kTrigRange = 3.5f;
+constexpr int kTrigHalf = 7 << (kTrigLog2 - 1);      // 3.5 * 2^7
 constexpr int kTrigSize = 2 * kTrigHalf + 1;
-constexpr float kTrigRange = 8.0f;
 __device__ __forceinline__ void sincos_tab(const float2* __restrict__ tab, float x, float& s, float& c) {
   const float t = __fmaf_rn(x, (float)(1 << kTrigLog2), 12582912.f);
   const float k = t - 12582912.f;
   const float r = __fmaf_rn(k, -1.0f / (float)(1 << kTrigLog2), x);
   const unsigned idx = min((unsigned)(__float_as_int(t) - (0x4B400000 - kTrigHalf)), (unsigned)(kTrigSize - 1));
   const float2 e = tab[idx];
-  const float r2 = r * r;
-  const float a = -0.5f * r2;
-  const float sr = __fmaf_rn(r2 * r, -0.16666667f, r);
-  s = __fmaf_rn(e.x, a, __fmaf_rn(e.y, sr, e.x));
-  c = __fmaf_rn(e.y, a, __fmaf_rn(-e.x, sr, e.y));
+  const float hr = 0.5f * r;
+  s = __fmaf_rn(r, __fmaf_rn(-e.x, hr, e.y), e.x);
+  c = __fmaf_rn(-r, __fmaf_rn(e.y, hr, e.x), e.y);
 }
 
 template <bool FAST>

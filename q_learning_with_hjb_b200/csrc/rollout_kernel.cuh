@@ -207,7 +207,7 @@ __device__ __forceinline__ bool inside_box(const DevBox& b, const float* z) {
   return in;
 }
 
-// (sin, cos)(k 2^-5 + aoff) in double, rounded to fp32, for the `nt` angle arguments of a system.  One copy per translation
+// (sin, cos)(k 2^-7 + aoff) in double, rounded to fp32, for the `nt` angle arguments of a system.  One copy per translation
 // unit: fp64 sincos carries a large slow path.
 static __device__ __noinline__ void build_trig_tables(float2* tab, int nt, float aoff0, float aoff1) {
   for (int i = threadIdx.x; i < nt * kTrigSize; i += blockDim.x) {
@@ -290,6 +290,11 @@ __global__ void __launch_bounds__(256) rollout_kernel(const __grid_constant__ Ro
 
   auto run = [&](auto cwrap) {
   constexpr bool CWRAP = decltype(cwrap)::value;
+  // the plain step loop is issue-bound: four steps per trip cost 54.3 instead of 58 instructions per quad-2D Euler step
+  // (loop control, and the rounding of a / 2 pi shared between a step's wrap and the next step's table index); recorded
+  // and boxed rollouts are bound by their stores and stay rolled
+  constexpr int kUnroll = (REC || BOX) ? 1 : 4;
+#pragma unroll kUnroll
   for (int32_t t = 0; t < a.T; ++t) {
     if constexpr (BOX) alive = alive && inside_box<S>(a.box, z);
     typename S::Trig tr;

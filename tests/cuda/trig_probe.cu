@@ -4,6 +4,7 @@
 //   1  MUFU + first-order correction of the argument's rounding  (x / 2 pi is rounded to fp32 before the MUFU)
 //   2  quadrant reduction + minimax polynomials (no MUFU)
 //   3  libdevice sincosf
+//   4  shared-memory table (2^-7 spacing, built in double) + second-order Taylor step — what the rollout kernels use
 // Prints max |err| of sin and cos against fp64 and ns per call in a dependent loop.
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -o tests/cuda/build/trig_probe tests/cuda/trig_probe.cu
 #include <cmath>
@@ -27,9 +28,20 @@ __device__ __forceinline__ void sincos_mufu_corrected(float x, float& s, float& 
   c = __fmaf_rn(-d, s0, c0);
 }
 
+__shared__ float2 g_tab[kTrigSize];
+__device__ void build_tab() {
+  for (int i = threadIdx.x; i < kTrigSize; i += blockDim.x) {
+    double sv, cv;
+    sincos((double)(i - kTrigHalf) * (1.0 / (double)(1 << kTrigLog2)), &sv, &cv);
+    g_tab[i] = make_float2((float)sv, (float)cv);
+  }
+  __syncthreads();
+}
+
 template <int V>
 __device__ __forceinline__ void sc(float x, float& s, float& c) {
-  if constexpr (V == 0) { s = __sinf(x); c = __cosf(x); }
+  if constexpr (V == 4) sincos_tab(g_tab, x, s, c);
+  else if constexpr (V == 0) { s = __sinf(x); c = __cosf(x); }
   else if constexpr (V == 1) sincos_mufu_corrected(x, s, c);
   else if constexpr (V == 2) sincos_poly(x, s, c);
   else sincosf(x, &s, &c);
@@ -37,6 +49,7 @@ __device__ __forceinline__ void sc(float x, float& s, float& c) {
 
 template <int V>
 __global__ void err_kernel(float lo, float hi, long long npts, double* out) {
+  if (V == 4) build_tab();
   double es = 0, ec = 0;
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < npts; i += stride) {
@@ -58,6 +71,7 @@ __global__ void err_kernel(float lo, float hi, long long npts, double* out) {
 
 template <int V>
 __global__ void time_kernel(int reps, float* sink) {
+  if (V == 4) build_tab();
   float x = 0.001f * threadIdx.x, acc = 0.f;
   for (int r = 0; r < reps; ++r) {
     float s, c;
@@ -74,6 +88,7 @@ void run(const char* name) {
   cudaMalloc(&d, 16);
   const float ranges[3][2] = {{-3.14159274f, 3.14159274f}, {0.f, 6.2831855f}, {-0.01f, 0.01f}};
   for (auto& r : ranges) {
+    if (V == 4 && r[1] > kTrigRange) continue;      // the table covers the wrapped range only
     cudaMemset(d, 0, 16);
     err_kernel<V><<<148 * 8, 256>>>(r[0], r[1], 1LL << 28, d);
     double h[2];
@@ -101,5 +116,6 @@ int main() {
   run<1>("mufu+corr");
   run<2>("poly");
   run<3>("libdevice");
+  run<4>("table+taylor2");
   return cudaDeviceSynchronize() != cudaSuccess;
 }
