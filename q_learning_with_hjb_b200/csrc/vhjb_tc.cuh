@@ -112,6 +112,37 @@ __device__ __forceinline__ void gemm3(uint32_t tm, uint32_t sbd, uint32_t acc0) 
   gemm3_seq<A, B, IDESC, DCOL, KSTEPS>(tm, sbd, acc0, std::make_integer_sequence<int, 3 * KSTEPS>{});
 }
 
+// One of the three products of gemm3 over all K steps (PR = 0: (hi, hi), 1: (A lo, B hi), 2: (A hi, B lo)); acc0 = the
+// accumulate flag of its first MMA.  A pass that produces the B (or A) operand of a chain GEMM stores the hi pieces first
+// and hands them over before it computes the lo pieces: the two products that need hi alone (two thirds of the GEMM) run
+// under the rest of the pass.
+template <class A, class B, uint32_t IDESC, uint32_t DCOL, int PR, int K>
+__device__ __forceinline__ void mma_piece(uint32_t tm, uint32_t sbd, uint32_t acc) {
+  constexpr uint32_t a_lo = ((A::addr + (PR == 1 ? A::piece : 0u) + K * A::kadv) >> 4) | ((A::lbo >> 4) << 16);
+  constexpr uint32_t b_lo = ((B::addr + (PR == 2 ? B::piece : 0u) + K * B::kadv) >> 4) | ((B::lbo >> 4) << 16);
+  constexpr uint32_t a_hi = (A::sbo >> 4) | (1u << 14), b_hi = (B::sbo >> 4) | (1u << 14);
+  mma_imm<a_lo, a_hi, b_lo, b_hi, IDESC, DCOL>(tm, sbd, acc);
+}
+template <class A, class B, uint32_t IDESC, uint32_t DCOL, int PR, int... K>
+__device__ __forceinline__ void gemm_product_seq(uint32_t tm, uint32_t sbd, uint32_t acc0, std::integer_sequence<int, K...>) {
+  (mma_piece<A, B, IDESC, DCOL, PR, K>(tm, sbd, K == 0 ? acc0 : 1u), ...);
+}
+template <int KSTEPS, class A, class B, uint32_t IDESC, uint32_t DCOL, int PR>
+__device__ __forceinline__ void gemm_product(uint32_t tm, uint32_t sbd, uint32_t acc0) {
+  gemm_product_seq<A, B, IDESC, DCOL, PR>(tm, sbd, acc0, std::make_integer_sequence<int, KSTEPS>{});
+}
+// the part of D = A B^T that needs only the hi piece of the pass's operand (B_FROM_PASS: the pass wrote B, else A) ...
+template <int KSTEPS, class A, class B, uint32_t IDESC, uint32_t DCOL, bool B_FROM_PASS>
+__device__ __forceinline__ void gemm3_early(uint32_t tm, uint32_t sbd) {
+  gemm_product<KSTEPS, A, B, IDESC, DCOL, 0>(tm, sbd, 0u);
+  gemm_product<KSTEPS, A, B, IDESC, DCOL, B_FROM_PASS ? 1 : 2>(tm, sbd, 1u);
+}
+// ... and the product with its lo piece
+template <int KSTEPS, class A, class B, uint32_t IDESC, uint32_t DCOL, bool B_FROM_PASS>
+__device__ __forceinline__ void gemm3_late(uint32_t tm, uint32_t sbd) {
+  gemm_product<KSTEPS, A, B, IDESC, DCOL, B_FROM_PASS ? 2 : 1>(tm, sbd, 1u);
+}
+
 template <int FMT> struct Fm;
 template <> struct Fm<kBF16> {
   static constexpr float ws = 1.f, iws = 1.f;
@@ -121,6 +152,15 @@ template <> struct Fm<kBF16> {
     const __nv_bfloat162 l = __floats2bfloat162_rn(x0 - hf.x, x1 - hf.y);
     hi = *reinterpret_cast<const uint32_t*>(&h);
     lo = *reinterpret_cast<const uint32_t*>(&l);
+  }
+  static __device__ __forceinline__ uint32_t pack_hi(float x0, float x1) {
+    const __nv_bfloat162 h = __floats2bfloat162_rn(x0, x1);
+    return *reinterpret_cast<const uint32_t*>(&h);
+  }
+  static __device__ __forceinline__ uint32_t pack_lo(float x0, float x1, uint32_t hi) {
+    const float2 hf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&hi));
+    const __nv_bfloat162 l = __floats2bfloat162_rn(x0 - hf.x, x1 - hf.y);
+    return *reinterpret_cast<const uint32_t*>(&l);
   }
 };
 // two floats -> packed fp16 pair (x0 in the low half), round to nearest, SATURATING at +-65504: an adjoint chain whose
@@ -137,6 +177,11 @@ template <> struct Fm<kF16> {
     const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hi));
     lo = f2h2_sat(x0 - hf.x, x1 - hf.y);
   }
+  static __device__ __forceinline__ uint32_t pack_hi(float x0, float x1) { return f2h2_sat(x0, x1); }
+  static __device__ __forceinline__ uint32_t pack_lo(float x0, float x1, uint32_t hi) {
+    const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hi));
+    return f2h2_sat(x0 - hf.x, x1 - hf.y);
+  }
 };
 
 // 8 consecutive columns [c0, c0 + 8) of row r of X[R][C] (row-block stride rb) -> one 16-byte chunk per piece
@@ -150,6 +195,28 @@ __device__ __forceinline__ void store8(uint8_t* smem, uint32_t buf, uint32_t pie
   const uint32_t off = buf + (uint32_t)(r >> 3) * rb + ((uint32_t)(c0 >> 3) << 7) + ((uint32_t)(r & 7) << 4);
   *reinterpret_cast<uint4*>(smem + off) = hi;
   *reinterpret_cast<uint4*>(smem + off + piece) = lo;
+}
+
+// the same in two steps: the hi piece first (returned for the second step), the lo piece later
+template <int FMT>
+__device__ __forceinline__ uint4 store8_hi(uint8_t* smem, uint32_t buf, uint32_t rb, int r, int c0, const float* o) {
+  uint4 hi;
+  hi.x = Fm<FMT>::pack_hi(o[0], o[1]);
+  hi.y = Fm<FMT>::pack_hi(o[2], o[3]);
+  hi.z = Fm<FMT>::pack_hi(o[4], o[5]);
+  hi.w = Fm<FMT>::pack_hi(o[6], o[7]);
+  *reinterpret_cast<uint4*>(smem + buf + (uint32_t)(r >> 3) * rb + ((uint32_t)(c0 >> 3) << 7) + ((uint32_t)(r & 7) << 4)) = hi;
+  return hi;
+}
+template <int FMT>
+__device__ __forceinline__ void store8_lo(uint8_t* smem, uint32_t buf, uint32_t piece, uint32_t rb, int r, int c0, const float* o,
+                                          const uint4& hi) {
+  uint4 lo;
+  lo.x = Fm<FMT>::pack_lo(o[0], o[1], hi.x);
+  lo.y = Fm<FMT>::pack_lo(o[2], o[3], hi.y);
+  lo.z = Fm<FMT>::pack_lo(o[4], o[5], hi.z);
+  lo.w = Fm<FMT>::pack_lo(o[6], o[7], hi.w);
+  *reinterpret_cast<uint4*>(smem + buf + piece + (uint32_t)(r >> 3) * rb + ((uint32_t)(c0 >> 3) << 7) + ((uint32_t)(r & 7) << 4)) = lo;
 }
 
 // Activations on the tensor path.  The pre-activation columns of TMEM (a1, a2) hold a STASH from which sigma, sigma'
@@ -256,6 +323,9 @@ __global__ void __launch_bounds__(kThreads, 1) vhjb_tc_kernel(const __grid_const
   // the passes hidden under a GEMM (9b, 10b) arrive on their own barrier: a warp reaches them without waiting for
   // the other warps' previous arrival, and two arrivals of one warp must never count towards the same phase
   uint64_t* bar_passb = bar_pass + 5;
+  // early hand-over of a pass's hi pieces (split steps 1, 2, 4, 5, 7, 8, 10a): the issuer starts the two products that
+  // need hi alone while the pass computes the lo pieces
+  uint64_t* bar_passh = bar_pass + 6;
   uint32_t* tptr = reinterpret_cast<uint32_t*>(smem + kMisc + 568);
   float* sF = reinterpret_cast<float*>(smem + kMisc + 576);    // 2^f_s: weight-gradient scale of the forward operands
   float* sYm = reinterpret_cast<float*>(smem + kMisc + 832);   // max_c |2 y_c| of the state (second column half)
@@ -298,6 +368,7 @@ __global__ void __launch_bounds__(kThreads, 1) vhjb_tc_kernel(const __grid_const
     mbar_init(bar_wg6, 1);
     mbar_init(bar_wg9, 1);
     mbar_init(bar_passb, kComputeWarps);
+    mbar_init(bar_passh, kComputeWarps);
     mbar_fence_init();
   }
   if (warp == kComputeWarps) tmem_alloc(tptr, 512);
@@ -328,7 +399,25 @@ __global__ void __launch_bounds__(kThreads, 1) vhjb_tc_kernel(const __grid_const
     using H0_mn = MnMaj<kH0, kHPiece, kRbH>; using H0_k = KMaj<kH0, kHPiece, kRbH>;
     using G0_mn = MnMaj<kG0, kHPiece, kRbH>; using G0_k = KMaj<kG0, kHPiece, kRbH>;
     using Y1_mn = MnMaj<kF2, kYPiece, kRbY>; using Y1_k = KMaj<kF2, kYPiece, kRbY>;   // ybar lives in F2's space
-    uint32_t ph = 0, phb = 0;
+    uint32_t ph = 0, phb = 0, phh = 0;
+    // a split group: the products that need only the hi pieces of the pass's operand go first, on the early arrival
+#define HJB_TC_GROUP2(EARLY, LATE)        \
+  do {                                    \
+    mbar_wait(bar_passh, phh);            \
+    phh ^= 1u;                            \
+    tc_fence_after();                     \
+    if (elect_one()) {                    \
+      EARLY;                              \
+    }                                     \
+    __syncwarp();                         \
+    mbar_wait(bar_pass, ph);              \
+    ph ^= 1u;                             \
+    tc_fence_after();                     \
+    if (elect_one()) {                    \
+      LATE;                               \
+    }                                     \
+    __syncwarp();                         \
+  } while (0)
     // one group: wait for the passes' arrival, then issue (one elected lane); commits are explicit
 #define HJB_TC_GROUP(...)                 \
   do {                                    \
@@ -357,15 +446,19 @@ __global__ void __launch_bounds__(kThreads, 1) vhjb_tc_kernel(const __grid_const
       const uint32_t acc = (it == 0 || (it + blockIdx.x) % kFlushTiles == 0) ? 0u : 1u;
       const bool more = it + 1 < n_iter;
       // G1: a2^T = W2^T h1^T
-      HJB_TC_GROUP(gemm3<8, W2_mn, F0_mn, idN64_mn_mn, cA2>(tm, sb, 0u); mma_commit(bar_mma));
+      HJB_TC_GROUP2((gemm3_early<8, W2_mn, F0_mn, idN64_mn_mn, cA2, true>(tm, sb)),
+                    (gemm3_late<8, W2_mn, F0_mn, idN64_mn_mn, cA2, true>(tm, sb), mma_commit(bar_mma)));
       // G2: y = h2 W3                      (lanes = states)
-      HJB_TC_GROUP(gemm3<8, F1_mn, W3_mn, idY_mn_mn, cY>(tm, sb, 0u); mma_commit(bar_mma));
+      HJB_TC_GROUP2((gemm3_early<8, F1_mn, W3_mn, idY_mn_mn, cY, false>(tm, sb)),
+                    (gemm3_late<8, F1_mn, W3_mn, idY_mn_mn, cY, false>(tm, sb), mma_commit(bar_mma)));
       // G3: b2^T = W3 gy^T
       HJB_TC_GROUP(gemm3<4, W3_k, Y0_k, idN64_k_k, cB2>(tm, sb, 0u); mma_commit(bar_mma));
       // G4: b1^T = W2 g2^T
-      HJB_TC_GROUP(gemm3<8, W2_k, F0_mn, idN64_k_mn, cWk>(tm, sb, 0u); mma_commit(bar_mma));
+      HJB_TC_GROUP2((gemm3_early<8, W2_k, F0_mn, idN64_k_mn, cWk, true>(tm, sb)),
+                    (gemm3_late<8, W2_k, F0_mn, idN64_k_mn, cWk, true>(tm, sb), mma_commit(bar_mma)));
       // G5: g0 = g1 W1^T                   (lanes = states, 16 columns)
-      HJB_TC_GROUP(gemm3<8, F1_mn, W1_k, idN16_mn_k, cG0>(tm, sb, 0u); mma_commit(bar_mma));
+      HJB_TC_GROUP2((gemm3_early<8, F1_mn, W1_k, idN16_mn_k, cG0, false>(tm, sb)),
+                    (gemm3_late<8, F1_mn, W1_k, idN16_mn_k, cG0, false>(tm, sb), mma_commit(bar_mma)));
       if constexpr (!GRAD) {
         // after the epilogue: the next tile's H0 is in place
         HJB_TC_GROUP(if (more) { HJB_G0; });
@@ -374,17 +467,20 @@ __global__ void __launch_bounds__(kThreads, 1) vhjb_tc_kernel(const __grid_const
         HJB_TC_GROUP(gemm3<1, W1_mn, G0_k, idN64_mn_k, cWk>(tm, sb, 0u); mma_commit(bar_mma);
                      gemm3<4, F1_k, G0_mn, idN16_k_mn, cW1g>(tm, sb, acc); mma_commit(bar_wg6));
         // G7: g2bar^T = W2^T b1bar^T ; W2bar += b1bar^T g2
-        HJB_TC_GROUP(gemm3<8, W2_mn, F2_mn, idN64_mn_mn, cWk>(tm, sb, 0u); mma_commit(bar_mma);
-                     gemm3<4, F2_k, F0_k, idN128_k_k, cW2g>(tm, sb, acc));
+        HJB_TC_GROUP2((gemm3_early<8, W2_mn, F2_mn, idN64_mn_mn, cWk, true>(tm, sb)),
+                      (gemm3_late<8, W2_mn, F2_mn, idN64_mn_mn, cWk, true>(tm, sb), mma_commit(bar_mma),
+                       gemm3<4, F2_k, F0_k, idN128_k_k, cW2g>(tm, sb, acc)));
         // G8: gybar = b2bar W3 (lanes = states) ; W3bar += b2bar^T gy
-        HJB_TC_GROUP(gemm3<8, F1_mn, W3_mn, idY_mn_mn, cWk>(tm, sb, 0u); mma_commit(bar_mma);
-                     gemm3<4, F1_k, Y0_mn, idW3g_k_mn, cW3g>(tm, sb, acc));
+        HJB_TC_GROUP2((gemm3_early<8, F1_mn, W3_mn, idY_mn_mn, cWk, false>(tm, sb)),
+                      (gemm3_late<8, F1_mn, W3_mn, idY_mn_mn, cWk, false>(tm, sb), mma_commit(bar_mma),
+                       gemm3<4, F1_k, Y0_mn, idW3g_k_mn, cW3g>(tm, sb, acc)));
         // G9a: a2bar_pre^T = W3 ybar^T
         HJB_TC_GROUP(gemm3<4, W3_k, Y1_k, idN64_k_k, cWk>(tm, sb, 0u); mma_commit(bar_mma));
         // G9b: W3bar += h2^T ybar           (h2 recomputed under G9a)
         HJB_TC_GROUP_B(gemm3<4, F0_k, Y1_mn, idW3g_k_mn, cW3g>(tm, sb, 1u); mma_commit(bar_wg9));
         // G10a: a1bar_pre^T = W2 a2bar^T
-        HJB_TC_GROUP(gemm3<8, W2_k, F1_mn, idN64_k_mn, cWk>(tm, sb, 0u); mma_commit(bar_mma));
+        HJB_TC_GROUP2((gemm3_early<8, W2_k, F1_mn, idN64_k_mn, cWk, true>(tm, sb)),
+                      (gemm3_late<8, W2_k, F1_mn, idN64_k_mn, cWk, true>(tm, sb), mma_commit(bar_mma)));
         // G10b: W2bar += h1^T a2bar         (h1 recomputed under G10a)
         HJB_TC_GROUP_B(gemm3<4, F0_k, F1_k, idN128_k_k, cW2g>(tm, sb, 1u));
         // G11: W1bar^T += a1bar^T h0 ; then the next tile's first GEMM (its H0 was written during step 6)
@@ -394,6 +490,7 @@ __global__ void __launch_bounds__(kThreads, 1) vhjb_tc_kernel(const __grid_const
     }
 #undef HJB_G0
 #undef HJB_TC_GROUP_B
+#undef HJB_TC_GROUP2
 #undef HJB_TC_GROUP
   } else {
     // ================================ element-wise passes ================================
@@ -424,18 +521,38 @@ __global__ void __launch_bounds__(kThreads, 1) vhjb_tc_kernel(const __grid_const
       ph ^= 1u;
       tc_fence_after();
     };
-    // feature pass: out(j, s) = fn(D(j, s), stash(j, s)) for the 32 states of this thread -> X[feature][state]
-    auto feature_pass = [&](uint32_t cD, uint32_t cStash, uint32_t buf, auto fn) {
+    // the hi pieces of a split step's operand are in shared memory
+    auto pass_half = [&]() {
+      fence_async_smem();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_passh);
+    };
+    // feature pass: out(j, s) = fn(D(j, s), stash(j, s)) for the 32 states of this thread -> X[feature][state];
+    // the hi pieces go first and are handed over (pass_half) before the lo pieces are computed
+    auto feature_pass = [&](auto split, uint32_t cD, uint32_t cStash, uint32_t buf, auto fn) {
       uint32_t d[32], st[32];
       tmem_ld32(tl + cD + sc0, d);
       tmem_ld32(tl + cStash + sc0, st);
       tc_wait_ld();
+      uint4 hi[4];
 #pragma unroll
       for (int g = 0; g < 4; ++g) {
         float o[8];
 #pragma unroll
-        for (int t = 0; t < 8; ++t) o[t] = fn(__uint_as_float(d[8 * g + t]), __uint_as_float(st[8 * g + t]));
-        store8<FMT>(smem, buf, kFPiece, kRbF, j, sc0 + 8 * g, o);
+        for (int t = 0; t < 8; ++t) {
+          o[t] = fn(__uint_as_float(d[8 * g + t]), __uint_as_float(st[8 * g + t]));
+          d[8 * g + t] = __float_as_uint(o[t]);
+        }
+        hi[g] = store8_hi<FMT>(smem, buf, kRbF, j, sc0 + 8 * g, o);
+      }
+      if constexpr (decltype(split)::value) pass_half();
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        float o[8];
+#pragma unroll
+        for (int t = 0; t < 8; ++t) o[t] = __uint_as_float(d[8 * g + t]);
+        store8_lo<FMT>(smem, buf, kFPiece, kRbF, j, sc0 + 8 * g, o, hi[g]);
       }
     };
     // h = sigma(a) [* 2^f_s]; `first`: the columns hold the raw pre-activation (tanh: replaced by the stash here)
@@ -448,17 +565,37 @@ __global__ void __launch_bounds__(kThreads, 1) vhjb_tc_kernel(const __grid_const
         for (int t = 0; t < 32; ++t) st[t] = __float_as_uint(tc_stash<ACT>(__uint_as_float(st[t]) * iws));
         tmem_st32(tl + cStash + sc0, st);
       }
+      if constexpr (!decltype(scaled)::value) {   // forward passes (steps 1, 2): split hand-over like feature_pass
+        uint4 hi[4];
 #pragma unroll
-      for (int g = 0; g < 4; ++g) {
-        float o[8];
+        for (int g = 0; g < 4; ++g) {
+          float o[8];
 #pragma unroll
-        for (int t = 0; t < 8; ++t) o[t] = tc_sig<ACT>(__uint_as_float(st[8 * g + t]) * iws);
-        if constexpr (decltype(scaled)::value) {
+          for (int t = 0; t < 8; ++t) {
+            o[t] = tc_sig<ACT>(__uint_as_float(st[8 * g + t]) * iws);
+            st[8 * g + t] = __float_as_uint(o[t]);
+          }
+          hi[g] = store8_hi<FMT>(smem, buf, kRbF, j, sc0 + 8 * g, o);
+        }
+        pass_half();
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          float o[8];
+#pragma unroll
+          for (int t = 0; t < 8; ++t) o[t] = __uint_as_float(st[8 * g + t]);
+          store8_lo<FMT>(smem, buf, kFPiece, kRbF, j, sc0 + 8 * g, o, hi[g]);
+        }
+      } else {
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          float o[8];
+#pragma unroll
+          for (int t = 0; t < 8; ++t) o[t] = tc_sig<ACT>(__uint_as_float(st[8 * g + t]) * iws);
           const float4 f0 = *reinterpret_cast<const float4*>(sF + sc0 + 8 * g), f1 = *reinterpret_cast<const float4*>(sF + sc0 + 8 * g + 4);
           o[0] *= f0.x; o[1] *= f0.y; o[2] *= f0.z; o[3] *= f0.w;
           o[4] *= f1.x; o[5] *= f1.y; o[6] *= f1.z; o[7] *= f1.w;
+          store8<FMT>(smem, buf, kFPiece, kRbF, j, sc0 + 8 * g, o);
         }
-        store8<FMT>(smem, buf, kFPiece, kRbF, j, sc0 + 8 * g, o);
       }
       if constexpr (decltype(first)::value && ACT == HJB_ACT_TANH) tc_wait_st();
     };
@@ -729,7 +866,7 @@ __global__ void __launch_bounds__(kThreads, 1) vhjb_tc_kernel(const __grid_const
       // P4: g2 = b2 sigma'(a2) -> F0
       wait_mma();
       tmark(it);
-      feature_pass(cB2, cA2, kF0, masked);
+      feature_pass(std::true_type{}, cB2, cA2, kF0, masked);
       tmark(it);
       pass_done();                                              // -> G4
       // P5: g1 = b1 sigma'(a1) -> F1
@@ -749,12 +886,13 @@ __global__ void __launch_bounds__(kThreads, 1) vhjb_tc_kernel(const __grid_const
         dnext = vnext ? __ldg(a.dones + nidx) : 0.f;
         cnext = vnext ? (STREAM ? __ldcg(a.costs + nidx) : __ldg(a.costs + nidx)) : 1.f;
       }
-      if constexpr (kSmooth)
+      if constexpr (kSmooth) {
         feature_pass_k(cWk, cA1, kF1, [&](float d, float st, int k) {
           chain1[k] = d * (iws * tc_d2<ACT>(st));
           return masked(d, st);
         });
-      else feature_pass(cWk, cA1, kF1, masked);
+        pass_half();
+      } else feature_pass(std::true_type{}, cWk, cA1, kF1, masked);
       tmark(it);
       pass_done();                                              // -> G5
       // P6 (epilogue warps): control, Hamiltonian residual, adjoint seeds (vhjb.py:204-253)
@@ -834,12 +972,13 @@ __global__ void __launch_bounds__(kThreads, 1) vhjb_tc_kernel(const __grid_const
         // P7: b1bar = g1bar sigma'(a1) -> F2 ; then h0 2^f_s -> G0 buffer (for step 11) once W1bar's GEMM has read g0bar
         wait_mma();
         tmark(it);
-        if constexpr (kSmooth)
+        if constexpr (kSmooth) {
           feature_pass_k(cWk, cA1, kF2, [&](float d, float st, int k) {
             chain1[k] *= d * iws;                               // g1bar b1 sigma''(a1)
             return masked(d, st);
           });
-        else feature_pass(cWk, cA1, kF2, masked);
+          pass_half();
+        } else feature_pass(std::true_type{}, cWk, cA1, kF2, masked);
         if (epi_warp) {
           wait_bar(bar_wg6, tpar);
           store_h0(kG0, fscale);
@@ -849,12 +988,13 @@ __global__ void __launch_bounds__(kThreads, 1) vhjb_tc_kernel(const __grid_const
         // P8: b2bar = g2bar sigma'(a2) -> F1   (W1bar's GEMM, the last reader of g1 in F1, precedes G7 in issue order)
         wait_mma();
         tmark(it);
-        if constexpr (kSmooth)
+        if constexpr (kSmooth) {
           feature_pass_x(cWk, cA2, cB2, kF1, std::true_type{}, [&](float d, float st, float& x) {
             x *= d * (iws * tc_d2<ACT>(st));                    // b2 -> g2bar b2 sigma''(a2)
             return masked(d, st);
           });
-        else feature_pass(cWk, cA2, kF1, masked);
+          pass_half();
+        } else feature_pass(std::true_type{}, cWk, cA2, kF1, masked);
         tmark(it);
         pass_done();                                            // -> G8
         // P9a (state warps): ybar = 2 gybar + 2 y Vbar -> Y1 (F2's space: W2bar's GEMM of step 7 precedes G8)
@@ -901,9 +1041,10 @@ __global__ void __launch_bounds__(kThreads, 1) vhjb_tc_kernel(const __grid_const
         // P10a: a2bar = a2bar_pre sigma'(a2) -> F1             (b2bar's last reader, step 8, precedes G9a)
         wait_mma();
         tmark(it);
-        if constexpr (kSmooth)
+        if constexpr (kSmooth) {
           feature_pass_x(cWk, cA2, cB2, kF1, std::false_type{}, [&](float d, float st, float& x) { return watched(d, st) + x; });
-        else feature_pass(cWk, cA2, kF1, watched);
+          pass_half();
+        } else feature_pass(std::true_type{}, cWk, cA2, kF1, watched);
         tmark(it);
         pass_done();                                            // -> G10a
         // P10b (under G10a): h1 2^f_s -> F0 once W3bar's GEMM of step 9 has read h2 (and ybar in F2)
@@ -915,7 +1056,7 @@ __global__ void __launch_bounds__(kThreads, 1) vhjb_tc_kernel(const __grid_const
         tmark(it);
         if constexpr (kSmooth)
           feature_pass_k(cWk, cA1, kF2, [&](float d, float st, int k) { return watched(d, st) + chain1[k]; });
-        else feature_pass(cWk, cA1, kF2, watched);
+        else feature_pass(std::false_type{}, cWk, cA1, kF2, watched);
         tmark(it);
         pass_done();                                            // -> G11 (+ G0 of the next tile)
       }
