@@ -207,7 +207,8 @@ typedef struct hjb_vnet {
   int32_t act; /* hjb_activation */
   int32_t features[3];
   int32_t impl; /* 0: tensor-core kernels (fp16 x 3, vhjb_tc.cuh); 1: fp32 CUDA-core kernels (vhjb_simt.cuh) — exact for
-                   batches whose adjoint seeds or chain gain leave the fp16 range management (hjb_vhjb_saturation) */
+                   on-device cross-check of the tensor path (which sends what leaves its fp16 range management through the
+                   same fp32 kernel by itself: hjb_vhjb_deferred) */
   const float* params; /* DEVICE pointer, 128 n + 24576 floats */
   float mean[HJB_MAX_N], std[HJB_MAX_N], xf[HJB_MAX_N];
   float eps_s; /* config.epsilon_scalar */
@@ -339,11 +340,15 @@ int hjb_vhjb_train_step_peer(const hjb_system* sys, const hjb_vnet* net, const h
  * sample stored with cost ~ 0) does NOT go through that chain: the kernel records its index and the fp32 CUDA-core kernel,
  * launched behind it by the same entry point, computes exactly those states; their weight gradients are summed after the
  * tensor kernel's partials in a fixed order (hjb_vhjb_deferred: how many states of the last launch took that pass).
- * What remains countable: a deferred list that is full (2048 states per epilogue warp of the tensor kernel: the state
- * then stays on the tensor path with clipped seeds), or an adjoint chain that grows past fp16's 65504 between the seeds
- * and the first layer (a gain above ~1000: conversions saturate, nothing becomes inf / NaN).  hjb_vhjb_saturation returns
- * that count for the last hjb_vhjb_loss_grad on this workspace (device float `count`, stream-ordered): 0 for every batch
- * met in the reference's configurations; callers that see non-zero set hjb_vnet.impl = 1 (fp32 CUDA-core kernels).
+ * Two things can still escape that management: a deferred list that is full (2048 states per epilogue warp of the tensor
+ * kernel), or an adjoint chain that grows past fp16's 65504 between the seeds and the first layer (a backward gain above
+ * ~1000: conversions saturate, nothing becomes inf / NaN).  The tensor kernel counts both, the fp32 pass behind it reads the
+ * count and, when it is non-zero, runs the WHOLE launch in fp32; the reductions then leave the tensor launch's partials out
+ * (hjb_vhjb_deferred == B for such a launch).  So every launch is exact, decided on the device, and the next launch is
+ * back on the tensor cores.  hjb_vhjb_saturation returns the count of what was neither computed in range, nor deferred,
+ * nor redone for the last hjb_vhjb_loss_grad on this workspace (device float `count`, stream-ordered): 0 by construction
+ * for the gradient entry points of this library; kept in the ABI for callers that poll it (a non-zero value would mean:
+ * set hjb_vnet.impl = 1, the fp32 CUDA-core kernels).  The workspace must be zero-filled before its first use.
  */
 int hjb_vhjb_saturation(const void* workspace, int32_t n, float* count, void* stream);
 /* The same count summed over every gradient launch on this workspace since the last reset (count nullable; reset != 0

@@ -174,18 +174,18 @@ class VhjbKernels:
         return self.grad, self.sums
 
     def saturated(self) -> int:
-        """Number of states of the last ``loss_grad`` that the tensor-core kernel had to clip (include/hjb_b200.h
-        ``hjb_vhjb_saturation``): out-of-range seeds are deferred to the fp32 pass (``deferred()``), so what is counted
-        here is a full deferred list or an adjoint chain beyond fp16's range — 0 in every reference configuration.
-        Synchronises the stream."""
+        """Number of states of the last ``loss_grad`` that were neither computed in range, nor deferred, nor redone
+        (include/hjb_b200.h ``hjb_vhjb_saturation``): out-of-range seeds are deferred to the fp32 pass (``deferred()``), and
+        a launch in which a deferred list filled up or an adjoint chain left fp16's range is redone as a whole by that pass
+        — so this reads 0 by construction.  Synchronises the stream."""
         out = self.torch.zeros(1, device="cuda", dtype=self.torch.float32)
         L.check(L.lib().hjb_vhjb_saturation(L.ptr(self.workspace), self.n, L.ptr(out), L.stream_ptr()), "hjb_vhjb_saturation")
         return int(out.item())
 
     def deferred(self) -> int:
         """States of the last ``loss_grad`` / ``train_step`` that the tensor-core kernel handed to the fp32 pass (their
-        adjoint seeds lie beyond its fp16 range management: near-goal states, terminal samples with cost ~ 0).
-        Synchronises the stream."""
+        adjoint seeds lie beyond its fp16 range management: near-goal states, terminal samples with cost ~ 0); the whole
+        batch when the launch had to be redone (see ``saturated``).  Synchronises the stream."""
         out = self.torch.zeros(1, device="cuda", dtype=self.torch.float32)
         L.check(L.lib().hjb_vhjb_deferred(L.ptr(self.workspace), self.n, L.ptr(out), L.stream_ptr()), "hjb_vhjb_deferred")
         return int(out.item())

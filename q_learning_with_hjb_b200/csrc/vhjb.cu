@@ -37,6 +37,7 @@ __global__ void __launch_bounds__(256) vhjb_reduce_kernel(const float* __restric
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= count) return;
   float s = 0.f;
+  if (dtail != nullptr && dtail[5] != 0.f) ncta = 0;     // the fp32 pass redid the whole batch (vhjb_simt.cuh: redo_all)
   for (int c = 0; c < ncta; ++c) s += partial[(int64_t)c * pstride + first + j];
   if (dtail != nullptr) {
     const int nd = (int)dtail[3];
@@ -50,11 +51,12 @@ __global__ void __launch_bounds__(256) vhjb_reduce_kernel(const float* __restric
 // hjb_vhjb_stream_failures resets it); when it is non-zero the loss sums of this step are poisoned with NaN and the
 // guarded Adam update (hjb_vhjb_adam_guarded) skips the step.
 __global__ void vhjb_sat_kernel(const float* __restrict__ partial, int64_t pstride, int ncta, int at, float* __restrict__ tail,
-                                int accumulate, int streamed, float* __restrict__ sums) {
+                                int accumulate, int streamed, float* __restrict__ sums, const float* __restrict__ dtail) {
   // one warp: lane l sums the CTAs l, l + 32, ... (counts are small integers: exact in any order), then a shuffle tree
   float s = 0.f, f = 0.f;
+  const bool redone = dtail != nullptr && dtail[5] != 0.f;   // what the tensor launch could not hold was recomputed in fp32
   for (int c = threadIdx.x; c < ncta; c += 32) {
-    s += partial[(int64_t)c * pstride + at];
+    if (!redone) s += partial[(int64_t)c * pstride + at];
     if (streamed) f += partial[(int64_t)c * pstride + at + 1];
   }
 #pragma unroll
@@ -143,6 +145,7 @@ __global__ void __launch_bounds__(256) vhjb_reduce_adam_kernel(const float* __re
                                                                const float* __restrict__ norm, float reg,
                                                                float* __restrict__ loss_acc, const float* __restrict__ dtail) {
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (dtail != nullptr && dtail[5] != 0.f) ncta = 0;     // the fp32 pass redid the whole batch (vhjb_simt.cuh: redo_all)
   if (j < P) {
     float g = 0.f;
     for (int c = 0; c < ncta; ++c) g += partial[(int64_t)c * pstride + j];
@@ -226,6 +229,7 @@ __global__ void __launch_bounds__(256) vhjb_reduce_exchange_adam_kernel(const fl
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   const int Q = P + 4, nblk = gridDim.x;
   const int parity = (int)(x.seq & 1u);
+  if (dtail != nullptr && dtail[5] != 0.f) ncta = 0;     // the fp32 pass redid the whole batch (vhjb_simt.cuh: redo_all)
   float mine = 0.f;
   if (j < P + 2) {
     for (int c = 0; c < ncta; ++c) mine += partial[(int64_t)c * pstride + j];
@@ -492,7 +496,7 @@ static int run_vhjb(const hjb_system* sys, const hjb_vnet* net, const hjb_task* 
     if (e != cudaSuccess) return (int)e;
   }
   if (want_grad) {  // saturation count of the fp16 range management (vhjb_tc.cuh) -> workspace tail
-    vhjb_sat_kernel<<<1, 32, 0, st>>>(a.partial, a.pstride, l.grid, P + 2, a.tail, (int)accumulate, ready != nullptr, sums);
+    vhjb_sat_kernel<<<1, 32, 0, st>>>(a.partial, a.pstride, l.grid, P + 2, a.tail, (int)accumulate, ready != nullptr, sums, dtail);
     e = cudaGetLastError();
     if (e != cudaSuccess) return (int)e;
   }

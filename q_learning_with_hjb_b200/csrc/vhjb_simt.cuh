@@ -61,7 +61,8 @@ struct VhjbArgs {
   int defer_gather;     // CUDA-core kernel: 1 = the batch is the concatenation of the deferred lists
   int part_slot0;       // first per-CTA partial slot of this launch
   float* tail;          // workspace tail words: [0] saturation (launch), [1] saturation (total), [2] stream failures,
-                        // [3] CTAs of the deferred pass that wrote partials, [4] deferred states of the last launch
+                        // [3] CTAs of the deferred pass that wrote partials, [4] deferred states of the last launch,
+                        // [5] 1 = the deferred pass ran the whole batch (the tensor launch's partials are void)
 };
 constexpr int kDeferCap = 2048;   // entries per list; a list that is full counts further states as saturated (not deferred)
 
@@ -191,8 +192,18 @@ __global__ void __launch_bounds__(VTHREADS, 1) vhjb_kernel(const __grid_constant
   int* sPre = reinterpret_cast<int*>(sVb + VBM);     // [defer_lists + 1] exclusive prefix sums of the list lengths
   int64_t n_tiles = a.n_tiles;
   int64_t n_states = a.B;
+  bool redo_all = false;
   if constexpr (GRAD) {
     if (a.defer_gather) {
+      // The tensor launch counts (partial[cta][P + 2]) what its fp16 range management could not hold even so: an adjoint
+      // chain that reached the fp16 ceiling behind in-range seeds, a deferred list that was full.  Any such event and this
+      // pass runs the WHOLE batch in fp32; tail[5] tells the reductions to leave the tensor launch's partials out.  Rare
+      // (a trained net with a large backward gain and states next to the goal), exact, decided on the device.
+      __shared__ int sRedo;
+      if (tid == 0) sRedo = 0;
+      __syncthreads();
+      for (int c = tid; c < a.defer_lists / 4; c += VTHREADS)
+        if (__ldcg(a.partial + (int64_t)c * a.pstride + vhjb_param_count(N) + 2) != 0.f) sRedo = 1;
       if (warp == 0) {
         int run = 0;
         for (int base = 0; base < a.defer_lists; base += 32) {
@@ -210,11 +221,13 @@ __global__ void __launch_bounds__(VTHREADS, 1) vhjb_kernel(const __grid_constant
         if (lane == 0) sPre[a.defer_lists] = run;
       }
       __syncthreads();
-      n_states = sPre[a.defer_lists];
+      redo_all = sRedo != 0;
+      n_states = redo_all ? a.B : (int64_t)sPre[a.defer_lists];
       n_tiles = (n_states + VBM - 1) / VBM;
       if (blockIdx.x == 0 && tid == 0) {
         a.tail[3] = (float)min((int64_t)gridDim.x, n_tiles);
         a.tail[4] = (float)n_states;                      // hjb_vhjb_deferred: states of this launch that took the fp32 pass
+        a.tail[5] = redo_all ? 1.f : 0.f;
       }
       if ((int64_t)blockIdx.x >= n_tiles) return;      // (whole CTA: nothing to do, no partial written, none read)
     }
@@ -254,7 +267,7 @@ __global__ void __launch_bounds__(VTHREADS, 1) vhjb_kernel(const __grid_constant
     int64_t idx = tile * VBM + lane;   // the state this lane owns
     const bool valid = idx < n_states;
     if constexpr (GRAD) {
-      if (a.defer_gather && warp == 0) {   // entry idx of the concatenated lists: binary search over the prefix sums
+      if (a.defer_gather && !redo_all && warp == 0) {   // entry idx of the concatenated lists: binary search over the prefix sums
         int lo = 0, hi = a.defer_lists;
         const int j = (int)idx;
         while (hi - lo > 1) {
