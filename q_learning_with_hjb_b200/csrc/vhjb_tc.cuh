@@ -613,23 +613,38 @@ __global__ void __launch_bounds__(kThreads, 1) vhjb_tc_kernel(const __grid_const
     };
     // smooth activations: the b1 chain (b1 sigma''(a1), then g1bar b1 sigma''(a1)) of this thread's 32 states
     float chain1[kSmooth ? 32 : 1];
-    // feature pass with the column index handed to fn (for chain1)
-    auto feature_pass_k = [&](uint32_t cD, uint32_t cStash, uint32_t buf, auto fn) {
+    // feature pass with the column index handed to fn (for chain1); split hand-over like feature_pass
+    auto feature_pass_k = [&](auto split, uint32_t cD, uint32_t cStash, uint32_t buf, auto fn) {
       uint32_t d[32], st[32];
       tmem_ld32(tl + cD + sc0, d);
       tmem_ld32(tl + cStash + sc0, st);
       tc_wait_ld();
+      uint4 hi[4];
 #pragma unroll
       for (int g = 0; g < 4; ++g) {
         float o[8];
 #pragma unroll
-        for (int t = 0; t < 8; ++t) o[t] = fn(__uint_as_float(d[8 * g + t]), __uint_as_float(st[8 * g + t]), 8 * g + t);
-        store8<FMT>(smem, buf, kFPiece, kRbF, j, sc0 + 8 * g, o);
+        for (int t = 0; t < 8; ++t) {
+          o[t] = fn(__uint_as_float(d[8 * g + t]), __uint_as_float(st[8 * g + t]), 8 * g + t);
+          d[8 * g + t] = __float_as_uint(o[t]);
+        }
+        hi[g] = store8_hi<FMT>(smem, buf, kRbF, j, sc0 + 8 * g, o);
+      }
+      if constexpr (decltype(split)::value) pass_half();
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        float o[8];
+#pragma unroll
+        for (int t = 0; t < 8; ++t) o[t] = __uint_as_float(d[8 * g + t]);
+        store8_lo<FMT>(smem, buf, kFPiece, kRbF, j, sc0 + 8 * g, o, hi[g]);
       }
     };
     // feature pass with a third TMEM operand x (the b2 chain in the y columns), 16 columns at a time;
-    // out = fn(d, stash, x) (x is replaced by the new chain value when WB)
+    // out = fn(d, stash, x) (x is replaced by the new chain value when WB); the hi pieces of both halves go first, then the
+    // hand-over (pass_half: these passes are split steps), then the lo pieces
     auto feature_pass_x = [&](uint32_t cD, uint32_t cStash, uint32_t cX, uint32_t buf, auto wb, auto fn) {
+      float ov[32];
+      uint4 hi[4];
 #pragma unroll
       for (int hf = 0; hf < 2; ++hf) {
         uint32_t d[16], st[16], x[16];
@@ -639,18 +654,22 @@ __global__ void __launch_bounds__(kThreads, 1) vhjb_tc_kernel(const __grid_const
         tc_wait_ld();
 #pragma unroll
         for (int g = 0; g < 2; ++g) {
-          float o[8];
 #pragma unroll
           for (int t = 0; t < 8; ++t) {
             float xv = __uint_as_float(x[8 * g + t]);
-            o[t] = fn(__uint_as_float(d[8 * g + t]), __uint_as_float(st[8 * g + t]), xv);
+            ov[16 * hf + 8 * g + t] = fn(__uint_as_float(d[8 * g + t]), __uint_as_float(st[8 * g + t]), xv);
             x[8 * g + t] = __float_as_uint(xv);
           }
-          store8<FMT>(smem, buf, kFPiece, kRbF, j, sc0 + 16 * hf + 8 * g, o);
+          hi[2 * hf + g] = store8_hi<FMT>(smem, buf, kRbF, j, sc0 + 16 * hf + 8 * g, ov + 16 * hf + 8 * g);
         }
-        if constexpr (decltype(wb)::value) tmem_st16(tl + cX + sc0 + 16 * hf, x);
+        if constexpr (decltype(wb)::value) {
+          tmem_st16(tl + cX + sc0 + 16 * hf, x);
+          tc_wait_st();          // (x's registers are reused by the next half)
+        }
       }
-      if constexpr (decltype(wb)::value) tc_wait_st();
+      pass_half();
+#pragma unroll
+      for (int g = 0; g < 4; ++g) store8_lo<FMT>(smem, buf, kFPiece, kRbF, j, sc0 + 8 * g, ov + 8 * g, hi[g]);
     };
 
     float xraw[N], z[N];
@@ -886,13 +905,12 @@ __global__ void __launch_bounds__(kThreads, 1) vhjb_tc_kernel(const __grid_const
         dnext = vnext ? __ldg(a.dones + nidx) : 0.f;
         cnext = vnext ? (STREAM ? __ldcg(a.costs + nidx) : __ldg(a.costs + nidx)) : 1.f;
       }
-      if constexpr (kSmooth) {
-        feature_pass_k(cWk, cA1, kF1, [&](float d, float st, int k) {
+      if constexpr (kSmooth)
+        feature_pass_k(std::true_type{}, cWk, cA1, kF1, [&](float d, float st, int k) {
           chain1[k] = d * (iws * tc_d2<ACT>(st));
           return masked(d, st);
         });
-        pass_half();
-      } else feature_pass(std::true_type{}, cWk, cA1, kF1, masked);
+      else feature_pass(std::true_type{}, cWk, cA1, kF1, masked);
       tmark(it);
       pass_done();                                              // -> G5
       // P6 (epilogue warps): control, Hamiltonian residual, adjoint seeds (vhjb.py:204-253)
@@ -972,13 +990,12 @@ __global__ void __launch_bounds__(kThreads, 1) vhjb_tc_kernel(const __grid_const
         // P7: b1bar = g1bar sigma'(a1) -> F2 ; then h0 2^f_s -> G0 buffer (for step 11) once W1bar's GEMM has read g0bar
         wait_mma();
         tmark(it);
-        if constexpr (kSmooth) {
-          feature_pass_k(cWk, cA1, kF2, [&](float d, float st, int k) {
+        if constexpr (kSmooth)
+          feature_pass_k(std::true_type{}, cWk, cA1, kF2, [&](float d, float st, int k) {
             chain1[k] *= d * iws;                               // g1bar b1 sigma''(a1)
             return masked(d, st);
           });
-          pass_half();
-        } else feature_pass(std::true_type{}, cWk, cA1, kF2, masked);
+        else feature_pass(std::true_type{}, cWk, cA1, kF2, masked);
         if (epi_warp) {
           wait_bar(bar_wg6, tpar);
           store_h0(kG0, fscale);
@@ -988,13 +1005,12 @@ __global__ void __launch_bounds__(kThreads, 1) vhjb_tc_kernel(const __grid_const
         // P8: b2bar = g2bar sigma'(a2) -> F1   (W1bar's GEMM, the last reader of g1 in F1, precedes G7 in issue order)
         wait_mma();
         tmark(it);
-        if constexpr (kSmooth) {
+        if constexpr (kSmooth)
           feature_pass_x(cWk, cA2, cB2, kF1, std::true_type{}, [&](float d, float st, float& x) {
             x *= d * (iws * tc_d2<ACT>(st));                    // b2 -> g2bar b2 sigma''(a2)
             return masked(d, st);
           });
-          pass_half();
-        } else feature_pass(std::true_type{}, cWk, cA2, kF1, masked);
+        else feature_pass(std::true_type{}, cWk, cA2, kF1, masked);
         tmark(it);
         pass_done();                                            // -> G8
         // P9a (state warps): ybar = 2 gybar + 2 y Vbar -> Y1 (F2's space: W2bar's GEMM of step 7 precedes G8)
@@ -1041,10 +1057,9 @@ __global__ void __launch_bounds__(kThreads, 1) vhjb_tc_kernel(const __grid_const
         // P10a: a2bar = a2bar_pre sigma'(a2) -> F1             (b2bar's last reader, step 8, precedes G9a)
         wait_mma();
         tmark(it);
-        if constexpr (kSmooth) {
+        if constexpr (kSmooth)
           feature_pass_x(cWk, cA2, cB2, kF1, std::false_type{}, [&](float d, float st, float& x) { return watched(d, st) + x; });
-          pass_half();
-        } else feature_pass(std::true_type{}, cWk, cA2, kF1, watched);
+        else feature_pass(std::true_type{}, cWk, cA2, kF1, watched);
         tmark(it);
         pass_done();                                            // -> G10a
         // P10b (under G10a): h1 2^f_s -> F0 once W3bar's GEMM of step 9 has read h2 (and ybar in F2)
@@ -1055,7 +1070,7 @@ __global__ void __launch_bounds__(kThreads, 1) vhjb_tc_kernel(const __grid_const
         wait_mma();
         tmark(it);
         if constexpr (kSmooth)
-          feature_pass_k(cWk, cA1, kF2, [&](float d, float st, int k) { return watched(d, st) + chain1[k]; });
+          feature_pass_k(std::false_type{}, cWk, cA1, kF2, [&](float d, float st, int k) { return watched(d, st) + chain1[k]; });
         else feature_pass(std::false_type{}, cWk, cA1, kF2, watched);
         tmark(it);
         pass_done();                                            // -> G11 (+ G0 of the next tile)
