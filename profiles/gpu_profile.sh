@@ -13,5 +13,9 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv \
 $CMD > gpurun_out/${TAG}_plain2.log 2>&1 &&
 ncu --set full --clock-control none --import-source on -k regex:${KERNEL} -s ${SKIP:-3} -c 1 \
     -o gpurun_out/${TAG}_full -f $CMD > gpurun_out/${TAG}_ncu_full.log 2>&1
+# the raw metric page travels back as CSV (small); the report itself (8-13 MB with sources) only when KEEP_REP=1 —
+# gpurun merges at most 64 MiB of gpurun_out/ back
+ncu -i gpurun_out/${TAG}_full.ncu-rep --page raw --csv > gpurun_out/${TAG}_raw.csv 2>/dev/null
+[ "${KEEP_REP:-0}" = "1" ] || rm -f gpurun_out/${TAG}_full.ncu-rep
 tail -1 gpurun_out/${TAG}_plain.log | cut -c1-300
 tail -2 gpurun_out/${TAG}_ncu_full.log

@@ -29,6 +29,15 @@ KEYS = ["gpu__time_duration.sum", "launch__registers_per_thread", "launch__grid_
         "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "smsp__cycles_active.avg", "sm__cycles_elapsed.avg"]
 
 
+def raw_page(tag, rep):
+    """The raw metric page of the capture: the CSV exported on the GPU box (gpu_profile.sh) when it is there and not older
+    than a report of the same tag, else exported here from the report."""
+    raw = os.path.join(OUT, f"{tag}_raw.csv")
+    if os.path.exists(raw) and (not os.path.exists(rep) or os.path.getmtime(raw) >= os.path.getmtime(rep)):
+        return open(raw).read()
+    return subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+
+
 def launches(tag):
     path = os.path.join(OUT, f"{tag}_launches.csv")
     rows = [r for r in csv.reader(l for l in open(path) if l.startswith('"'))]
@@ -49,7 +58,7 @@ def launches(tag):
 
 def full(tag):
     rep = os.path.join(OUT, f"{tag}_full.ncu-rep")
-    txt = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    txt = raw_page(tag, rep)
     rows = list(csv.reader(io.StringIO(txt)))
     hdr, units, vals = rows[0], rows[1], rows[2]
     d = {h: (vals[i], units[i]) for i, h in enumerate(hdr)}
@@ -63,7 +72,7 @@ def full(tag):
 def traffic(tag):
     """dram__bytes_read.sum + dram__bytes_write.sum of the profiled launch, in bytes (None if absent)."""
     rep = os.path.join(OUT, f"{tag}_full.ncu-rep")
-    txt = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    txt = raw_page(tag, rep)
     rows = list(csv.reader(io.StringIO(txt)))
     hdr, units, vals = rows[0], rows[1], rows[2]
     mult = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}

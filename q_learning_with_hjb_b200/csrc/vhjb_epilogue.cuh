@@ -15,7 +15,7 @@ template <class S, int UFORM, int RFORM, bool GRAD>
 __device__ __forceinline__ void state_epilogue(const VhjbArgs& a, const float* g0, float Vy, const float* z, float zz, float lz,
                                                const float* f, const float* G, float done, float cost, bool valid, int64_t idx,
                                                float inv_norm0, float inv_norm1, float& hjb_sum, float& term_sum, float* pbar,
-                                               float& Vbar) {
+                                               float& Vbar, float icost_pre = 0.f) {
   constexpr int N = S::N, M = S::M;
   float p[N];
 #pragma unroll
@@ -25,10 +25,15 @@ __device__ __forceinline__ void state_epilogue(const VhjbArgs& a, const float* g
   bool inside[M];
 #pragma unroll
   for (int k = 0; k < M; ++k) {
-    float s = 0.f;
+    // (gradient kernel: two partial sums, half the dependent chain — its epilogue is one warp per scheduler on the
+    // critical path of the tile; the residual kernels run at their register cap and overlap their epilogues)
+    float s0 = 0.f, s1 = 0.f;
 #pragma unroll
-    for (int i = 0; i < N; ++i) s = fmaf(p[i], G[i * M + k], s);
-    c[k] = s;
+    for (int i = 0; i < N; ++i) {
+      if (GRAD && (i & 1)) s1 = fmaf(p[i], G[i * M + k], s1);
+      else s0 = fmaf(p[i], G[i * M + k], s0);
+    }
+    c[k] = GRAD ? s0 + s1 : s0;
   }
 #pragma unroll
   for (int k = 0; k < M; ++k) {
@@ -44,15 +49,17 @@ __device__ __forceinline__ void state_epilogue(const VhjbArgs& a, const float* g
     }
     du[k] = u[k] - a.uf[k];
   }
-  float xdot[N], vdot = 0.f;
+  float xdot[N], vdot0 = 0.f, vdot1 = 0.f;
 #pragma unroll
   for (int i = 0; i < N; ++i) {
     float s = f[i];
 #pragma unroll
     for (int k = 0; k < M; ++k) s = fmaf(G[i * M + k], u[k], s);
     xdot[i] = s;
-    vdot = fmaf(p[i], s, vdot);
+    if (GRAD && (i & 1)) vdot1 = fmaf(p[i], s, vdot1);
+    else vdot0 = fmaf(p[i], s, vdot0);
   }
+  const float vdot = GRAD ? vdot0 + vdot1 : vdot0;
   float r;
 #pragma unroll
   for (int i = 0; i < N; ++i) pbar[i] = 0.f;
@@ -69,7 +76,10 @@ __device__ __forceinline__ void state_epilogue(const VhjbArgs& a, const float* g
     const float den = l + a.eps;
     const float iden = 1.0f / den;
     r = fmaf(vdot, iden, 1.f);
-    const float tq = V / (cost + a.eps) - 1.f;
+    // 1 / (cost + eps) depends on the input alone: the gradient kernel computes it a phase ahead (icost_pre), off the
+    // critical path of the epilogue (three IEEE divisions were a third of its samples)
+    const float icost = icost_pre > 0.f ? icost_pre : 1.0f / (cost + a.eps);
+    const float tq = fmaf(V, icost, -1.f);
     if (valid) {
       hjb_sum += fabsf(r) * (1.f - done);
       term_sum += fabsf(tq) * done;
@@ -97,7 +107,7 @@ __device__ __forceinline__ void state_epilogue(const VhjbArgs& a, const float* g
 #pragma unroll
         for (int i = 0; i < N; ++i) pbar[i] = fmaf(G[i * M + jj], s, pbar[i]);
       }
-      Vbar = valid ? a.reg * done * inv_norm1 * sign0(tq) / (cost + a.eps) : 0.f;
+      Vbar = valid ? a.reg * done * inv_norm1 * sign0(tq) * icost : 0.f;
     }
   } else {
     r = vdot + cost;

@@ -323,7 +323,7 @@ __global__ void __launch_bounds__(kThreads, 1) vhjb_tc_kernel(const __grid_const
   // the passes hidden under a GEMM (9b, 10b) arrive on their own barrier: a warp reaches them without waiting for
   // the other warps' previous arrival, and two arrivals of one warp must never count towards the same phase
   uint64_t* bar_passb = bar_pass + 5;
-  // early hand-over of a pass's hi pieces (split steps 1, 2, 4, 5, 7, 8, 10a): the issuer starts the two products that
+  // early hand-over of a pass's hi pieces (split steps 1, 2, 3, 4, 5, 7, 8, 10a): the issuer starts the two products that
   // need hi alone while the pass computes the lo pieces
   uint64_t* bar_passh = bar_pass + 6;
   uint32_t* tptr = reinterpret_cast<uint32_t*>(smem + kMisc + 568);
@@ -452,7 +452,8 @@ __global__ void __launch_bounds__(kThreads, 1) vhjb_tc_kernel(const __grid_const
       HJB_TC_GROUP2((gemm3_early<8, F1_mn, W3_mn, idY_mn_mn, cY, false>(tm, sb)),
                     (gemm3_late<8, F1_mn, W3_mn, idY_mn_mn, cY, false>(tm, sb), mma_commit(bar_mma)));
       // G3: b2^T = W3 gy^T
-      HJB_TC_GROUP(gemm3<4, W3_k, Y0_k, idN64_k_k, cB2>(tm, sb, 0u); mma_commit(bar_mma));
+      HJB_TC_GROUP2((gemm3_early<4, W3_k, Y0_k, idN64_k_k, cB2, true>(tm, sb)),
+                    (gemm3_late<4, W3_k, Y0_k, idN64_k_k, cB2, true>(tm, sb), mma_commit(bar_mma)));
       // G4: b1^T = W2 g2^T
       HJB_TC_GROUP2((gemm3_early<8, W2_k, F0_mn, idN64_k_mn, cWk, true>(tm, sb)),
                     (gemm3_late<8, W2_k, F0_mn, idN64_k_mn, cWk, true>(tm, sb), mma_commit(bar_mma)));
@@ -674,7 +675,7 @@ __global__ void __launch_bounds__(kThreads, 1) vhjb_tc_kernel(const __grid_const
 
     float xraw[N], z[N];
     float fdyn[N], Gdyn[N * M];            // f(x), g(x) of the state this thread owns (epilogue warps)
-    float lz = 0.f, zz = 0.f, done = 0.f, cost = 1.f;
+    float lz = 0.f, zz = 0.f, done = 0.f, cost = 1.f, icost = 0.f, hmax_in = 0.f;
     float xnext[N], dnext = 0.f, cnext = 1.f;   // epilogue warps: the next tile's inputs, loads issued one tile ahead
     bool vnext = false;
     float Vsum = 0.f, Vbar = 0.f, gymax = 0.f, fscale = 0.f;
@@ -833,6 +834,10 @@ __global__ void __launch_bounds__(kThreads, 1) vhjb_tc_kernel(const __grid_const
         S::fg(a.sys, zi, tr, fdyn, Gdyn);
         zz = 0.f;
         lz = 0.f;
+        icost = 1.0f / (cost + a.eps);                 // (for the epilogue: off its critical path)
+        hmax_in = 0.f;                                 // max |h0| of the state (the deferral test of step 6)
+#pragma unroll
+        for (int i = 0; i < N; ++i) hmax_in = fmaxf(hmax_in, fabsf((z[i] - a.mean[i]) * a.inv_std[i]));
 #pragma unroll
         for (int i = 0; i < N; ++i) {
           zz = fmaf(z[i], z[i], zz);
@@ -864,6 +869,7 @@ __global__ void __launch_bounds__(kThreads, 1) vhjb_tc_kernel(const __grid_const
         tmem_ld32(tl + cY + sc0, yv);
         tc_wait_ld();
         float v = 0.f, ym = 0.f;
+        uint4 hi[4];
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
           float o[8];
@@ -872,9 +878,18 @@ __global__ void __launch_bounds__(kThreads, 1) vhjb_tc_kernel(const __grid_const
             const float y = __uint_as_float(yv[8 * g + t]) * iws;
             v = fmaf(y, y, v);
             o[t] = 2.f * y;
+            yv[8 * g + t] = __float_as_uint(o[t]);
             ym = fmaxf(ym, fabsf(o[t]));
           }
-          if (sact) store8<FMT>(smem, kY0, kYPiece, kRbY, sj, sc0 + 8 * g, o);
+          if (sact) hi[g] = store8_hi<FMT>(smem, kY0, kRbY, sj, sc0 + 8 * g, o);
+        }
+        pass_half();                                            // -> the two products of G3 that need gy's hi piece only
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          float o[8];
+#pragma unroll
+          for (int t = 0; t < 8; ++t) o[t] = __uint_as_float(yv[8 * g + t]);
+          if (sact) store8_lo<FMT>(smem, kY0, kYPiece, kRbY, sj, sc0 + 8 * g, o, hi[g]);
         }
         if (hh == 1 && sact) { sV[sj] = v; sYm[sj] = ym; }
         asm volatile("bar.sync 1, 256;" ::: "memory");          // column halves of every quarter meet
@@ -926,7 +941,7 @@ __global__ void __launch_bounds__(kThreads, 1) vhjb_tc_kernel(const __grid_const
         // (the state's loss terms are added below: a deferred state's terms come from the fp32 pass, like its gradient)
         float hjb_s = 0.f, term_s = 0.f;
         state_epilogue<S, UFORM, RFORM, GRAD>(a, g0v, Vsum, z, zz, lz, fdyn, Gdyn, done, cost, valid, idx, inv_norm0, inv_norm1,
-                                              hjb_s, term_s, pbar, Vbar);
+                                              hjb_s, term_s, pbar, Vbar, icost);
         if constexpr (!GRAD) { hjb_sum += hjb_s; term_sum += term_s; }
         if constexpr (GRAD) {
           float gb[16];
@@ -947,9 +962,7 @@ __global__ void __launch_bounds__(kThreads, 1) vhjb_tc_kernel(const __grid_const
           // ... and so does a state whose INPUT is tiny: below 2^-3 the lo piece of an fp16 split is subnormal (absolute
           // resolution 3e-8), so activations of order |h0| < 2^-10 are good to 3e-5 relative at best — irrelevant for V
           // and u (absolute errors), but the normalised residual v-dot / (l + eps) + 1 and its adjoints are scale-free.
-          float hmax = 0.f;
-#pragma unroll
-          for (int i = 0; i < N; ++i) hmax = fmaxf(hmax, fabsf((z[i] - a.mean[i]) * a.inv_std[i]));
+          const float hmax = hmax_in;
           const bool in_range = eb > 8 && eb < 226;
           const int ks = eb - 126, ts = ks - expE;
           bool defer = sact && valid && ((in_range && ts > kSeedCap) || hmax < 9.765625e-4f);
@@ -961,7 +974,7 @@ __global__ void __launch_bounds__(kThreads, 1) vhjb_tc_kernel(const __grid_const
             else { defer = false; sat_count += 1.f; }
           }
           if (!defer) { hjb_sum += hjb_s; term_sum += term_s; }
-          float lam = 0.f, fs = 0.f;
+            float lam = 0.f, fs = 0.f;
           if (in_range) {
             const int as = max(-24, min(kSeedCap, ts));
             lam = defer ? 0.f : __uint_as_float((uint32_t)(as - ks + 127) << 23);   // 2^(a_s - k_s), exponent in [19, 252]
