@@ -822,6 +822,8 @@ def measure_vhjb(w, steps, warmup, rank, world, local, want_cpu, extras=False, v
     train_ms = timed(train, steps)
     clk = clocks.stop(wall0, time.time())
     res_ms = timed(residual_only, steps)
+    for _ in range(2):           # (first call: the three reduction kernels of this entry point are loaded lazily)
+        grad_kernel_only()
     grad_ms = timed(grad_kernel_only, steps)
     for _ in range(2):
         e2e()
