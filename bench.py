@@ -412,7 +412,7 @@ def measure_rollout(wname, integ, envs, T, record_stride, steps, warmup, rank, w
     collective on the data path), the kernel's mean launch time on this rank, its roofline.  Used for the secondary lines."""
     import torch
     import torch.distributed as dist
-    from tests.helpers import make_controller, make_dynamics
+    from q_learning_with_hjb_b200.workloads import make_controller, make_dynamics
     from q_learning_with_hjb_b200.rollout import BatchedRollout, RunningCost
     w = ROLLOUTS[wname]
     dyn = make_dynamics(w["sys"])
@@ -469,7 +469,7 @@ def verify_rollout_sharding(rank, world):
     stream keyed by one seed); rank 0 then integrates the whole batch alone and compares bit for bit."""
     import torch
     import torch.distributed as dist
-    from tests.helpers import make_controller, make_dynamics
+    from q_learning_with_hjb_b200.workloads import make_controller, make_dynamics
     from q_learning_with_hjb_b200 import parallel
     N, T = 1 << 18, 200
     dyn = make_dynamics("quad2d")
@@ -500,7 +500,7 @@ def run_rollout(args, w, integ):
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    from tests.helpers import make_controller, make_dynamics
+    from q_learning_with_hjb_b200.workloads import make_controller, make_dynamics
     from q_learning_with_hjb_b200.rollout import BatchedRollout, RunningCost
 
     envs = args.envs or w["envs"]
@@ -711,17 +711,16 @@ def verify_vhjb_sharding(rank, world):
     weights up to the order of the fp32 partial sums."""
     import torch
     import torch.distributed as dist
-    from oracle import vhjb_oracle as V          # weight init + synthetic batch only
-    from tests.helpers_vhjb import flat_params, make_kernels, sample_batch
     from q_learning_with_hjb_b200 import parallel
+    from q_learning_with_hjb_b200 import workloads as WL
     from q_learning_with_hjb_b200.controller.vhjb import AdamState
     B = 64 * 148 * 8 + 1000                      # ragged: shard sizes differ
-    xs, dones, costs = (torch.as_tensor(a).cuda() for a in sample_batch("quad10d", B, seed=77))
+    xs, dones, costs = (torch.as_tensor(a).cuda() for a in WL.sample_vhjb_batch("quad10d", B, seed=77))
     lo, hi = parallel.shard_bounds(B, rank, world)
-    W0 = torch.as_tensor(flat_params(V.init_weights(10, seed=3))).cuda()
+    W0 = torch.as_tensor(WL.flat_params(WL.init_weights(10, seed=3))).cuda()
 
     def run(local_only):
-        k, _ = make_kernels("quad10d")
+        k, _ = WL.make_vhjb_kernels("quad10d")
         w = W0.clone()
         opt = AdamState(0, torch.zeros_like(w), torch.zeros_like(w))
         sl = slice(0, B) if local_only else slice(lo, hi)
@@ -753,17 +752,16 @@ def measure_vhjb(w, steps, warmup, rank, world, local, want_cpu, extras=False, v
     the secondary measurement attached to the default line."""
     import torch
     import torch.distributed as dist
-    from oracle import vhjb_oracle as V          # weights init + synthetic batch only (not on the timed path)
-    from tests.helpers_vhjb import flat_params, make_kernels, sample_batch
+    from q_learning_with_hjb_b200 import workloads as WL       # (product-side: nothing of oracle/ or tests/ on this arm)
     from q_learning_with_hjb_b200.controller.vhjb import AdamState
 
     B = w["states"]
-    k, p = make_kernels(w["problem"])
-    n = p.sys.n
-    W = V.init_weights(n, seed=0)
-    params = torch.as_tensor(flat_params(W)).cuda()
+    k, p = WL.make_vhjb_kernels(w["problem"])
+    n = len(p.xf)
+    W = WL.init_weights(n, seed=0)
+    params = torch.as_tensor(WL.flat_params(W)).cuda()
     opt = AdamState(0, torch.zeros_like(params), torch.zeros_like(params))
-    xs, dones, costs = sample_batch(w["problem"], B, seed=1234 + rank)
+    xs, dones, costs = WL.sample_vhjb_batch(w["problem"], B, seed=1234 + rank)
     host = [torch.as_tensor(a).pin_memory() for a in (xs, dones, costs)]
     dev = [h.cuda() for h in host]
     out_host = torch.empty(4, dtype=torch.float32).pin_memory()

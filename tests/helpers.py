@@ -17,60 +17,18 @@ SCALES = {"linear": [2, 2], "cartpole": [3, 4, 3, 5], "acrobot": [4, 4, 6, 6], "
 
 
 def make_dynamics(kind):
-    from q_learning_with_hjb_b200.configs import gin_compat as gin
-    from q_learning_with_hjb_b200.configs.dynamics import dynamics_config as DC
-    cfg = os.path.join(PKG, "configs", "dynamics")
-    if kind == "linear":
-        from q_learning_with_hjb_b200.dynamics.linear import LinearDynamics
-        gin.parse_config_file(os.path.join(cfg, "linear.gin"))
-        return LinearDynamics(DC.LinearDynamicsConfig())
-    if kind == "cartpole":
-        from q_learning_with_hjb_b200.dynamics.cartpole import Cartpole
-        gin.parse_config_file(os.path.join(cfg, "cartpole.gin"))
-        return Cartpole(DC.CartpoleDynamicsConfig())
-    if kind == "acrobot":
-        from q_learning_with_hjb_b200.dynamics.acrobot import Acrobot
-        return Acrobot()
-    if kind == "quad2d":
-        from q_learning_with_hjb_b200.dynamics.quadrotors import Quadrotors2D
-        gin.parse_config_file(os.path.join(cfg, "quadrotors2D.gin"))
-        return Quadrotors2D(DC.Quadrotors2DConfig())
-    if kind == "quad10d":
-        from q_learning_with_hjb_b200.dynamics.quadrotors import NearHoverQuadcopter
-        gin.parse_config_file(os.path.join(cfg, "near_hover_quadcopter.gin"))
-        return NearHoverQuadcopter(DC.NearHoverQuadcopterConfig())
-    raise ValueError(kind)
+    """The package's Dynamics object of a kind (q_learning_with_hjb_b200/workloads.py: one definition for tests and bench)."""
+    from q_learning_with_hjb_b200 import workloads
+    return workloads.make_dynamics(kind)
 
 
 def make_controller(kind, dyn):
-    if kind == "lqr":
-        from q_learning_with_hjb_b200.controller.lqr import LQR
-        return LQR(dyn, np.eye(2), np.eye(1))
-    if kind == "cartpole_lqr":   # the notebook's inline LQR about xf = [0, 3.1415926, 0, 0], unclipped
-        from q_learning_with_hjb_b200.controller.lqr import StateFeedback
-        from q_learning_with_hjb_b200.controller.controller_basic import lqr_gain
-        xf = np.array([0, 3.1415926, 0, 0])
-        Minv = np.linalg.inv(dyn.get_M(xf))
-        A = np.zeros((4, 4)); A[0, 2] = A[1, 3] = 1
-        A[2:, :2] = -Minv @ np.array([[0, 0], [0, -dyn.mp * dyn.g * dyn.l]])
-        B = np.concatenate([np.zeros(2), Minv @ dyn.get_B()]).reshape(4, 1)
-        K, _ = lqr_gain(A, B, np.eye(4), np.eye(1))
-        return StateFeedback(dyn, K, xf=xf, uf=np.zeros(1), clip=False)
-    if kind == "cartpole_es":
-        from q_learning_with_hjb_b200.controller.cartpole_energy_shaping import CartpoleEnergyShapingController
-        return CartpoleEnergyShapingController(dyn)
-    if kind == "acrobot_es":
-        from q_learning_with_hjb_b200.controller.acrobot_energy_shaping import AcrobotEnergyShapingController
-        return AcrobotEnergyShapingController(dyn)
-    from q_learning_with_hjb_b200.controller import quadrotors_model_based_controller as QC
-    if kind == "quad2d_hover":
-        return QC.Quadrotors2DHoveringController(dyn, np.zeros(6), np.eye(6), np.eye(2))
-    if kind == "quad10d_hover":
-        return QC.NearHoverQuadcopterHoveringController(dyn, np.zeros(10), np.eye(10), np.eye(3))
+    from q_learning_with_hjb_b200 import workloads
     if kind == "quad2d_track":
+        from q_learning_with_hjb_b200.controller import quadrotors_model_based_controller as QC
         planner = QC.Quadrotors2DWaypointsPlanner(O.TRACK_WAYPOINTS, dyn, avg_speed=O.TRACK_SPEED)
         return QC.Quadrotors2DTrackingController(dyn, planner, np.eye(6), np.eye(2))
-    raise ValueError(kind)
+    return workloads.make_controller(kind, dyn)
 
 
 def oracle_pair(skind, ckind):

@@ -212,3 +212,24 @@ def test_kernel_source_hash_is_independent_of_the_checkout_directory(tmp_path):
             shutil.copy(os.path.join(build.CSRC, f), d / f)
     assert build._digest([str(a / f) for f in names]) == build._digest([str(b / f) for f in names])
     assert build._digest([str(a / f) for f in names])[:16] == build.source_hash("rollout")
+
+
+def test_bench_workloads_are_the_problems_the_tests_check():
+    """bench.py builds what it times from q_learning_with_hjb_b200/workloads.py (nothing of oracle/ or tests/ on the measured
+    arm); the parity tests build the same problems from the oracle's descriptions (tests/helpers_vhjb.py).  Same goal, same
+    forms, the same random weights and the same synthetic batch, bit for bit."""
+    from oracle import vhjb_oracle as V
+    from q_learning_with_hjb_b200 import workloads as WL
+    from tests import helpers_vhjb as H
+    forms = {"clip": "clipped", "bang": "bangbang"}
+    for name in ("linear", "cartpole", "quad2d", "quad10d", "di_mintime"):
+        w, p = WL.vhjb_workload(name), H.problem(name)
+        assert np.array_equal(w.xf, p.xf) and np.allclose(w.uf, p.uf, rtol=1e-15, atol=0) and w.act == p.act
+        assert w.control_form == forms[p.control_form] and w.residual_form == p.residual_form
+        assert w.eps == p.eps and w.eps_s == p.eps_s
+        assert np.array_equal(p.Q, np.eye(p.sys.n)) and np.array_equal(p.R, np.eye(p.sys.m))
+        for a, b in zip(WL.sample_vhjb_batch(name, 777, seed=5), H.sample_batch(name, 777, seed=5)):
+            assert a.dtype == np.float32 and np.array_equal(a, b)
+        for a, b in zip(WL.init_weights(p.sys.n, seed=3), V.init_weights(p.sys.n, seed=3)):
+            assert a.dtype == np.float32 and np.array_equal(a, b.astype(np.float32))     # (the oracle keeps float64)
+    assert np.array_equal(WL.flat_params(WL.init_weights(2)), H.flat_params(V.init_weights(2)))
