@@ -14,6 +14,10 @@ reference loop (``u = ctl.get_control_efforts(x); x = dyn.simulate(x, u)``, scri
 travelling copy under baseline/_ref (tools/install_reference_baseline.py; /root/reference in the build container), one
 process per core on a bounded sample — ``cpu_baseline.kind = "reference"``.  The vectorised NumPy port
 (oracle/rollout_oracle.py, fp64 and fp32) is reported beside it; it is the fallback when no reference copy is present.
+
+What this file takes from ``oracle/`` (test infrastructure): the CHECKER of the untimed ``parity`` block, the ``cpu_baseline``
+legs and the reference arm.  Everything on the measured arm — dynamics, controllers, value-net weights, synthetic batches,
+initial states — comes from the package (``q_learning_with_hjb_b200/workloads.py``, ``hjb_sample_states``).
 """
 from __future__ import annotations
 
