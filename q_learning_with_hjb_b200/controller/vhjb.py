@@ -706,10 +706,10 @@ class VHJBController(Controller):
                 avg_hjb.append(float(hjbs) / n_batches)
                 avg_term.append(float(terms) / n_batches)
             # Range check of the tensor-core gradient pass, once per epoch (one host read).  States whose adjoint seeds lie
-            # beyond the fp16 range management take the fp32 pass behind the tensor kernel in every update (exact, no
-            # switch of kernels); what can still be counted here is an adjoint CHAIN that outgrew fp16 (a backward gain
-            # above ~1000 — not met in any reference configuration): clipped and counted, never silent, and from then on the
-            # fp32 CUDA-core kernels take over.
+            # beyond the fp16 range management take the fp32 pass behind the tensor kernel in every update, and a launch
+            # whose adjoint CHAIN outgrew fp16 (a backward gain above ~1000) is redone as a whole by that pass — both exact
+            # and decided on the device, so this count is 0 by construction; the poll stays as a safety net (a non-zero
+            # count would mean the library met something it neither computed in range, nor deferred, nor redid).
             if n_batches and self.kernels.impl == "tensor" and self.kernels.saturated_total() > 0:
                 self.kernels.impl = "simt"
                 print(f"epoch:{epoch + 1}, adjoint range check tripped: continuing with the fp32 CUDA-core kernels")
