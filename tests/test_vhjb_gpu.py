@@ -693,3 +693,21 @@ def test_train_loop_loss_accumulator_matches_params_update():
     assert ca == cb and ca > 0 and torch.equal(wa, wb)
     for a, b in zip(la, lb):
         np.testing.assert_allclose(a, b, rtol=2e-6, atol=1e-9)
+
+
+@pytest.mark.parametrize("name", ["quad10d", "di_mintime", "cartpole"])
+def test_bench_workload_kernels_are_the_tested_kernels(name):
+    """bench.py builds the kernels it times from q_learning_with_hjb_b200/workloads.py; the parity tests above build them
+    from the oracle's problem descriptions (tests/helpers_vhjb.py).  Same task structure, the same bits out."""
+    import torch
+    from q_learning_with_hjb_b200 import workloads as WL
+    k1, w = WL.make_vhjb_kernels(name)
+    k2, p = make_kernels(name)
+    params = torch.as_tensor(WL.flat_params(WL.init_weights(len(w.xf), seed=2))).cuda()
+    xd, dd, cd = (torch.as_tensor(a).cuda() for a in WL.sample_vhjb_batch(name, 4096, seed=9))
+    outs = []
+    for k in (k1, k2):
+        k.counts(dd, w.eps)
+        g, s = k.loss_grad(params, xd, dd, cd, 0.5)
+        outs.append((g.clone(), s.clone()))
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
