@@ -322,7 +322,8 @@ int hjb_vhjb_train_step(const hjb_system* sys, const hjb_vnet* net, const hjb_ta
  * counts_out — pass that buffer as `norm` of the next call (alternate two buffers).  peer_bufs / peer_flags:
  * device arrays [world] of pointers to every rank's exchange buffer (hjb_vhjb_peer_exchange_floats floats) and flag array
  * (hjb_vhjb_peer_exchange_flags uint32, zeroed once before the first step) in peer-accessible memory (e.g. torch symmetric
- * memory); step = 1, 2, ... identical on all ranks.  A wait that gives up (~2 s) raises hjb_vhjb_stream_failures' word,
+ * memory); step = 1, 2, ... identical on all ranks; world = 1 is accepted (the rank exchanges with itself: bit-identical
+ * to hjb_vhjb_train_step).  A wait that gives up (~2 s) raises hjb_vhjb_stream_failures' word,
  * turns the loss sums into NaN and skips the update.
  */
 int64_t hjb_vhjb_peer_exchange_floats(int32_t n, int32_t world);

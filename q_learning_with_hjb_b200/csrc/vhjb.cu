@@ -666,7 +666,7 @@ int hjb_vhjb_train_step_peer(const hjb_system* sys, const hjb_vnet* net, const h
                              int32_t rank, int32_t world, void* workspace, void* stream) {
   if (!sys || !net || !task || !net->params || !m || !v || !norm || !grad || !sums || !workspace || B < 0 || step < 1)
     return HJB_ERR_BAD_ARG;
-  if (!peer_bufs || !peer_flags || world < 2 || world > 64 || rank < 0 || rank >= world) return HJB_ERR_BAD_ARG;
+  if (!peer_bufs || !peer_flags || world < 1 || world > 64 || rank < 0 || rank >= world) return HJB_ERR_BAD_ARG;
   if (B > 0 && (!xs || !dones || !costs)) return HJB_ERR_BAD_ARG;
   PeerExchange x;
   x.bufs = reinterpret_cast<float* const*>(peer_bufs);

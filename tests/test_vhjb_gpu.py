@@ -711,3 +711,52 @@ def test_bench_workload_kernels_are_the_tested_kernels(name):
         g, s = k.loss_grad(params, xd, dd, cd, 0.5)
         outs.append((g.clone(), s.clone()))
     assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+
+
+def test_peer_exchange_step_with_one_rank_equals_the_plain_step():
+    """hjb_vhjb_train_step_peer (reduce -> exchange over peer memory -> Adam in one kernel; the N-GPU path, verified against
+    the single-GPU run at N = 2, 4, 8 by bench.py's `verify` block) driven here with world = 1: the rank stores into its own
+    exchange buffer, raises and awaits its own flag, sums one slot and updates — three steps must leave the same bits in
+    the weights, the Adam moments and the loss sums as hjb_vhjb_train_step, and return the next batch's normalisers."""
+    import torch
+    from q_learning_with_hjb_b200 import _lib as L
+    from q_learning_with_hjb_b200.controller.vhjb import AdamState
+    B = 20000
+    name = "quad10d"
+    ka, p = make_kernels(name)
+    kb, _ = make_kernels(name)
+    xs, dones, costs = (torch.as_tensor(a).cuda() for a in sample_batch(name, B, seed=3))
+    W0 = torch.as_tensor(flat_params(V.init_weights(p.sys.n, seed=1))).cuda()
+    # plain single-process steps
+    wa = W0.clone()
+    oa = AdamState(0, torch.zeros_like(wa), torch.zeros_like(wa))
+    sums_a = []
+    for _ in range(3):
+        s, _n = ka.train_step(wa, oa, xs, dones, costs, 0.25, 1e-3, local=True)
+        sums_a.append(s.clone())
+    # the peer entry point, world = 1
+    lib = L.lib()
+    nf, ng = int(lib.hjb_vhjb_peer_exchange_floats(p.sys.n, 1)), int(lib.hjb_vhjb_peer_exchange_flags(p.sys.n, 1))
+    buf = torch.zeros(nf, device="cuda", dtype=torch.float32)
+    flg = torch.zeros(ng, device="cuda", dtype=torch.int32)
+    bufs = torch.tensor([buf.data_ptr()], dtype=torch.int64, device="cuda")
+    flags = torch.tensor([flg.data_ptr()], dtype=torch.int64, device="cuda")
+    wb = W0.clone()
+    ob = AdamState(0, torch.zeros_like(wb), torch.zeros_like(wb))
+    kb.counts(dones, p.eps)                                   # this batch's normalisers (one rank: local = global)
+    norm = [kb.norm.clone(), torch.zeros(2, device="cuda")]
+    local_next = torch.zeros(2, device="cuda")
+    loss_acc = torch.zeros(3, device="cuda")
+    for i in range(3):
+        L.check(lib.hjb_vhjb_count(L.ptr(dones), B, 0.0, L.ptr(local_next), L.ptr(kb.workspace), L.stream_ptr()), "count")
+        kb._bind(wb)
+        ob.count += 1
+        L.check(lib.hjb_vhjb_train_step_peer(kb.sys_spec, kb.net, kb.task, L.ptr(xs), L.ptr(dones), L.ptr(costs), B, 0.25, 1e-3,
+                                             0.9, 0.999, 1e-8, int(ob.count), L.ptr(ob.mu), L.ptr(ob.nu), L.ptr(norm[i & 1]),
+                                             L.ptr(kb.grad), L.ptr(kb.sums), L.ptr(loss_acc), L.ptr(local_next),
+                                             L.ptr(norm[(i + 1) & 1]), L.ptr(bufs), L.ptr(flags), 0, 1, L.ptr(kb.workspace),
+                                             L.stream_ptr()), "hjb_vhjb_train_step_peer")
+        assert torch.equal(kb.sums[:2], sums_a[i][:2]), i
+        assert torch.equal(norm[(i + 1) & 1], norm[i & 1])     # same batch again: the delivered normalisers are this step's
+    assert torch.equal(wa, wb) and torch.equal(oa.mu, ob.mu) and torch.equal(oa.nu, ob.nu)
+    assert kb.stream_failures() == 0 and not torch.equal(wb, W0)
