@@ -20,6 +20,9 @@ NVCC_FLAGS = [
     "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC",
     "--expt-relaxed-constexpr",
+    # the fatbin (SASS + the line tables and PTX text -lineinfo attaches, which were more than half of every object) is stored
+    # zstd-compressed and inflated by the driver at load (CUDA >= 12.8): libhjb_b200.so 120 MB -> ~15 MB, same SASS
+    "--compress-mode=size",
 ]
 
 
@@ -96,7 +99,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
                 if verbose and out:
                     print(out)
     if jobs or not os.path.exists(LIB_PATH):
-        cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB_PATH, *objs]
+        cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "--compress-mode=size", "-o", LIB_PATH, *objs]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
