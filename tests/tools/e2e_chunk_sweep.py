@@ -1,7 +1,7 @@
 """Developer tool: end-to-end time of VhjbKernels.train_step_host and BatchedRollout.run_host against the number of
 pipeline pieces (run on a GPU box)."""
 import os, sys, time
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np
 import torch
 from oracle import vhjb_oracle as V
