@@ -81,7 +81,17 @@ typedef enum hjb_control_kind {
    * Quadrotors2DWaypointsPlanner.update(t) returns (:77-233; minimum snap + differential flatness).  The reference is a
    * device table ref[ref_steps][n + m] (row t: x_ref, then u_ref, at time t * dt; rows past the end repeat the last:
    * hover at the final way-point), the same for every environment — planned once per horizon, not once per step.      */
-  HJB_CTL_TRACK = 3
+  HJB_CTL_TRACK = 3,
+  /* The double integrator's time-optimal bang-bang law, examples/double_integrator_optimal_time.ipynb cell 18
+   * (get_analytical_control): x = [pos, vel]; u = 0 inside x^T x <= aux[0]; u = +aux[1] when (vel < 0 and
+   * pos <= vel^2 / 2) or (vel >= 0 and pos < -vel^2 / 2); else u = -aux[1].  n = 2, m = 1.                            */
+  HJB_CTL_SWITCH_CURVE = 4,
+  /* Bang-bang policy read from a value function on a regular grid (the notebook's comparison with a level-set solver,
+   * cell 18: get_level_set_control): u = -aux[4] sign(T[iv][ip]) with T = dV/dvel as a device table ref[ref_steps = nv]
+   * [ref_offset = np] and (iv, ip) the NEAREST grid node of (vel, pos) — node = ceil(t - 1/2) of the fractional index
+   * t = (x - min) / step, clamped to the grid: scipy's RegularGridInterpolator(method="nearest", bounds_error=False,
+   * fill_value=None).  aux = {pos_min, 1 / pos_step, vel_min, 1 / vel_step, amplitude}.  n = 2, m = 1.               */
+  HJB_CTL_GRID_SIGN = 5
 } hjb_control_kind;
 
 typedef struct hjb_control {
@@ -91,9 +101,10 @@ typedef struct hjb_control {
   float P[16];                    /* ACROBOT_ES: 4 x 4 row-major */
   float xf[HJB_MAX_N], uf[HJB_MAX_M];
   float aux[8];
-  const float* ref;   /* TRACK: device pointer, [ref_steps][n + m] row-major; else unused (null)        */
-  int32_t ref_steps;  /* TRACK: rows of ref                                                              */
-  int32_t ref_offset; /* TRACK: step 0 of the call is row ref_offset (per-step calls at a given time)   */
+  const float* ref;   /* TRACK: device pointer, [ref_steps][n + m] row-major; GRID_SIGN: the table; else null */
+  int32_t ref_steps;  /* TRACK: rows of ref; GRID_SIGN: rows (vel nodes)                                  */
+  int32_t ref_offset; /* TRACK: step 0 of the call is row ref_offset (per-step calls at a given time);
+                         GRID_SIGN: columns (pos nodes)                                                    */
 } hjb_control;
 
 /* ---- running cost l(x,u) = dx^T Q dx + (u-uf)^T R (u-uf), dx = wrap(x - xf) -----------------------
@@ -165,6 +176,15 @@ int hjb_control_efforts(const hjb_system* sys, const hjb_control* ctl, int32_t f
 
 /* Batched Dynamics.states_wrap (cartpole.py:52-64, acrobot.py:72-81, quadrotors.py:48-70,151-170), in place. */
 int hjb_states_wrap(const hjb_system* sys, float* x, int64_t B, void* stream);
+
+/*
+ * Time to the goal ball of recorded trajectories — the bookkeeping of examples/double_integrator_optimal_time.ipynb
+ * cell 20 (`if x_{k+1}^T x_{k+1} <= metric: optimal_t = min(k dt, optimal_t)`, optimal_t starting at T) for every
+ * environment of a rollout: xs = hjb_rollout's time-major record with record_stride = 1 ([rows][N][n], row 0 = x0, so
+ * rows = steps + 1); t_hit [N] (device) = (first row r >= 1 inside the ball - 1) * dt, or t_max if there is none.
+ */
+int hjb_time_to_goal(const float* xs, int64_t N, int32_t n, int32_t rows, float metric, float dt, float t_max, float* t_hit,
+                     void* stream);
 
 /*
  * Counter-based sampling of states on the device: x[i] = wrap(U(-std, std) + mean), the distribution of

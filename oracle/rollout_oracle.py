@@ -182,6 +182,15 @@ class OracleSystem:
             k3 = self.xdot(x + 0.5 * dt * k2, u)
             k4 = self.xdot(x + dt * k3, u)
             xn = x + (dt / 6.0) * (k1 + 2 * k2 + 2 * k3 + k4)
+        elif integrator == "discrete":
+            # exact zero-order hold of a LINEAR system: examples/double_integrator_optimal_time.ipynb cell 4
+            # (``scipy.signal.cont2discrete`` once, then ``dynamics_step(x, u) = Ad x + Bd u``)
+            if self.kind != "linear":
+                raise ValueError("integrator='discrete' needs a linear system")
+            import scipy.signal
+            A, B = np.asarray(self.par["A"], dtype=np.float64), np.asarray(self.par["B"], dtype=np.float64)
+            Ad, Bd, *_ = scipy.signal.cont2discrete((A, B, np.eye(A.shape[0]), np.zeros((A.shape[0], B.shape[1]))), dt=dt)
+            xn = x @ Ad.T.astype(DT) + u @ Bd.T.astype(DT)
         else:
             raise ValueError(integrator)
         return self.wrap(xn)
@@ -202,6 +211,12 @@ class OracleController:
       track       u_t = clip(u_ref(t) - K wrap(x - x_ref(t))): the feedback law of
                   controller/quadrotors_model_based_controller.py:36-38 about what Quadrotors2DWaypointsPlanner.update(t)
                   returns (:77-233); ``planner`` is an OraclePlanner, ``dt`` the step of the time grid
+      switch_curve  examples/double_integrator_optimal_time.ipynb cell 18, ``get_analytical_control``: the double
+                  integrator's time-optimal bang-bang law (x = [pos, vel]; 0 inside x^T x <= metric)
+      grid_sign   same cell, ``get_level_set_control``: u = -sign(dV/dvel) read at the NEAREST node of a regular
+                  (vel, pos) grid — scipy's RegularGridInterpolator(method="nearest", bounds_error=False,
+                  fill_value=None), restated in closed form in ``nearest_node`` and pinned against scipy itself
+                  (tests/test_kat.py); ``grid`` = the table [nv, np], ``grid_axes`` = (pos nodes, vel nodes)
     """
     kind: str
     K: Optional[np.ndarray] = None        # (m, n) LQR gain
@@ -214,9 +229,24 @@ class OracleController:
     eps_state: float = 1.0
     eps: float = 1000.0
     planner: Optional["OraclePlanner"] = None
+    metric: float = 1e-4                  # switch_curve: radius^2 of the goal ball
+    amp: float = 1.0                      # switch_curve / grid_sign: |u|
+    grid: Optional[np.ndarray] = None     # grid_sign: dV/dvel on the grid, [nv, np]
+    grid_axes: Optional[Tuple[np.ndarray, np.ndarray]] = None
 
     def control(self, sys: OracleSystem, x: np.ndarray, t: float = 0.0) -> np.ndarray:
         x = np.asarray(x, dtype=DT)
+        if self.kind == "switch_curve":
+            p, v = x[:, 0], x[:, 1]
+            plus = ((v < 0) & (p <= 0.5 * v ** 2)) | ((v >= 0) & (p < -0.5 * v ** 2))
+            u = np.where(plus, self.amp, -self.amp)
+            return np.where(p * p + v * v <= self.metric, 0.0, u)[:, None].astype(DT)
+        if self.kind == "grid_sign":
+            pos_axis, vel_axis = self.grid_axes
+            g = np.asarray(self.grid)
+            ip = nearest_node(x[:, 0], pos_axis)
+            iv = nearest_node(x[:, 1], vel_axis)
+            return (-self.amp * np.sign(g[iv, ip]))[:, None].astype(DT)
         if self.kind == "track":
             x_ref, u_ref = self.planner.update(t)
             dx = sys.wrap(x - x_ref)
@@ -260,6 +290,19 @@ class OracleController:
             u = np.where((quad < self.eps)[:, None], u_lqr, u_sw[:, None])
             return np.clip(u, sys.umin, sys.umax)                         # :119
         raise ValueError(self.kind)
+
+
+def nearest_node(x, axis):
+    """Index of the node of ``axis`` (ascending) that scipy's ``RegularGridInterpolator(method="nearest",
+    bounds_error=False, fill_value=None)`` reads for coordinate ``x`` — its algorithm, restated: the cell is
+    i = searchsorted(axis, x) - 1 clamped to [0, n - 2], the normalised distance y = (x - axis[i]) / (axis[i+1] - axis[i])
+    (outside the axis y < 0 or y > 1: extrapolation), and the node is i when y <= 1/2, else i + 1.  On a regular axis this
+    is ceil(t - 1/2) of the fractional index t, clamped — the form the CUDA controller evaluates."""
+    axis = np.asarray(axis, dtype=np.float64)
+    x = np.asarray(x, dtype=np.float64)
+    i = np.clip(np.searchsorted(axis, x) - 1, 0, len(axis) - 2)
+    y = (x - axis[i]) / (axis[i + 1] - axis[i])
+    return np.where(y <= 0.5, i, i + 1).astype(np.int64)
 
 
 class OraclePlanner:
@@ -332,6 +375,8 @@ def control_scale(sys: OracleSystem, ctl: OracleController, x: np.ndarray) -> np
     an fp32 evaluation of the law can be expected to be accurate (cancellation between large terms is a property
     of the law, not of the implementation).  Used only to normalise errors in the parity tests."""
     x = np.asarray(x, dtype=DT)
+    if ctl.kind in ("switch_curve", "grid_sign"):
+        return np.full(len(x), ctl.amp, dtype=DT)
     K = np.abs(np.asarray(ctl.K, dtype=DT))
     if ctl.kind == "feedback":
         dx = np.abs(sys.wrap(x - ctl.xf))

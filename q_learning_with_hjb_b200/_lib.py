@@ -16,7 +16,7 @@ HJB_MAX_M = 3
 # hjb_system_kind
 SYS_LINEAR, SYS_CARTPOLE, SYS_ACROBOT, SYS_QUAD2D, SYS_QUAD10D = range(5)
 # hjb_control_kind
-CTL_FEEDBACK, CTL_CARTPOLE_ES, CTL_ACROBOT_ES, CTL_TRACK = range(4)
+CTL_FEEDBACK, CTL_CARTPOLE_ES, CTL_ACROBOT_ES, CTL_TRACK, CTL_SWITCH_CURVE, CTL_GRID_SIGN = range(6)
 # hjb_integrator
 INT_EULER, INT_RK4, INT_DISCRETE = range(3)
 INTEGRATORS = {"euler": INT_EULER, "rk4": INT_RK4, "discrete": INT_DISCRETE}
@@ -87,6 +87,7 @@ SYMBOLS = {
     "hjb_dynamics": (C.c_int, [C.POINTER(HjbSystem), C.c_int32, C.c_int32, _P, _P, C.c_int64, _P, _P, _P, _P, _P]),
     "hjb_control_efforts": (C.c_int, [C.POINTER(HjbSystem), C.POINTER(HjbControl), C.c_int32, _P, C.c_int64, _P, _P]),
     "hjb_states_wrap": (C.c_int, [C.POINTER(HjbSystem), _P, C.c_int64, _P]),
+    "hjb_time_to_goal": (C.c_int, [_P, C.c_int64, C.c_int32, C.c_int32, C.c_float, C.c_float, C.c_float, _P, _P]),
     "hjb_sample_states": (C.c_int, [C.c_int32, C.c_int32, C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_uint64, C.c_int64,
                                     C.c_int64, _P, _P]),
     "hjb_fma_peak_probe": (C.c_int, [_P, C.c_int64, C.c_int32, C.POINTER(C.c_double), _P]),

@@ -9,6 +9,7 @@
 #include <cstring>
 
 #include "rollout_kernel.cuh"
+#include "mintime_ctl.cuh"
 #include "step_kernels.cuh"
 
 namespace hjb {
@@ -121,7 +122,7 @@ static void make_dev_ctl(const hjb_system* s, const hjb_control* c, DevSys& ds, 
   std::memcpy(d.xf, c->xf, sizeof(d.xf));
   std::memcpy(d.uf, c->uf, sizeof(d.uf));
   std::memcpy(d.aux, c->aux, sizeof(d.aux));
-  d.ref = c->kind == HJB_CTL_TRACK ? c->ref : nullptr;
+  d.ref = (c->kind == HJB_CTL_TRACK || c->kind == HJB_CTL_GRID_SIGN) ? c->ref : nullptr;
   d.ref_steps = c->ref_steps;
   d.ref_offset = c->ref_offset;
   if (c->kind == HJB_CTL_CARTPOLE_ES) {
@@ -217,6 +218,7 @@ int hjb_rollout(const hjb_system* sys, const hjb_control* ctl, const hjb_cost* c
   if (!sys || !ctl || !opts || N < 0 || T < 0) return HJB_ERR_BAD_ARG;
   if (!dims_ok(sys)) return HJB_ERR_UNSUPPORTED;
   if (ctl->kind == HJB_CTL_TRACK && (!ctl->ref || ctl->ref_steps <= 0 || ctl->ref_offset < 0)) return HJB_ERR_BAD_ARG;
+  if (ctl->kind == HJB_CTL_GRID_SIGN && (!ctl->ref || ctl->ref_steps <= 0 || ctl->ref_offset <= 0)) return HJB_ERR_BAD_ARG;
   if (N == 0) return HJB_OK;
   if (!x0) return HJB_ERR_BAD_ARG;
   if (cost && !cost_spec) return HJB_ERR_BAD_ARG;
@@ -251,6 +253,11 @@ int hjb_rollout(const hjb_system* sys, const hjb_control* ctl, const hjb_cost* c
   cudaError_t e = cudaErrorNotSupported;
   switch (sys->kind) {
     case HJB_SYS_LINEAR:
+      if (ctl->kind == HJB_CTL_SWITCH_CURVE || ctl->kind == HJB_CTL_GRID_SIGN) {   // the double integrator's bang-bang laws
+        if (sys->n == 2 && sys->m == 1)
+          e = ctl->kind == HJB_CTL_SWITCH_CURVE ? rollout_linear21_switch(a, v, fast, st) : rollout_linear21_grid(a, v, fast, st);
+        break;
+      }
       if (ctl->kind != HJB_CTL_FEEDBACK) break;
       if (sys->n == 2 && sys->m == 1) e = rollout_linear21_fb(a, v, fast, st);
       else if (sys->n == 4 && sys->m == 1) e = rollout_linear41_fb(a, v, fast, st);
@@ -310,11 +317,20 @@ int hjb_control_efforts(const hjb_system* sys, const hjb_control* ctl, int32_t f
   if (B == 0) return HJB_OK;
   if (!x || !u) return HJB_ERR_BAD_ARG;
   if (ctl->kind == HJB_CTL_TRACK && (!ctl->ref || ctl->ref_steps <= 0 || ctl->ref_offset < 0)) return HJB_ERR_BAD_ARG;
+  if (ctl->kind == HJB_CTL_GRID_SIGN && (!ctl->ref || ctl->ref_steps <= 0 || ctl->ref_offset <= 0)) return HJB_ERR_BAD_ARG;
   CtlArgs a;
   make_dev_sys(sys, a.sys);
   make_dev_ctl(sys, ctl, a.sys, a.ctl);
   a.x = x; a.u = u; a.B = B;
   return to_status(step_control(sys->kind, ctl->kind, a, fast_trig != 0, (cudaStream_t)stream));
+}
+
+int hjb_time_to_goal(const float* xs, int64_t N, int32_t n, int32_t rows, float metric, float dt, float t_max, float* t_hit,
+                     void* stream) {
+  if (N < 0 || n <= 0 || n > HJB_MAX_N || rows < 1) return HJB_ERR_BAD_ARG;
+  if (N == 0) return HJB_OK;
+  if (!xs || !t_hit) return HJB_ERR_BAD_ARG;
+  return to_status(first_hit(xs, N, n, rows, metric, dt, t_max, t_hit, (cudaStream_t)stream));
 }
 
 int hjb_states_wrap(const hjb_system* sys, float* x, int64_t B, void* stream) {

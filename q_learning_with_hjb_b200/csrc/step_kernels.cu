@@ -3,6 +3,7 @@
 // (Dynamics.get_control_affine_matrix / dynamics_step / simulate, Controller.get_control_efforts) and for
 // the per-step parity tests.
 #include "rollout_kernel.cuh"
+#include "mintime_ctl.cuh"
 #include "step_kernels.cuh"
 
 namespace hjb {
@@ -127,6 +128,10 @@ cudaError_t step_control(int sys_kind, int ctl_kind, const CtlArgs& a, bool fast
   if (ctl_kind == HJB_CTL_ACROBOT_ES && sys_kind == HJB_SYS_ACROBOT)
     return launch_ctl_fast<AcrobotSys, AcrobotESCtl>(a, fast, st);
   if (ctl_kind == HJB_CTL_TRACK && sys_kind == HJB_SYS_QUAD2D) return launch_ctl_fast<Quad2DSys, TrackCtl>(a, fast, st);
+  if (sys_kind == HJB_SYS_LINEAR && a.sys.n == 2 && a.sys.m == 1) {
+    if (ctl_kind == HJB_CTL_SWITCH_CURVE) return launch_ctl_fast<Lin21, SwitchCurveCtl>(a, fast, st);
+    if (ctl_kind == HJB_CTL_GRID_SIGN) return launch_ctl_fast<Lin21, GridSignCtl>(a, fast, st);
+  }
   return cudaErrorNotSupported;
 }
 

@@ -233,3 +233,25 @@ def test_bench_workloads_are_the_problems_the_tests_check():
         for a, b in zip(WL.init_weights(p.sys.n, seed=3), V.init_weights(p.sys.n, seed=3)):
             assert a.dtype == np.float32 and np.array_equal(a, b.astype(np.float32))     # (the oracle keeps float64)
     assert np.array_equal(WL.flat_params(WL.init_weights(2)), H.flat_params(V.init_weights(2)))
+
+
+def test_min_time_controllers_host_side():
+    """controller/min_time.py without a device: argument checks, the notebook's central-difference table
+    (double_integrator_optimal_time.ipynb cell 18) and the switching-curve controller's parameter block."""
+    from q_learning_with_hjb_b200 import _lib as L
+    from q_learning_with_hjb_b200.controller.min_time import GridPolicyController, SwitchingCurveController
+    from tests.helpers import make_dynamics
+    dyn = make_dynamics("linear")
+    c = SwitchingCurveController(dyn, metric=1e-4, amplitude=1.0).control_spec()
+    assert c.kind == L.CTL_SWITCH_CURVE and c.aux[0] == np.float32(1e-4) and c.aux[1] == 1.0
+    with pytest.raises(ValueError):
+        SwitchingCurveController(make_dynamics("cartpole"))
+    pos, vel = np.linspace(-1, 1, 11), np.linspace(-2, 2, 21)
+    V = np.add.outer(vel ** 2, pos)                                            # dV/dvel = 2 vel
+    g = GridPolicyController.from_value_function(dyn, V, pos, vel)
+    assert g.table.shape == (19, 11) and np.allclose(g.table, 2 * vel[1:-1, None], atol=1e-6)
+    assert np.allclose(g.vel, vel[1:-1]) and np.allclose(g.pos, pos)
+    with pytest.raises(ValueError):
+        GridPolicyController(dyn, np.zeros((19, 11)), pos, vel)                 # axes / table mismatch
+    with pytest.raises(ValueError):
+        GridPolicyController(dyn, np.zeros((3, 3)), [0.0, 1.0, 3.0], [0.0, 1.0, 2.0])   # not equally spaced

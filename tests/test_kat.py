@@ -91,6 +91,73 @@ def test_kat_double_integrator_time_to_origin():
     assert abs(tl.mean() - 4.104) < 1e-12 and abs(tl.std() - 1.281602122345309) < 1e-12
 
 
+def _notebook_cell21_states():
+    """The ten initial states of double_integrator_optimal_time.ipynb cell 21 (NumPy's global stream as the notebook left it)."""
+    np.random.seed(0)
+    np.random.uniform(low=-1, high=1, size=(2 ** 16, 2))
+    for _ in range(6012):
+        np.random.uniform(low=-1, high=1, size=(2,))
+    return np.stack([np.random.uniform(low=-1, high=1, size=(2,)) for _ in range(10)])
+
+
+def _double_integrator():
+    return O.OracleSystem("linear", 2, 1, 0.01, np.array([-1.0]), np.array([1.0]),
+                          {"A": np.array([[0.0, 1.0], [0.0, 0.0]]), "B": np.array([[0.0], [1.0]])})
+
+
+def _level_set_fixture():
+    import os
+    d = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "double_integrator_level_set.npz"))
+    V, vel = d["value_level_set"], d["vel"]
+    return (V[2:, :] - V[:-2, :]) / (2 * float(d["dv"])), d["pos"], vel[1:-1], d
+
+
+def _oracle_time_to_origin(ctl, x0, T=500, dt=0.01, metric=1e-4):
+    xs, _, _, _ = O.rollout(_double_integrator(), ctl, x0, T, "discrete", record_stride=1)
+    hit = (xs[1:] ** 2).sum(-1) <= metric                     # the state AFTER step k
+    return np.where(hit.any(0), np.argmax(hit, 0) * dt, T * dt)
+
+
+def test_kat_double_integrator_level_set_and_analytic_policies_of_the_oracle():
+    # examples/double_integrator_optimal_time.ipynb cell 21 prints "mean level set 1.6170000000000002 / std level set
+    # 0.6021802055863344" and "mean analytical set 1.572 / std 0.5365407719828942": the oracle's grid_sign / switch_curve
+    # controllers and its exact-ZOH step reproduce both from the reference's own level-set data (tests/golden/
+    # double_integrator_level_set.npz, oracle/make_golden_level_set.py).
+    dVdvel, pos, vel, _ = _level_set_fixture()
+    x0 = _notebook_cell21_states()
+    tl = _oracle_time_to_origin(O.OracleController("grid_sign", grid=dVdvel, grid_axes=(pos, vel)), x0)
+    ta = _oracle_time_to_origin(O.OracleController("switch_curve"), x0)
+    assert abs(tl.mean() - 1.6170000000000002) < 1e-12 and abs(tl.std() - 0.6021802055863344) < 1e-12
+    assert abs(ta.mean() - 1.572) < 1e-12 and abs(ta.std() - 0.5365407719828942) < 1e-12
+
+
+def test_nearest_node_is_scipys_nearest_interpolation():
+    # the notebook's policy goes through scipy's RegularGridInterpolator(method="nearest", bounds_error=False,
+    # fill_value=None): the oracle's restatement must pick the same node everywhere, ties and extrapolation included
+    from scipy.interpolate import RegularGridInterpolator
+    rng = np.random.default_rng(0)
+    pos, vel = np.linspace(-1, 1, 101), np.linspace(-1, 1, 101)[1:-1]
+    T = rng.standard_normal((99, 101))
+    f = RegularGridInterpolator((vel, pos), T, method="nearest", bounds_error=False, fill_value=None)
+    x = rng.uniform(-1.3, 1.3, size=(100000, 2))
+    x[:1000, 0] = pos[rng.integers(0, 100, 1000)] + 0.01       # (near-)ties
+    x[1000:2000, 1] = vel[rng.integers(0, 98, 1000)] + 0.01
+    x[2000:3000, 0] = pos[rng.integers(0, 101, 1000)]          # on the nodes
+    mine = T[O.nearest_node(x[:, 1], vel), O.nearest_node(x[:, 0], pos)]
+    assert np.array_equal(mine, f(x[:, ::-1]))
+
+
+def test_level_set_fixture_agrees_with_the_analytic_minimum_time():
+    # the fixture's analytic value function is the double integrator's closed-form minimum time (to the origin) within
+    # one time step; the level-set solver's surface lies within its own (boundary-dominated) error of it
+    _, pos, _, d = _level_set_fixture()
+    P, V = np.meshgrid(pos, d["vel"])
+    s = np.where(P > -0.5 * V * np.abs(V), 1.0, -1.0)
+    Tstar = s * V + 2 * np.sqrt(np.maximum(0.5 * V * V + s * P, 0.0))
+    assert np.abs(Tstar - d["value_analytic"]).max() < 0.011
+    assert np.abs(d["value_level_set"] - d["value_analytic"]).mean() < 0.3
+
+
 def test_kat_are_identity():
     # examples/nonpostive-definite-neural-structures.ipynb cell 4: A=B=Q=R=I2 -> P = (1+sqrt 2) I
     _, P = O.lqr_gain(np.eye(2), np.eye(2), np.eye(2), np.eye(2))
