@@ -4,7 +4,9 @@ the HJB residual |dV/dx . (A x + B u) + l(x)|, u = -sign(dV/dx . B), l = 1[|x|^2
 [-1, 1]^2 (Adam 1e-3, shuffled minibatches of 256, 100 epochs), then the time the learned bang-bang policy needs to reach
 |x|^2 <= 1e-4 under the exact zero-order-hold step — against the analytic optimum and the saturated LQR.
 
-The notebook reports (cell 21 output): learned 2.61 +- 0.89 s, LQR 4.10 +- 1.28 s, analytic 1.57 +- 0.54 s.
+The notebook reports (cell 21 output): learned 2.61 +- 0.89 s, LQR 4.10 +- 1.28 s, level-set solver's policy
+1.62 +- 0.60 s, analytic 1.57 +- 0.54 s.  The three model-based policies run inside the rollout kernel
+(controller/lqr.py, controller/min_time.py); the learned policy is evaluated per step through the residual kernel.
 
     python examples/double_integrator_min_time.py [--epochs 100] [--batch 256]
 """
@@ -98,11 +100,38 @@ def learned_control(k, params):
 
 
 def lqr_control():
+    """Host-side saturated LQR with R = 1 (a cross-check for the tests; ``device_times`` runs the notebook's R = 0.01)."""
     import scipy.linalg
     A, B = np.array([[0.0, 1.0], [0.0, 0.0]]), np.array([[0.0], [1.0]])
     P = scipy.linalg.solve_continuous_are(A, B, np.eye(2), np.eye(1))
     K = B.T @ P
     return lambda x: np.clip(-x @ K.T, -1.0, 1.0)
+
+
+def device_times(dyn, x0, T=15.0):
+    """Saturated LQR, the analytic optimum and (when the level-set data is at hand) the level-set solver's policy, every
+    trajectory stepped by the rollout kernel with the exact zero-order-hold update (notebook cells 18-21)."""
+    import scipy.linalg
+    from q_learning_with_hjb_b200.controller.lqr import StateFeedback
+    from q_learning_with_hjb_b200.controller.min_time import GridPolicyController, SwitchingCurveController, time_to_goal
+    A, B = np.array([[0.0, 1.0], [0.0, 0.0]]), np.array([[0.0], [1.0]])
+    R = np.array([[0.01]])                                    # cell 4: the LQR the notebook compares with
+    P = scipy.linalg.solve_continuous_are(A, B, np.eye(2), R)
+    ctls = [("saturated LQR", StateFeedback(dyn, np.linalg.inv(R) @ B.T @ P, clip=True)),
+            ("analytic optimum", SwitchingCurveController(dyn, METRIC))]
+    fixture = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden",
+                           "double_integrator_level_set.npz")
+    if os.path.exists(fixture):
+        d = np.load(fixture)
+        ctls.append(("level-set solver's policy", GridPolicyController.from_value_function(dyn, d["value_level_set"], d["pos"],
+                                                                                            d["vel"])))
+    steps = int(round(T / DT))
+    out = []
+    for name, ctl in ctls:
+        res = dyn.rollout(ctl, np.asarray(x0, dtype=np.float32), steps, integrator="discrete", record_stride=1,
+                          record_controls=False)
+        out.append((name, time_to_goal(res, DT, METRIC, t_max=T)))
+    return out
 
 
 def main():
@@ -116,9 +145,9 @@ def main():
     params, losses = train(k, args.epochs, args.batch)
     print(f"trained {args.epochs} epochs in {time.time() - t0:.1f} s, final loss {losses[-1]:.5f}")
     x0 = np.random.default_rng(1).uniform(-1, 1, size=(args.trajectories, 2))
-    for name, ctl in (("learned (sin net, tcgen05 kernels)", learned_control(k, params)), ("saturated LQR", lqr_control()),
-                      ("analytic optimum", analytic_control)):
-        t = time_to_origin(ctl, x0)
+    t = time_to_origin(learned_control(k, params), x0)
+    print(f"time to origin, learned (sin net, tcgen05 kernels): {t.mean():.3f} +- {t.std():.3f} s")
+    for name, t in device_times(dyn, x0):
         print(f"time to origin, {name}: {t.mean():.3f} +- {t.std():.3f} s")
 
 

@@ -46,6 +46,11 @@ def test_double_integrator_training_reproduces_the_notebook():
     assert t_opt.mean() < t_learned.mean() < 0.75 * t_lqr.mean()
     assert abs(t_learned.mean() / t_opt.mean() - NOTEBOOK_LEARNED_TIME / NOTEBOOK_ANALYTIC_TIME) < 0.45
     assert (t_learned < 15.0).mean() > 0.97            # (almost) every trajectory reaches the origin
+    # the model-based policies of the comparison inside the rollout kernel (controller/min_time.py) against the host loop
+    dev = dict(D.device_times(dyn, x0))
+    assert abs(dev["analytic optimum"].mean() - t_opt.mean()) < 0.01 and np.abs(dev["analytic optimum"] - t_opt).max() < 0.1
+    assert t_opt.mean() < dev["level-set solver's policy"].mean() < t_learned.mean()
+    assert dev["saturated LQR"].mean() > 2.0 * t_opt.mean()          # notebook: 4.10 s against 1.57 s
 
 
 # examples/cartpole_balancing.ipynb cell 10 output, epochs 10..100: (loss, cumulated cost), all trajectories of length 200
