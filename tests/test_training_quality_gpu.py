@@ -48,7 +48,10 @@ def test_double_integrator_training_reproduces_the_notebook():
     assert (t_learned < 15.0).mean() > 0.97            # (almost) every trajectory reaches the origin
     # the model-based policies of the comparison inside the rollout kernel (controller/min_time.py) against the host loop
     dev = dict(D.device_times(dyn, x0))
-    assert abs(dev["analytic optimum"].mean() - t_opt.mean()) < 0.01 and np.abs(dev["analytic optimum"] - t_opt).max() < 0.1
+    # (the example's host loop stamps a hit with the index of the state that is inside, the notebook's cell 20 — and
+    # hjb_time_to_goal — with the step that produced it: one time step apart)
+    t_dev = dev["analytic optimum"] + D.DT
+    assert abs(t_dev.mean() - t_opt.mean()) < 0.005 and np.abs(t_dev - t_opt).max() < 0.1
     assert t_opt.mean() < dev["level-set solver's policy"].mean() < t_learned.mean()
     assert dev["saturated LQR"].mean() > 2.0 * t_opt.mean()          # notebook: 4.10 s against 1.57 s
 
