@@ -80,15 +80,23 @@ void make_dev_sys(const hjb_system* s, DevSys& d) {
       break;
     }
     case HJB_SYS_QUAD2D: {  // par = {g, m, r, I}
+      const double dt = s->dt;
       d.c[0] = p[0];
       d.c[1] = (float)(1.0 / (double)p[1]);
       d.c[2] = (float)((double)p[2] / (double)p[3]);
+      d.c[3] = (float)(dt / (double)p[1]);                       // the explicit Euler step with dt folded in (systems.cuh)
+      d.c[4] = (float)((double)p[0] * dt);
+      d.c[5] = (float)((double)p[2] * dt / (double)p[3]);
       break;
     }
     case HJB_SYS_QUAD10D: {  // par = {g, m, kT, n0}
+      const double dt = s->dt;
       d.c[0] = p[0];
       d.c[1] = (float)((double)p[2] / (double)p[1]);
       d.c[2] = p[3];
+      d.c[3] = (float)((double)p[0] * dt);
+      d.c[4] = (float)((double)p[2] * dt / (double)p[1]);
+      d.c[5] = (float)((double)p[3] * dt);
       break;
     }
   }

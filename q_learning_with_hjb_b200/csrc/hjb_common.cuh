@@ -27,8 +27,8 @@ struct DevSys {
   // derived constants, per kind (filled by api.cu::make_dev_sys):
   //  CARTPOLE c = {M11=mc+mp, kappa=mp*l, M22=mp*l^2, gamma=mp*g*l, M11*M22, 1/l, g/l}
   //  ACROBOT  c = {M11_0=I1+I2+m2*l1^2, a=m2*l1*l2/2, I2, G1=(m1*l1/2+m2*l1)*g, G12=m2*g*l2/2}
-  //  QUAD2D   c = {g, 1/m, r/I}
-  //  QUAD10D  c = {g, kT/m, n0}
+  //  QUAD2D   c = {g, 1/m, r/I,   dt/m, g dt, r dt/I}      (c[3..5]: the explicit Euler step with dt folded in)
+  //  QUAD10D  c = {g, kT/m, n0,   g dt, kT dt/m, n0 dt}
   float c[8];
   float A[16], B[8];  // LINEAR
   // internal-coordinate angle offsets (see systems.cuh): the goal angles of a FEEDBACK controller, else 0
@@ -142,6 +142,19 @@ __device__ __forceinline__ void sincos_tab(const float2* __restrict__ tab, float
   const float hr = 0.5f * r;
   s = __fmaf_rn(r, __fmaf_rn(-e.x, hr, e.y), e.x);
   c = __fmaf_rn(-r, __fmaf_rn(e.y, hr, e.x), e.y);
+}
+
+// The same evaluation from a WIDE table entry (S, C, -S/2, -C/2): the halved values come with the load (one LDS.128), so the
+// multiply by r / 2 disappears — four FFMAs, bit-identical to sincos_tab (scaling by 1/2 is exact: fma(r, -S/2, C) and
+// fma(-S, r/2, C) round the same number).  Used where the tables of all resident CTAs fit in shared memory.
+__device__ __forceinline__ void sincos_tab4(const float4* __restrict__ tab, float x, float& s, float& c) {
+  const float t = __fmaf_rn(x, (float)(1 << kTrigLog2), 12582912.f);
+  const float k = t - 12582912.f;
+  const float r = __fmaf_rn(k, -1.0f / (float)(1 << kTrigLog2), x);
+  const unsigned idx = min((unsigned)(__float_as_int(t) - (0x4B400000 - kTrigHalf)), (unsigned)(kTrigSize - 1));
+  const float4 e = tab[idx];
+  s = __fmaf_rn(r, __fmaf_rn(r, e.z, e.y), e.x);
+  c = __fmaf_rn(r, __fmaf_rn(r, e.w, -e.x), e.y);
 }
 
 template <bool FAST>

@@ -133,10 +133,14 @@ __device__ __forceinline__ void integrate(const DevSys& ps, float* x, const type
 #pragma unroll
     for (int i = 0; i < N; ++i) x[i] = d[i];
   } else if constexpr (INTEG == HJB_INT_EULER) {
-    float d[N];
-    S::xdot(ps, x, tr0, u, d);
+    if constexpr (S::kFusedEuler) {
+      S::euler(ps, x, tr0, u);          // dt folded into the system's constants (systems.cuh)
+    } else {
+      float d[N];
+      S::xdot(ps, x, tr0, u, d);
 #pragma unroll
-    for (int i = 0; i < N; ++i) x[i] = fmaf(d[i], ps.dt, x[i]);
+      for (int i = 0; i < N; ++i) x[i] = fmaf(d[i], ps.dt, x[i]);
+    }
   } else {
     const float h = ps.dt, hh = 0.5f * ps.dt;
     float k[N], acc[N], xt[N];
@@ -209,13 +213,16 @@ __device__ __forceinline__ bool inside_box(const DevBox& b, const float* z) {
 
 // (sin, cos)(k 2^-7 + aoff) in double, rounded to fp32, for the `nt` angle arguments of a system.  One copy per translation
 // unit: fp64 sincos carries a large slow path.
-static __device__ __noinline__ void build_trig_tables(float2* tab, int nt, float aoff0, float aoff1) {
+// `wide`: entries (S, C, -S/2, -C/2) as float4 (TableTrigT<true>), else (S, C) as float2.
+static __device__ __noinline__ void build_trig_tables(void* tab, bool wide, int nt, float aoff0, float aoff1) {
   for (int i = threadIdx.x; i < nt * kTrigSize; i += blockDim.x) {
     const int k = i / kTrigSize, j = i - k * kTrigSize;
     const double off = k == 2 ? (double)aoff0 + (double)aoff1 : (double)(k == 1 ? aoff1 : aoff0);
     double sv, cv;
     sincos((double)(j - kTrigHalf) * (1.0 / (double)(1 << kTrigLog2)) + off, &sv, &cv);
-    tab[i] = make_float2((float)sv, (float)cv);
+    const float sf = (float)sv, cf = (float)cv;
+    if (wide) static_cast<float4*>(tab)[i] = make_float4(sf, cf, -0.5f * sf, -0.5f * cf);
+    else static_cast<float2*>(tab)[i] = make_float2(sf, cf);
   }
 }
 
@@ -239,11 +246,18 @@ __global__ void __launch_bounds__(256) rollout_kernel(const __grid_constant__ Ro
   // fast instantiations of systems with angles: sin / cos from per-CTA tables (hjb_common.cuh::sincos_tab)
   constexpr bool kTab = S::kFast && S::NANG > 0;
   constexpr int NT = kTab ? trig_tables<S>() : 0;
-  __shared__ __align__(16) float2 trig_tab[kTab ? NT * kTrigSize : 1];
-  using TC = std::conditional_t<kTab, TableTrig, DirectTrig<S::kFast>>;
+  // wide entries (one FMA-pipe instruction less per evaluation) for the systems with ONE table (cart-pole, quad-2D: 14 KB x
+  // 8 CTAs per SM); two wide tables would not fit 8 times per SM (acrobot: 230 KB) or next to the staging buffers of the
+  // recorded variants within the 48 KB of static shared memory (10-D quadcopter)
+  // (... and only where the loop is bound by its instructions: the recorded variants are bound by their stores to HBM and
+  // lose 4-5 % with the larger shared-memory carve-out — C4 with every step recorded: 1.55e11 -> 1.48e11 env-steps/s)
+  constexpr bool kWide = kTab && NT == 1 && !REC;
+  using TabTrig = TableTrigT<kWide>;
+  __shared__ __align__(16) typename TabTrig::Entry trig_tab[kTab ? NT * kTrigSize : 1];
+  using TC = std::conditional_t<kTab, TabTrig, DirectTrig<S::kFast>>;
   TC tc;
   if constexpr (kTab) {
-    build_trig_tables(trig_tab, NT, a.sys.aoff[0], a.sys.aoff[1]);
+    build_trig_tables(trig_tab, kWide, NT, a.sys.aoff[0], a.sys.aoff[1]);
     __syncthreads();
     tc.tab = trig_tab;
   }

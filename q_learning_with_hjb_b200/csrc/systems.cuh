@@ -17,6 +17,8 @@
 // Reference formulas: dynamics/{linear,cartpole,acrobot,quadrotors}.py through the manipulator form of
 // dynamics/dynamics_basic.py:64-94, with the 2x2 M^-1 written in closed form.
 #pragma once
+#include <type_traits>
+
 #include "hjb_common.cuh"
 
 namespace hjb {
@@ -34,14 +36,18 @@ struct DirectTrig {
   template <bool GUARD = false>
   __device__ __forceinline__ float tangent(int, float z, float aoff) const { return tan_<FAST>(z + aoff); }
 };
-struct TableTrig {
+// WIDE: entries (S, C, -S/2, -C/2) — one instruction less per evaluation, twice the shared memory (rollout_kernel.cuh)
+template <bool WIDE>
+struct TableTrigT {
   // sin / cos of the acrobot's q1 + q2 from those of q1 and q2 by the addition theorems (4 FMA-pipe instructions instead of
   // a third 14-instruction table evaluation; the error of the sum of two ~7e-8 table values stays below 2e-7)
   static constexpr bool kSumByAddition = true;
-  const float2* tab;   // [tables][kTrigSize], shared memory
+  using Entry = std::conditional_t<WIDE, float4, float2>;
+  const Entry* tab;   // [tables][kTrigSize], shared memory
   template <bool GUARD = false>
   __device__ __forceinline__ void angle(int k, float z, float aoff, float& s, float& c) const {
     if (GUARD && !(fabsf(z) <= kTrigRange)) sincos_poly(z + aoff, s, c);
+    else if constexpr (WIDE) sincos_tab4(tab + k * kTrigSize, z, s, c);
     else sincos_tab(tab + k * kTrigSize, z, s, c);
   }
   template <bool GUARD = false>
@@ -85,6 +91,7 @@ template <int N_, int M_, bool FAST>
 struct LinearSys {
   static constexpr int N = N_, M = M_, NANG = 0;
   static constexpr bool kFast = FAST;
+  static constexpr bool kFusedEuler = false;
   static constexpr int KIND = HJB_SYS_LINEAR;
   static __device__ __forceinline__ constexpr int ang(int) { return 0; }
   struct Trig {};
@@ -124,6 +131,7 @@ template <bool FAST>
 struct CartpoleSys {
   static constexpr int N = 4, M = 1, NANG = 1;
   static constexpr bool kFast = FAST;
+  static constexpr bool kFusedEuler = false;
   static constexpr int KIND = HJB_SYS_CARTPOLE;
   static __device__ __forceinline__ constexpr int ang(int) { return 1; }
   struct Trig { float s, c; };
@@ -167,6 +175,7 @@ template <bool FAST>
 struct AcrobotSys {
   static constexpr int N = 4, M = 1, NANG = 2;
   static constexpr bool kFast = FAST;
+  static constexpr bool kFusedEuler = false;
   static constexpr int KIND = HJB_SYS_ACROBOT;
   static __device__ __forceinline__ constexpr int ang(int k) { return k; }
   struct Trig { float s1, c1, s2, c2, s12, c12; };
@@ -234,6 +243,7 @@ template <bool FAST>
 struct Quad2DSys {
   static constexpr int N = 6, M = 2, NANG = 1;
   static constexpr bool kFast = FAST;
+  static constexpr bool kFusedEuler = true;
   static constexpr int KIND = HJB_SYS_QUAD2D;
   static __device__ __forceinline__ constexpr int ang(int) { return 2; }
   struct Trig { float s, c; };
@@ -249,6 +259,17 @@ struct Quad2DSys {
     d[3] = -t.s * sm;
     d[4] = fmaf(t.c, sm, -p.c[0]);
     d[5] = (u[0] - u[1]) * p.c[2];
+  }
+  // x <- x + dt xdot with dt folded into the constants (c[3] = dt/m, c[4] = g dt, c[5] = r dt/I): 10 FMA-pipe instructions
+  // instead of the 12 of xdot + axpy (no separate S/m, a_x, a_z products)
+  static __device__ __forceinline__ void euler(const DevSys& p, float* x, const Trig& t, const float* u) {
+    const float sd = (u[0] + u[1]) * p.c[3];
+    x[0] = fmaf(x[3], p.dt, x[0]);
+    x[1] = fmaf(x[4], p.dt, x[1]);
+    x[2] = fmaf(x[5], p.dt, x[2]);
+    x[3] = fmaf(-t.s, sd, x[3]);
+    x[4] = fmaf(t.c, sd, x[4] - p.c[4]);
+    x[5] = fmaf(u[0] - u[1], p.c[5], x[5]);
   }
   static __device__ __forceinline__ void fg(const DevSys& p, const float* x, const Trig& t, float* f, float* g) {
     f[0] = x[3]; f[1] = x[4]; f[2] = x[5];
@@ -269,6 +290,7 @@ template <bool FAST>
 struct Quad10DSys {
   static constexpr int N = 10, M = 3, NANG = 2;
   static constexpr bool kFast = FAST;
+  static constexpr bool kFusedEuler = true;
   static constexpr int KIND = HJB_SYS_QUAD10D;
   static __device__ __forceinline__ constexpr int ang(int k) { return 3 + k; }
   struct Trig { float tx, ty; };
@@ -285,6 +307,16 @@ struct Quad10DSys {
     d[7] = fmaf(p.c[1], u[0], -p.c[0]);
     d[8] = p.c[2] * u[1];
     d[9] = p.c[2] * u[2];
+  }
+  // explicit Euler step with dt folded in (c[3] = g dt, c[4] = kT dt/m, c[5] = n0 dt): 11 instead of 15 instructions
+  static __device__ __forceinline__ void euler(const DevSys& p, float* x, const Trig& t, const float* u) {
+#pragma unroll
+    for (int i = 0; i < 5; ++i) x[i] = fmaf(x[5 + i], p.dt, x[i]);
+    x[5] = fmaf(t.tx, p.c[3], x[5]);
+    x[6] = fmaf(t.ty, p.c[3], x[6]);
+    x[7] = fmaf(u[0], p.c[4], x[7] - p.c[3]);
+    x[8] = fmaf(u[1], p.c[5], x[8]);
+    x[9] = fmaf(u[2], p.c[5], x[9]);
   }
   static __device__ __forceinline__ void fg(const DevSys& p, const float* x, const Trig& t, float* f, float* g) {
 #pragma unroll
