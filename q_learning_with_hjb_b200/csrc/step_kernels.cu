@@ -8,6 +8,20 @@
 
 namespace hjb {
 
+// One explicit Euler step in the reference's own order, x + xdot dt, then states_wrap (dynamics_basic.py:120-121).  The per-step
+// entry points (Dynamics.simulate, the learned-policy step) keep this order; the whole-horizon rollout kernel folds dt into the
+// constants of the two quadrotor systems (systems.cuh::euler: fewer instructions, the same step to a few ulps).  Data sets
+// grown by learned-policy rollouts therefore do not depend on that optimisation — a 200-epoch on-policy training is chaotic in
+// the last bit of its samples.
+template <class S>
+__device__ __forceinline__ void euler_step_plain(const DevSys& ps, float* x, const typename S::Trig& tr, const float* u) {
+  float d[S::N];
+  S::xdot(ps, x, tr, u, d);
+#pragma unroll
+  for (int i = 0; i < S::N; ++i) x[i] = fmaf(d[i], ps.dt, x[i]);
+  wrap_state<S>(x);
+}
+
 template <class S, int INTEG>
 __global__ void __launch_bounds__(256) dynamics_kernel(const __grid_constant__ DynArgs a) {
   constexpr int N = S::N, M = S::M;
@@ -37,7 +51,8 @@ __global__ void __launch_bounds__(256) dynamics_kernel(const __grid_constant__ D
   }
   if (a.x_next) {
     clip_u<S>(a.sys, u);           // simulate clips (dynamics_basic.py:118)
-    integrate<S, INTEG>(a.sys, x, tr, u, DirectTrig<S::kFast>{});
+    if constexpr (INTEG == HJB_INT_EULER) euler_step_plain<S>(a.sys, x, tr, u);
+    else integrate<S, INTEG>(a.sys, x, tr, u, DirectTrig<S::kFast>{});
     float xo[N];
     to_external<S>(a.sys, x, xo);
     store_row<N>(a.x_next, i, xo);
@@ -211,7 +226,7 @@ __global__ void __launch_bounds__(256) policy_step_kernel(const __grid_constant_
     typename S::Trig tr;
     S::trig(a.sys, x, tr);
     clip_u<S>(a.sys, u);
-    integrate<S, HJB_INT_EULER>(a.sys, x, tr, u, DirectTrig<S::kFast>{});
+    euler_step_plain<S>(a.sys, x, tr, u);
     float xo[N];
     to_external<S>(a.sys, x, xo);
     store_row<N>(a.x, i, xo);
