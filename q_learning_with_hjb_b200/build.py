@@ -54,7 +54,7 @@ def _digest(paths, extra=""):
 
 KERNEL_FAMILIES = {
     "rollout": ("hjb_common.cuh", "systems.cuh", "rollout_kernel.cuh"),
-    "vhjb": ("hjb_common.cuh", "systems.cuh", "umma.cuh", "vhjb_epilogue.cuh", "vhjb_simt.cuh", "vhjb_tc.cuh"),
+    "vhjb": ("hjb_common.cuh", "systems.cuh", "umma.cuh", "vhjb_epilogue.cuh", "vhjb_simt.cuh", "vhjb_tc.cuh", "vhjb_tc_res.cuh"),
 }
 
 
