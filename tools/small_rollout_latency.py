@@ -4,7 +4,7 @@ import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 import torch
-from tests.helpers import make_controller, make_dynamics
+from q_learning_with_hjb_b200.workloads import make_controller, make_dynamics
 from q_learning_with_hjb_b200.rollout import BatchedRollout, RunningCost
 
 for envs, T in ((4096, 500), (4096, 1), (256, 500), (65536, 500)):

@@ -9,7 +9,7 @@ import torch
 from q_learning_with_hjb_b200.configs import gin_compat as gin
 from q_learning_with_hjb_b200.configs.controller.vhjb_controller_config import VHJBControllerConfig
 from q_learning_with_hjb_b200.controller.vhjb import VHJBController
-from tests.helpers import PKG, make_dynamics
+from q_learning_with_hjb_b200.workloads import PKG, make_dynamics
 
 for kind, cfgfile in (("linear", "linear_vhjb_controller.gin"), ("cartpole", "cartpole_vhjb_controller.gin"),
                       ("quad2d", "quadrotors2DHovering_vhjb_controller.gin")):
