@@ -255,3 +255,17 @@ def test_min_time_controllers_host_side():
         GridPolicyController(dyn, np.zeros((19, 11)), pos, vel)                 # axes / table mismatch
     with pytest.raises(ValueError):
         GridPolicyController(dyn, np.zeros((3, 3)), [0.0, 1.0, 3.0], [0.0, 1.0, 2.0])   # not equally spaced
+
+
+def test_enum_values_of_the_header_match_the_ctypes_constants():
+    """include/hjb_b200.h is the contract: the controller / system kinds the Python side passes must be the header's."""
+    from q_learning_with_hjb_b200 import _lib as L
+    header = open(os.path.join(ROOT, "include", "hjb_b200.h")).read()
+    enums = {name: int(val) for name, val in re.findall(r"\b(HJB_(?:CTL|SYS|INT)_[A-Z0-9_]+)\s*=\s*(\d+)", header)}
+    want = {"HJB_CTL_FEEDBACK": L.CTL_FEEDBACK, "HJB_CTL_CARTPOLE_ES": L.CTL_CARTPOLE_ES, "HJB_CTL_ACROBOT_ES": L.CTL_ACROBOT_ES,
+            "HJB_CTL_TRACK": L.CTL_TRACK, "HJB_CTL_SWITCH_CURVE": L.CTL_SWITCH_CURVE, "HJB_CTL_GRID_SIGN": L.CTL_GRID_SIGN,
+            "HJB_SYS_LINEAR": L.SYS_LINEAR}
+    for name, value in want.items():
+        assert enums.get(name) == value, (name, enums.get(name), value)
+    for name, code in L.INTEGRATORS.items():
+        assert enums["HJB_INT_" + name.upper()] == code, name
